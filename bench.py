@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- LM bundle-adjustment throughput on synthetic BAL-shaped problems.
+
+A "step" is one LM trial step (one trip of bundle_euclid.m:139-241: residuals + finite-
+difference Jacobians + U/V/W, damping, V*^-1, Schur complement / PCG solve, back-substitution,
+new residual, accept/reject) over one synthetic problem.  Under N ranks the scene is sharded by
+point: every rank holds all cameras and `n` points of its own (weak scaling), the per-camera
+sums travel through NCCL all-reduce.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config venice] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = observations processed per second through whole LM
+trial steps, all ranks together, inputs resident in HBM; `e2e` = the same through the
+host-buffer C-ABI call (H2D of a, b, observations and D2H of a_new, b_new inside the timing).
+`--impl reference` times the CPU arm (oracle/: the reference's algorithm as a sparse OpenMP
+port, since the reference's dense n x m arrays cannot hold these sizes).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LM trial-step throughput (Jacobian + Schur + solve + update), observations/s"
+UNIT = "obs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="venice")
+    ap.add_argument("--scale", type=float, default=1.0, help="scale points/observations per rank")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--solver", default="auto", choices=["auto", "chol", "pcg"])
+    ap.add_argument("--pcg-rtol", type=float, default=1e-10)
+    ap.add_argument("--rtable", default="host", choices=["host", "device"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 8:
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_shard(args, rank):
+    from bundleadjustmentmatlab_b200 import synth
+    P = synth.make_config(args.config, seed=args.seed, scale=args.scale, point_seed=rank)
+    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T)
+    b = np.ascontiguousarray(P.Xe[:3].T)
+    return P, a, b
+
+
+def workload_name(args, P, world):
+    return (f"{args.config}-shaped synthetic BA, per rank: {P.m} cameras (shared), {P.n} points, {P.nobs} observations; "
+            f"{world} rank(s), point-sharded")
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle): bounded sample = whole LM trial steps on one rank's shard
+# ------------------------------------------------------------------------------------------
+def cpu_trial_steps(args, P, a, b, steps, warmup):
+    from oracle import lm
+    lib = lm.sparse_lib()
+    if args.cpu_threads > 0:
+        lib.orc_set_num_threads(args.cpu_threads)
+    cores = int(lib.orc_num_threads())
+    obs = lm.ObsList(P.m, P.n, P.obs_xy, P.obs_pt, P.obs_cam)
+    aa, bb, lam = a.T.copy(), b.T.copy(), 1e-3
+    times, iters = [], []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = lm.trial_step_pcg(P.K, aa, bb, obs, lam, pcg_rtol=args.pcg_rtol, pcg_max_iter=1000)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt); iters.append(r["pcg_iters"])
+        if r["old"] - r["new"] > 0:
+            rho = (r["old"] - r["new"]) / r["denom"]
+            aa, bb = r["a_new"], r["b_new"]
+            lam = lam * max(1.0 / 3.0, 1 - (2 * rho - 1) ** 3)
+        else:
+            lam = lam * 2
+    return times, iters, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    P, a, b = make_shard(args, 0)
+    times, iters, cores = cpu_trial_steps(args, P, a, b, args.steps, args.warmup)
+    total = sum(times)
+    val = P.nobs * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, P, 1), "solver": "pcg (block-Jacobi, implicit Schur)",
+                   "pcg_rtol": args.pcg_rtol, "pcg_iters_mean": float(np.mean(iters))},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} whole LM trial steps on one rank's shard ({P.nobs} observations), "
+                                   "oracle/oracle_sparse.c orc_trial_step_pcg (OpenMP); the reference's dense n x m "
+                                   "arrays cannot hold this size"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lm_iters_per_sec": len(times) / total,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, P, na=6):
+    """ALGORITHMIC bytes per launch of each kernel group."""
+    no, n, m = P.nobs, P.n, P.m
+    W = 3 * na * 8
+    table = {
+        # read (u,v)+point id, write W; per point b; per camera table/a/K in, partial U/eA out
+        "stage1_cam": no * (16 + 4 + W) + n * 24 + m * (288 + 8 * na + 32 + 8 * (na * (na + 1) // 2 + na)),
+        # read (u,v)+camera id; per point b in, V + eB + cost out
+        "stage1_pt": no * (16 + 4) + n * (24 + 72 + 24 + 8) + m * (72 + 8 * na + 32),
+        "pcg_sweep_pt": no * (W + 4 + 4) + n * (72 + 24 + 4) + m * 8 * na,
+        "pcg_sweep_cam": no * (W + 4) + n * 24 + m * 8 * na,
+        "schur": no * (W + 4) + n * (72 + 24) + m * 8 * (na * (na + 1) // 2 + na),
+        "stage3": no * (W + 4 + 4 + 16 + 4 + 4 + 8) + n * (72 + 24 + 24 + 24 + 24 + 8) + m * (72 + 8 * na + 32),
+        "vinv": n * (72 + 72) + m * 2 * 8 * na * na,
+    }
+    return table.get(name)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bundleadjustmentmatlab_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    P, a0, b0 = make_shard(args, rank)
+    solver = {"auto": capi.SOLVER_AUTO, "chol": capi.SOLVER_CHOL, "pcg": capi.SOLVER_PCG}[args.solver]
+    rtable = capi.RTABLE_HOST_LIBM if args.rtable == "host" else capi.RTABLE_DEVICE
+    ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=args.pcg_rtol, rtable=rtable, device=local)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.Context.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.set_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    ctx.set_problem_sparse(P.K.T, a0, b0, P.obs_xy, P.obs_pt, P.obs_cam)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm
+    infos = []
+    for _ in range(args.warmup):
+        ctx.trial_step()
+    barrier()
+    ctx.reset_timers(True)
+    l0 = ctx.kernel_launches
+    with ClockSampler(local) as clk:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            infos.append(ctx.trial_step())
+        ms = ctx.timer_stop()
+        barrier()
+    launches = ctx.kernel_launches - l0
+    groups = {}
+    for g in ("stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt", "pcg_sweep_cam", "stage3"):
+        avg, cnt = ctx.kernel_time(g)
+        groups[g] = {"avg_ms": avg, "count": cnt, "total_ms": avg * cnt}
+    ctx.reset_timers(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    nobs_all = torch.tensor([float(P.nobs)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nobs_all)
+    nobs_total = float(nobs_all.item())
+    value = nobs_total * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end arm: host buffers through the C ABI, LM control on the host
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+        ha, hb, hxy = pin(a0.shape), pin(b0.shape), pin(P.obs_xy.shape)
+        ha_new, hb_new = pin(a0.shape), pin(b0.shape)
+        ha[:] = a0; hb[:] = b0; hxy[:] = P.obs_xy
+        lam = 1e-3
+
+        def one():
+            nonlocal lam
+            info = ctx.trial_step_host(ha, hb, hxy, lam, ha_new, hb_new)
+            if info["accepted"]:
+                ha[:] = ha_new; hb[:] = hb_new
+                lam = lam * max(1.0 / 3.0, 1 - (2 * info["rho"] - 1) ** 3)
+            else:
+                lam = lam * 2
+        for _ in range(args.warmup):
+            one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = (ha.nbytes + hb.nbytes + hxy.nbytes) * 1
+        d2h = ha_new.nbytes + hb_new.nbytes + 64
+        e2e = {"value": nobs_total * args.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / args.steps}
+
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        dom = max((g for g in groups if algorithmic_bytes(g, P) and groups[g]["count"] > 0),
+                  key=lambda g: groups[g]["total_ms"], default=None)
+        roof = None
+        if dom:
+            ab = algorithmic_bytes(dom, P)
+            ach = ab / (groups[dom]["avg_ms"] * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get(args.config, {}).get(dom)
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": groups[dom]["avg_ms"],
+                    "launches": groups[dom]["count"], "peak_source": peak_kind,
+                    "share_of_step": groups[dom]["total_ms"] / (ms * 1.0)}
+        per_kernel = {}
+        for g, v in groups.items():
+            if v["count"]:
+                ab = algorithmic_bytes(g, P)
+                per_kernel[g] = {"avg_ms": round(v["avg_ms"], 5), "count": v["count"],
+                                 "GBps": (ab / (v["avg_ms"] * 1e-3) / 1e9) if ab else None}
+        js = sum(groups[g]["total_ms"] for g in ("stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "pcg_sweep_pt", "pcg_sweep_cam"))
+        cpu = None
+        if not args.no_cpu_baseline:
+            times, iters, cores = cpu_trial_steps(args, P, a0, b0, 1, 0)
+            cpu = {"value": P.nobs * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"1 whole LM trial step on rank 0's shard ({P.nobs} observations, {iters[0]} PCG iterations, "
+                             f"{sum(times):.1f} s): oracle/oracle_sparse.c orc_trial_step_pcg with OpenMP"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, P, world), "num_a": 6,
+                       "solver": "cholesky" if infos[-1]["solver_used"] == capi.SOLVER_CHOL else "pcg (block-Jacobi, implicit Schur)",
+                       "pcg_rtol": args.pcg_rtol, "rtable": args.rtable,
+                       "l2": "inputs larger than L2 (W alone is %.0f MB per rank)" % (P.nobs * 144 / 1e6)},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu,
+            "lm_iters_per_sec": args.steps / (ms_max * 1e-3),
+            "jacobian_schur_obs_per_sec": (nobs_total * args.steps / (js * 1e-3)) if js > 0 else None,
+            "pcg_iters_mean": float(np.mean([i["pcg_iters"] for i in infos])),
+            "accepted_steps": int(sum(i["accepted"] for i in infos)),
+            "cost_first_last": [infos[0]["old_cost"], infos[-1]["new_cost"]],
+            "kernels": per_kernel,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""Host-side mirror of the reference's operator interface for the BA hot path.
+
+``bundle_euclid(K, Te, w, Xe, x, *options)`` has the same name, argument meaning, option
+strings and outputs as ``toolbox/bundle/bundle_euclid.m:1-26`` of the reference; it only
+packs the arguments (bundle_euclid.m:81-102) and calls the C ABI (libvlgba.so), where the
+whole LM loop (bundle_euclid.m:111-267) runs on the GPU.  The three mex stages are exposed
+under their reference names for stage-level drop-in and parity tests.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+
+def parse_options(m, n, x, opts):
+    """bundle_euclid.m:43-79 (same option strings, same defaults)."""
+    o = dict(fix_structure=False, fix_motion=False, pivot=None, num_variableK=4, visible=None, verbose=False)
+    opts = list(opts)
+    k = 0
+    while k < len(opts):
+        key = str(opts[k]).lower()
+        if key == "fix_structure":
+            o["fix_structure"] = True
+        elif key == "fix_motion":
+            o["fix_motion"] = True
+        elif key == "fix_pivot":
+            o["pivot"] = np.asarray(opts[k + 1]).astype(bool).reshape(-1)
+            k += 1
+        elif key == "fix_calibration":
+            o["num_variableK"] = 0
+        elif key == "fix_principal":
+            o["num_variableK"] = 1
+        elif key == "visibility":
+            o["visible"] = np.asarray(opts[k + 1])
+            k += 1
+        elif key == "verbose":
+            o["verbose"] = True
+        k += 1
+    if o["visible"] is None:
+        o["visible"] = ((x[0] != 0) | (x[1] != 0)).reshape(n, m)      # bundle_euclid.m:50
+    return o
+
+
+def pack(K, Te, w, Xe, num_variableK):
+    """a = [w; Te; K-part], b = Xe(1:3,:)  (bundle_euclid.m:89-99), returned in wire layout."""
+    m = w.shape[1]
+    a = np.zeros((m, 6 + num_variableK))
+    a[:, 0:3] = w.T
+    a[:, 3:6] = Te.T
+    if num_variableK == 1:
+        a[:, 6] = K[0]
+    elif num_variableK == 4:
+        a[:, 6:10] = K.T
+    b = np.ascontiguousarray(Xe[0:3].T)
+    return a, b
+
+
+def make_context(K, Te, w, Xe, x, *options, **ctx_opts) -> capi.Context:
+    K = np.asarray(K, dtype=np.float64); Te = np.asarray(Te, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64); Xe = np.asarray(Xe, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    m, n = w.shape[1], x.shape[1]
+    o = parse_options(m, n, x, options)
+    ctx = capi.Context(num_variableK=o["num_variableK"], fix_structure=int(o["fix_structure"]),
+                       fix_motion=int(o["fix_motion"]), verbose=int(o["verbose"]), **ctx_opts)
+    a, b = pack(K, Te, w, Xe, o["num_variableK"])
+    vis = np.asfortranarray(np.asarray(o["visible"], dtype=np.float64).reshape(n, m))
+    ctx.set_problem_dense(np.ascontiguousarray(K.T), a, b, np.asfortranarray(x[0:2]), vis, pivot=o["pivot"])
+    return ctx
+
+
+def bundle_euclid(K, Te, w, Xe, x, *options, **ctx_opts):
+    """[K_ Te_ w_ Xe_ error_] = bundle_euclid(K, Te, w, Xe, x, ...)  -- bundle_euclid.m:1-26."""
+    Xe = np.asarray(Xe, dtype=np.float64)
+    ctx = make_context(K, Te, w, Xe, x, *options, **ctx_opts)
+    try:
+        K_, Te_, w_, Xe_, err = ctx.solve(Xe4=Xe[3])
+    finally:
+        ctx.close()
+    return K_.T.copy(), Te_.T.copy(), w_.T.copy(), Xe_.T.copy(), err
+
+
+def bundle_euclid_sparse(K, Te, w, Xe, obs_xy, obs_pt, obs_cam, *options, **ctx_opts):
+    """Same solve on an observation list (no dense n x m arrays): SURVEY.md row N1."""
+    K = np.asarray(K, dtype=np.float64); Xe = np.asarray(Xe, dtype=np.float64)
+    m, n = np.asarray(w).shape[1], Xe.shape[1]
+    o = parse_options(m, n, np.ones((2, 1, 1)), list(options) + ["visibility", np.zeros((0,))])
+    ctx = capi.Context(num_variableK=o["num_variableK"], fix_structure=int(o["fix_structure"]),
+                       fix_motion=int(o["fix_motion"]), verbose=int(o["verbose"]), **ctx_opts)
+    try:
+        a, b = pack(K, np.asarray(Te, dtype=np.float64), np.asarray(w, dtype=np.float64), Xe, o["num_variableK"])
+        ctx.set_problem_sparse(np.ascontiguousarray(K.T), a, b, obs_xy, obs_pt, obs_cam, pivot=o["pivot"])
+        K_, Te_, w_, Xe_, err = ctx.solve(Xe4=Xe[3])
+    finally:
+        ctx.close()
+    return K_.T.copy(), Te_.T.copy(), w_.T.copy(), Xe_.T.copy(), err

@@ -1,0 +1,857 @@
+// ba_kernels.cuh -- CUDA kernels (sm_100a, FP64) of the LM bundle-adjustment hot path.
+//
+// Data layout in HBM.  Observations are kept in the reference's own
+// traversal order (ascending i + n*j, camera-major: mex_bundle_1_XABeUVWeAeB.c:192-196),
+// called C-order: a camera's observations are one contiguous segment, so everything that
+// depends on the camera (rotation tables, a_j, K_j) is warp-uniform in the heavy kernels.
+// A second, point-major view (P-order: pt_ptr/pt_obs/pt_cam/pt_xy) serves the point-keyed
+// sums; pt_obs maps a P-order slot to its C-order position.
+//   W      [nobs][3][NA]   C-order, column-major NA x 3 block per observation
+//   U,Ud   [m][NA][NA]     eA,e_,da [m][NA]     V,Vinv [n][3][3]   eB,db,t [n][3]
+//   rtab   [m][4][9]       rotation matrices: base, w0+h, w1+h, w2+h
+#pragma once
+#include "ba_math.cuh"
+#include <stdint.h>
+
+namespace vlgba {
+
+constexpr int kWarpsPerBlock = 4;
+
+__host__ __device__ constexpr int nu_of(int na) { return na * (na + 1) / 2 + na; }
+
+struct Stage1Args {
+    int m, n, nchunks;
+    const double2* obs_xy;      // C-order
+    const int* obs_pt;          // C-order
+    const int* chunk_cam;
+    const int* chunk_begin;
+    const int* chunk_end;
+    const double* K4;
+    const double* a;
+    const double* b;
+    const double* rtab;
+    const unsigned char* cam_fixed;
+    int fix_structure;
+    double* W;
+    double* Upart;              // [nchunks][NU]
+    // diagnostics (NULL in production)
+    double* dX_hat; double* dA; double* dB; double* de;
+};
+
+// ---------------------------------------------------------------------------------------
+// stage 1, camera pass ("resid_jac_normal"): one warp per chunk of one camera's segment.
+// Per observation: X_hat, A, B, e (bit-exact, ba_math.cuh), W_ij = A'B written through a
+// shared-memory tile so that the global stores are contiguous, and the NU = NA(NA+1)/2 + NA
+// distinct entries of A'A and A'e staged in shared memory and accumulated by lane r in
+// ascending observation order -- the reference's order (mex_bundle_1_XABeUVWeAeB.c:281-290,
+// :317-323).  One partial per chunk; k_stage1_cam_finalize adds the chunks of a camera in
+// order.  With one chunk per camera (VLG_BA_ORDER_REFERENCE) U and eA are bit-identical to
+// the reference.
+// ---------------------------------------------------------------------------------------
+template <int NA, bool DIAG>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_stage1_cam(Stage1Args p)
+{
+    constexpr int NU = nu_of(NA);
+    constexpr int NW = 3 * NA;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* my = smem + (size_t)warp * (36 + NA + 4 + 32 * NU + 32 * NW);
+    double* camR = my;                 // 36
+    double* cama = my + 36;            // NA
+    double* camK = my + 36 + NA;       // 4
+    double* ust = my + 36 + NA + 4;    // 32 x NU
+    double* wst = ust + 32 * NU;       // 32 x NW
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= p.nchunks) return;
+    const int j = p.chunk_cam[c];
+    const int beg = p.chunk_begin[c], end = p.chunk_end[c];
+    for (int t = lane; t < 36; t += 32) camR[t] = p.rtab[(size_t)36 * j + t];
+    if (lane < NA) cama[lane] = p.a[(size_t)NA * j + lane];
+    if (lane < 4) camK[lane] = p.K4[(size_t)4 * j + lane];
+    __syncwarp();
+    double fx, fy, cx, cy;
+    effective_K<NA>(camK, cama, fx, fy, cx, cy);
+    const bool zeroW = p.fix_structure || p.cam_fixed[j];
+
+    constexpr int NACC = (NU + 31) / 32;
+    double acc[NACC];
+#pragma unroll
+    for (int t = 0; t < NACC; t++) acc[t] = 0.0;
+
+    for (int base = beg; base < end; base += 32) {
+        const int o = base + lane;
+        const int cnt = min(32, end - base);
+        if (o < end) {
+            const double2 xy = p.obs_xy[o];
+            const int i = p.obs_pt[o];
+            const double b0 = p.b[(size_t)3 * i], b1 = p.b[(size_t)3 * i + 1], b2 = p.b[(size_t)3 * i + 2];
+            double X0[2], A[2 * NA], B[6], e[2];
+            obs_jacobian<NA>(camR, cama, fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
+            if (DIAG) {
+                if (p.dX_hat) { p.dX_hat[(size_t)2 * o] = X0[0]; p.dX_hat[(size_t)2 * o + 1] = X0[1]; }
+                if (p.dA) for (int k = 0; k < 2 * NA; k++) p.dA[(size_t)2 * NA * o + k] = A[k];
+                if (p.dB) for (int k = 0; k < 6; k++) p.dB[(size_t)6 * o + k] = B[k];
+                if (p.de) { p.de[(size_t)2 * o] = e[0]; p.de[(size_t)2 * o + 1] = e[1]; }
+            }
+            // W(:,:,i,j) = A'B (mex_bundle_1_XABeUVWeAeB.c:305-314)
+#pragma unroll
+            for (int col = 0; col < 3; col++)
+#pragma unroll
+                for (int row = 0; row < NA; row++)
+                    wst[lane * NW + row + NA * col] =
+                        zeroW ? 0.0 : dot2(A[2 * row], A[2 * row + 1], B[2 * col], B[2 * col + 1]);
+            // upper triangle of A'A, then A'e
+#pragma unroll
+            for (int col = 0; col < NA; col++)
+#pragma unroll
+                for (int row = 0; row <= col; row++)
+                    ust[lane * NU + col * (col + 1) / 2 + row] =
+                        dot2(A[2 * row], A[2 * row + 1], A[2 * col], A[2 * col + 1]);
+#pragma unroll
+            for (int row = 0; row < NA; row++)
+                ust[lane * NU + NA * (NA + 1) / 2 + row] = dot2(A[2 * row], A[2 * row + 1], e[0], e[1]);
+        }
+        __syncwarp();
+        // contiguous store of the W tile
+        {
+            double* Wg = p.W + (size_t)NW * base;
+            const int tot = cnt * NW;
+            for (int t = lane; t < tot; t += 32) Wg[t] = wst[t];
+        }
+        // in-order accumulation: lane r owns entry r (and r+32, r+64 for NA = 10)
+#pragma unroll
+        for (int t = 0; t < NACC; t++) {
+            const int r = lane + 32 * t;
+            if (r < NU) {
+                double s = acc[t];
+                for (int k = 0; k < cnt; k++) s = VLG_P(s, ust[k * NU + r]);
+                acc[t] = s;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int t = 0; t < NACC; t++) {
+        const int r = lane + 32 * t;
+        if (r < NU) p.Upart[(size_t)NU * c + r] = acc[t];
+    }
+}
+
+// U_j, eA_j = sum of the camera's chunk partials in chunk order; fix_motion / fix_pivot
+// cameras are zeroed here (bundle_euclid.m:145-154).  One thread per (camera, entry).
+template <int NA>
+__global__ void k_stage1_cam_finalize(int m, const int* __restrict__ cam_chunk_ptr,
+                                      const double* __restrict__ Upart,
+                                      const unsigned char* __restrict__ cam_fixed,
+                                      double* __restrict__ U, double* __restrict__ eA)
+{
+    constexpr int NU = nu_of(NA);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * NU) return;
+    const int j = t / NU, r = t % NU;
+    double s = 0.0;
+    const int c0 = cam_chunk_ptr[j], c1 = cam_chunk_ptr[j + 1];
+    if (c1 > c0) {
+        s = Upart[(size_t)NU * c0 + r];
+        for (int c = c0 + 1; c < c1; c++) s = VLG_P(s, Upart[(size_t)NU * c + r]);
+    }
+    if (cam_fixed[j]) s = 0.0;
+    if (r < NA * (NA + 1) / 2) {
+        int col = 0;
+        while ((col + 1) * (col + 2) / 2 <= r) col++;
+        const int row = r - col * (col + 1) / 2;
+        U[(size_t)NA * NA * j + row + NA * col] = s;
+        U[(size_t)NA * NA * j + col + NA * row] = s;
+    } else {
+        eA[(size_t)NA * j + (r - NA * (NA + 1) / 2)] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 1, point pass: one thread per point walks its track in ascending camera order
+// (the reference's order for V_i and eB_i, mex_bundle_1_XABeUVWeAeB.c:293-302,:326-332),
+// recomputes B and e (4 of the 10 reprojections, bit-identical to the camera pass) and
+// writes V_i, eB_i and the point's share of the cost e'e (bundle_euclid.m:209).
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__global__ void k_stage1_pt(int n, const int* __restrict__ pt_ptr, const int* __restrict__ pt_cam,
+                            const double2* __restrict__ pt_xy, const double* __restrict__ K4,
+                            const double* __restrict__ a, const double* __restrict__ b,
+                            const double* __restrict__ rtab, int fix_structure,
+                            double* __restrict__ V, double* __restrict__ eB, double* __restrict__ cost_pt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double b0 = b[(size_t)3 * i], b1 = b[(size_t)3 * i + 1], b2 = b[(size_t)3 * i + 2];
+    double v00 = 0, v10 = 0, v20 = 0, v11 = 0, v21 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
+    const int q0 = pt_ptr[i], q1 = pt_ptr[i + 1];
+    for (int q = q0; q < q1; q++) {
+        const int j = pt_cam[q];
+        const double2 xy = pt_xy[q];
+        const double* R = rtab + (size_t)36 * j;
+        const double* aj = a + (size_t)NA * j;
+        double Rl[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rl[k] = __ldg(R + k);
+        double al[NA];
+#pragma unroll
+        for (int k = 3; k < NA; k++) al[k] = __ldg(aj + k);
+        double fx, fy, cx, cy;
+        double Kl[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
+        effective_K<NA>(Kl, al, fx, fy, cx, cy);
+        double B[6], e[2];
+        obs_point_jacobian(Rl, al[3], al[4], al[5], fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, B, e);
+        v00 = VLG_P(v00, dot2(B[0], B[1], B[0], B[1]));
+        v10 = VLG_P(v10, dot2(B[2], B[3], B[0], B[1]));
+        v20 = VLG_P(v20, dot2(B[4], B[5], B[0], B[1]));
+        v11 = VLG_P(v11, dot2(B[2], B[3], B[2], B[3]));
+        v21 = VLG_P(v21, dot2(B[4], B[5], B[2], B[3]));
+        v22 = VLG_P(v22, dot2(B[4], B[5], B[4], B[5]));
+        g0 = VLG_P(g0, dot2(B[0], B[1], e[0], e[1]));
+        g1 = VLG_P(g1, dot2(B[2], B[3], e[0], e[1]));
+        g2 = VLG_P(g2, dot2(B[4], B[5], e[0], e[1]));
+        cost += e[0] * e[0] + e[1] * e[1];
+    }
+    if (fix_structure) { v00 = v10 = v20 = v11 = v21 = v22 = 0.0; g0 = g1 = g2 = 0.0; }   // bundle_euclid.m:140-144
+    double* Vi = V + (size_t)9 * i;
+    Vi[0] = v00; Vi[1] = v10; Vi[2] = v20;
+    Vi[3] = v10; Vi[4] = v11; Vi[5] = v21;
+    Vi[6] = v20; Vi[7] = v21; Vi[8] = v22;
+    eB[(size_t)3 * i] = g0; eB[(size_t)3 * i + 1] = g1; eB[(size_t)3 * i + 2] = g2;
+    cost_pt[i] = cost;
+}
+
+// ---------------------------------------------------------------------------------------
+// deterministic sum of a long vector: fixed-shape two-level tree (grid of kRedBlocks CTAs,
+// then one CTA).  out[slot] = sum(in[0..n)).
+// ---------------------------------------------------------------------------------------
+constexpr int kRedBlocks = 296;
+constexpr int kRedThreads = 256;
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh)
+{
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_reduce_partial(const double* __restrict__ in, size_t n,
+                                                                double* __restrict__ part)
+{
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (size_t t = (size_t)blockIdx.x * kRedThreads + threadIdx.x; t < n; t += (size_t)kRedBlocks * kRedThreads)
+        v += in[t];
+    v = block_sum_256(v, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_reduce_final(const double* __restrict__ part, int nparts,
+                                                              double* __restrict__ out)
+{
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int t = threadIdx.x; t < nparts; t += kRedThreads) v += part[t];
+    v = block_sum_256(v, sh);
+    if (threadIdx.x == 0) *out = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// damping (bundle_euclid.m:162-173) and V*^-1 = pinv(V*) (bundle_euclid.m:178-181)
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__global__ void k_damp_U(int m, double lambda, const double* __restrict__ U, double* __restrict__ Ud)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * NA * NA) return;
+    const int r = t % (NA * NA);
+    const double u = U[t];
+    Ud[t] = (r % NA == r / NA) ? (1 + lambda) * u : u;
+}
+
+__global__ void k_vinv_damp(int n, double lambda, const double* __restrict__ V, double* __restrict__ Vinv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double Vd[9], Vi[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Vd[k] = V[(size_t)9 * i + k];
+    Vd[0] = (1 + lambda) * Vd[0]; Vd[4] = (1 + lambda) * Vd[4]; Vd[8] = (1 + lambda) * Vd[8];
+    sym_pinv<3>(Vd, Vi);
+#pragma unroll
+    for (int k = 0; k < 9; k++) Vinv[(size_t)9 * i + k] = Vi[k];
+}
+
+// ---------------------------------------------------------------------------------------
+// camera-keyed Schur pieces: e_j = eA_j - sum_i Y_ij eB_i (mex_bundle_2_Se_.c:132-155) and
+// the diagonal blocks S_jj = U*_j - sum_i Y_ij W_ij' (mex_bundle_2_Se_.c:80-118 with k = j),
+// Y_ij = W_ij V*_i^-1 formed on the fly (bundle_euclid.m:182-184; Y is never stored).
+// One warp per chunk, fixed xor-tree over lanes, chunk partials added in order.
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_cam_schur_diag(int nchunks, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_end,
+                 const int* __restrict__ obs_pt, const double* __restrict__ W, const double* __restrict__ Vinv,
+                 const double* __restrict__ eB, double* __restrict__ part /* [nchunks][NU] */)
+{
+    constexpr int NU = nu_of(NA);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= nchunks) return;
+    const int beg = chunk_begin[c], end = chunk_end[c];
+    double acc[NU];
+#pragma unroll
+    for (int t = 0; t < NU; t++) acc[t] = 0.0;
+    for (int o = beg + lane; o < end; o += 32) {
+        const int i = obs_pt[o];
+        double Wo[3 * NA], Vi[9], g[3], Y[3 * NA];
+        const double* Wg = W + (size_t)3 * NA * o;
+#pragma unroll
+        for (int k = 0; k < 3 * NA; k++) Wo[k] = Wg[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Vi[k] = __ldg(Vinv + (size_t)9 * i + k);
+#pragma unroll
+        for (int k = 0; k < 3; k++) g[k] = __ldg(eB + (size_t)3 * i + k);
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+            for (int r = 0; r < NA; r++)
+                Y[r + NA * cc] = Wo[r] * Vi[3 * cc] + Wo[r + NA] * Vi[1 + 3 * cc] + Wo[r + 2 * NA] * Vi[2 + 3 * cc];
+#pragma unroll
+        for (int col = 0; col < NA; col++)
+#pragma unroll
+            for (int row = 0; row <= col; row++)
+                acc[col * (col + 1) / 2 + row] +=
+                    Y[row] * Wo[col] + Y[row + NA] * Wo[col + NA] + Y[row + 2 * NA] * Wo[col + 2 * NA];
+#pragma unroll
+        for (int r = 0; r < NA; r++)
+            acc[NA * (NA + 1) / 2 + r] += Y[r] * g[0] + Y[r + NA] * g[1] + Y[r + 2 * NA] * g[2];
+    }
+#pragma unroll
+    for (int t = 0; t < NU; t++) {
+        double v = warp_sum(acc[t]);
+        if (lane == (t & 31)) part[(size_t)NU * c + t] = v;
+    }
+}
+
+// per-camera sum of chunk partials in chunk order: out[j][r] = sum_c part[c][r], r < nv
+__global__ void k_cam_sum_partials(int m, int nv, const int* __restrict__ cam_chunk_ptr, const double* __restrict__ part,
+                                   const int* __restrict__ done, double* __restrict__ out)
+{
+    if (done && *done) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * nv) return;
+    const int j = t / nv, r = t % nv;
+    double s = 0.0;
+    for (int c = cam_chunk_ptr[j]; c < cam_chunk_ptr[j + 1]; c++) s += part[(size_t)nv * c + r];
+    out[t] = s;
+}
+
+// S_jj = U*_j - sums (full NA x NA, symmetric), e_j = eA_j - sums, and optionally the
+// block-Jacobi preconditioner M_j^-1 = pinv(S_jj).  sums = [m][NU] (all-reduced over ranks).
+template <int NA>
+__global__ void k_cam_schur_finalize(int m, const double* __restrict__ sums, const double* __restrict__ Ud,
+                                     const double* __restrict__ eA, double* __restrict__ Sjj,
+                                     double* __restrict__ ebar, double* __restrict__ Minv)
+{
+    constexpr int NU = nu_of(NA);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const double* s = sums + (size_t)NU * j;
+    double M[NA * NA];
+#pragma unroll
+    for (int col = 0; col < NA; col++)
+#pragma unroll
+        for (int row = 0; row <= col; row++) {
+            const double v = Ud[(size_t)NA * NA * j + row + NA * col] - s[col * (col + 1) / 2 + row];
+            M[row + NA * col] = v;
+            M[col + NA * row] = v;
+        }
+#pragma unroll
+    for (int r = 0; r < NA; r++) ebar[(size_t)NA * j + r] = eA[(size_t)NA * j + r] - s[NA * (NA + 1) / 2 + r];
+    if (Sjj)
+#pragma unroll
+        for (int k = 0; k < NA * NA; k++) Sjj[(size_t)NA * NA * j + k] = M[k];
+    if (Minv) {
+        double Mi[NA * NA];
+        sym_pinv<NA>(M, Mi);
+#pragma unroll
+        for (int k = 0; k < NA * NA; k++) Minv[(size_t)NA * NA * j + k] = Mi[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// explicit Schur complement, block-sparse: one warp per structurally non-zero block (j,k),
+// j <= k, walking the precomputed list of (observation of j, observation of k) pairs that
+// share a point, ascending point index (mex_bundle_2_Se_.c:103-118 restricted to the terms
+// that are not exactly zero).  Writes S_jk and its mirror S_kj = S_jk' into the dense S.
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_schur_blocks(int nblocks, int N, int add_U, const int* __restrict__ blk_j, const int* __restrict__ blk_k,
+               const int64_t* __restrict__ blk_ptr, const int2* __restrict__ pairs,
+               const int* __restrict__ obs_pt, const double* __restrict__ W, const double* __restrict__ Vinv,
+               const double* __restrict__ Ud, double* __restrict__ S)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bidx = blockIdx.x * kWarpsPerBlock + warp;
+    if (bidx >= nblocks) return;
+    const int j = blk_j[bidx], k = blk_k[bidx];
+    double acc[NA * NA];
+#pragma unroll
+    for (int t = 0; t < NA * NA; t++) acc[t] = 0.0;
+    for (int64_t q = blk_ptr[bidx] + lane; q < blk_ptr[bidx + 1]; q += 32) {
+        const int2 pr = pairs[q];
+        const int i = obs_pt[pr.x];
+        double Wj[3 * NA], Wk[3 * NA], Vi[9], Y[3 * NA];
+#pragma unroll
+        for (int t = 0; t < 3 * NA; t++) Wj[t] = W[(size_t)3 * NA * pr.x + t];
+#pragma unroll
+        for (int t = 0; t < 3 * NA; t++) Wk[t] = W[(size_t)3 * NA * pr.y + t];
+#pragma unroll
+        for (int t = 0; t < 9; t++) Vi[t] = __ldg(Vinv + (size_t)9 * i + t);
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+            for (int r = 0; r < NA; r++)
+                Y[r + NA * cc] = Wj[r] * Vi[3 * cc] + Wj[r + NA] * Vi[1 + 3 * cc] + Wj[r + 2 * NA] * Vi[2 + 3 * cc];
+#pragma unroll
+        for (int col = 0; col < NA; col++)
+#pragma unroll
+            for (int row = 0; row < NA; row++)
+                acc[row + NA * col] += Y[row] * Wk[col] + Y[row + NA] * Wk[col + NA] + Y[row + 2 * NA] * Wk[col + 2 * NA];
+    }
+    double mine[(NA * NA + 31) / 32];
+#pragma unroll
+    for (int t = 0; t < NA * NA; t++) {
+        const double v = warp_sum(acc[t]);
+        if (lane == (t & 31)) mine[t >> 5] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < (NA * NA + 31) / 32; u++) {
+        const int t = lane + 32 * u;
+        if (t < NA * NA) {
+            const int row = t % NA, col = t / NA;
+            double v = -mine[u];
+            if (j == k && add_U) v += Ud[(size_t)NA * NA * j + t];
+            S[(size_t)(NA * j + row) + (size_t)N * (NA * k + col)] = v;
+            if (j != k) S[(size_t)(NA * k + col) + (size_t)N * (NA * j + row)] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// dense blocked Cholesky of S (lower triangle, column-major, leading dimension ld, order
+// Np = multiple of 32), right-looking, 32-wide panels, with elimination of non-positive
+// pivots (pinv semantics for the exactly-zero rows/columns of S: bundle_euclid.m:193).
+// ---------------------------------------------------------------------------------------
+constexpr int kNB = 32;
+
+__global__ void __launch_bounds__(kNB * kNB) k_chol_potrf(double* __restrict__ S, int ld, int kb)
+{
+    __shared__ double A[kNB][kNB + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;   // tx = column, ty = row
+    double* D = S + (size_t)kb * kNB + (size_t)ld * kb * kNB;
+    A[ty][tx] = D[ty + (size_t)ld * tx];
+    __syncthreads();
+    for (int j = 0; j < kNB; j++) {
+        if (tx == j && ty == j) {
+            const double d = A[j][j];
+            A[j][j] = d > 0.0 ? sqrt(d) : 0.0;
+        }
+        __syncthreads();
+        if (tx == j && ty > j) {
+            const double d = A[j][j];
+            A[ty][j] = d != 0.0 ? A[ty][j] / d : 0.0;
+        }
+        __syncthreads();
+        if (tx > j && ty >= tx) A[ty][tx] -= A[ty][j] * A[tx][j];
+        __syncthreads();
+    }
+    if (ty >= tx) D[ty + (size_t)ld * tx] = A[ty][tx];
+}
+
+// panel: X = A_ib,kb * L_kk^-T, one thread per row
+__global__ void __launch_bounds__(kNB) k_chol_trsm(double* __restrict__ S, int ld, int kb)
+{
+    __shared__ double L[kNB][kNB + 1];
+    const int ib = kb + 1 + blockIdx.x;
+    const int t = threadIdx.x;
+    const double* D = S + (size_t)kb * kNB + (size_t)ld * kb * kNB;
+    for (int c = 0; c < kNB; c++) L[t][c] = D[t + (size_t)ld * c];
+    __syncthreads();
+    double* P = S + (size_t)ib * kNB + (size_t)ld * kb * kNB;
+    double x[kNB];
+#pragma unroll
+    for (int c = 0; c < kNB; c++) x[c] = P[t + (size_t)ld * c];
+#pragma unroll
+    for (int c = 0; c < kNB; c++) {
+        double s = x[c];
+#pragma unroll
+        for (int q = 0; q < c; q++) s -= x[q] * L[c][q];
+        const double d = L[c][c];
+        x[c] = d != 0.0 ? s / d : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < kNB; c++) P[t + (size_t)ld * c] = x[c];
+}
+
+// trailing update: C_ib,jb -= X_ib X_jb' for ib >= jb > kb (lower triangle only)
+__global__ void __launch_bounds__(256) k_chol_syrk(double* __restrict__ S, int ld, int kb)
+{
+    const int jb = kb + 1 + blockIdx.x, ib = kb + 1 + blockIdx.y;
+    if (ib < jb) return;
+    __shared__ double Xi[kNB][kNB + 1], Xj[kNB][kNB + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 2 x 2 outputs each
+    const double* Pi = S + (size_t)ib * kNB + (size_t)ld * kb * kNB;
+    const double* Pj = S + (size_t)jb * kNB + (size_t)ld * kb * kNB;
+    for (int t = threadIdx.x; t < kNB * kNB; t += 256) {
+        const int r = t & 31, c = t >> 5;
+        Xi[r][c] = Pi[r + (size_t)ld * c];
+        Xj[r][c] = Pj[r + (size_t)ld * c];
+    }
+    __syncthreads();
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+#pragma unroll
+    for (int q = 0; q < kNB; q++) {
+        const double a0 = Xi[ty][q], a1 = Xi[ty + 16][q], b0 = Xj[tx][q], b1 = Xj[tx + 16][q];
+        c00 += a0 * b0; c01 += a0 * b1; c10 += a1 * b0; c11 += a1 * b1;
+    }
+    double* Cb = S + (size_t)ib * kNB + (size_t)ld * jb * kNB;
+    Cb[ty + (size_t)ld * tx] -= c00;
+    Cb[ty + (size_t)ld * (tx + 16)] -= c01;
+    Cb[ty + 16 + (size_t)ld * tx] -= c10;
+    Cb[ty + 16 + (size_t)ld * (tx + 16)] -= c11;
+}
+
+// x = S^+ rhs from the factor: forward then backward substitution, one CTA, x in shared
+// memory; eliminated pivots (L_cc = 0) give x_c = 0 (pinv of the zero rows of S).
+__global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ L, int ld, int Np, int N,
+                                                     const double* __restrict__ rhs, double* __restrict__ x_out)
+{
+    extern __shared__ double x[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int t = tid; t < Np; t += 1024) x[t] = t < N ? rhs[t] : 0.0;
+    __syncthreads();
+    const int nb = Np / kNB;
+    for (int kb = 0; kb < nb; kb++) {           // L y = rhs
+        if (warp == 0) {
+            const double* D = L + (size_t)kb * kNB + (size_t)ld * kb * kNB;
+            double y = x[kb * kNB + lane];
+            for (int c = 0; c < kNB; c++) {
+                const double d = D[c + (size_t)ld * c];
+                double yc = __shfl_sync(0xffffffffu, y, c);
+                yc = d != 0.0 ? yc / d : 0.0;
+                if (lane == c) y = yc;
+                if (lane > c) y -= D[lane + (size_t)ld * c] * yc;
+            }
+            x[kb * kNB + lane] = y;
+        }
+        __syncthreads();
+        for (int r = (kb + 1) * kNB + tid; r < Np; r += 1024) {
+            double s = x[r];
+            const double* Lr = L + r + (size_t)ld * kb * kNB;
+#pragma unroll 8
+            for (int c = 0; c < kNB; c++) s -= Lr[(size_t)ld * c] * x[kb * kNB + c];
+            x[r] = s;
+        }
+        __syncthreads();
+    }
+    for (int kb = nb - 1; kb >= 0; kb--) {      // L' x = y
+        {   // warp w handles column c = w: s_c = sum_{r below block} L[r][c] x[r]
+            const int c = kb * kNB + warp;
+            double s = 0.0;
+            for (int r = (kb + 1) * kNB + lane; r < Np; r += 32) s += L[r + (size_t)ld * c] * x[r];
+            s = warp_sum(s);
+            __syncthreads();
+            if (lane == 0) x[c] -= s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const double* D = L + (size_t)kb * kNB + (size_t)ld * kb * kNB;
+            double y = x[kb * kNB + lane];
+            for (int c = kNB - 1; c >= 0; c--) {
+                const double d = D[c + (size_t)ld * c];
+                double yc = __shfl_sync(0xffffffffu, y, c);
+                yc = d != 0.0 ? yc / d : 0.0;
+                if (lane == c) y = yc;
+                if (lane < c) y -= D[c + (size_t)ld * lane] * yc;
+            }
+            x[kb * kNB + lane] = y;
+        }
+        __syncthreads();
+    }
+    for (int t = tid; t < N; t += 1024) x_out[t] = x[t];
+}
+
+// ---------------------------------------------------------------------------------------
+// implicit Schur matvec q = S p = U* p - W V*^-1 W' p (never forming S), two sweeps.
+// ---------------------------------------------------------------------------------------
+// sweep 1, point-keyed: t_i = V*_i^-1 sum_j W_ij' p_j  (one thread per point, ascending j)
+template <int NA>
+__global__ void k_sweep_pt(int n, const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
+                           const int* __restrict__ pt_cam, const double* __restrict__ W,
+                           const double* __restrict__ Vinv, const double* __restrict__ p,
+                           const int* __restrict__ done, double* __restrict__ t_out)
+{
+    if (done && *done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int q = pt_ptr[i]; q < pt_ptr[i + 1]; q++) {
+        const double* Wo = W + (size_t)3 * NA * pt_obs[q];
+        const double* pj = p + (size_t)NA * pt_cam[q];
+#pragma unroll
+        for (int r = 0; r < NA; r++) {
+            const double pr = __ldg(pj + r);
+            s0 += Wo[r] * pr; s1 += Wo[r + NA] * pr; s2 += Wo[r + 2 * NA] * pr;
+        }
+    }
+    const double* Vi = Vinv + (size_t)9 * i;
+    t_out[(size_t)3 * i] = Vi[0] * s0 + Vi[3] * s1 + Vi[6] * s2;
+    t_out[(size_t)3 * i + 1] = Vi[1] * s0 + Vi[4] * s1 + Vi[7] * s2;
+    t_out[(size_t)3 * i + 2] = Vi[2] * s0 + Vi[5] * s1 + Vi[8] * s2;
+}
+
+// sweep 2, camera-keyed: chunk partial of sum_i W_ij t_i (one warp per chunk)
+template <int NA>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_sweep_cam(int nchunks, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_end,
+            const int* __restrict__ obs_pt, const double* __restrict__ W, const double* __restrict__ t_in,
+            const int* __restrict__ done, double* __restrict__ part /* [nchunks][NA] */)
+{
+    if (done && *done) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= nchunks) return;
+    double acc[NA];
+#pragma unroll
+    for (int r = 0; r < NA; r++) acc[r] = 0.0;
+    for (int o = chunk_begin[c] + lane; o < chunk_end[c]; o += 32) {
+        const int i = obs_pt[o];
+        const double t0 = __ldg(t_in + (size_t)3 * i), t1 = __ldg(t_in + (size_t)3 * i + 1), t2 = __ldg(t_in + (size_t)3 * i + 2);
+        const double* Wo = W + (size_t)3 * NA * o;
+#pragma unroll
+        for (int r = 0; r < NA; r++) acc[r] += Wo[r] * t0 + Wo[r + NA] * t1 + Wo[r + 2 * NA] * t2;
+    }
+#pragma unroll
+    for (int r = 0; r < NA; r++) {
+        const double v = warp_sum(acc[r]);
+        if (lane == r) part[(size_t)NA * c + r] = v;
+    }
+}
+
+// PCG scalars kept on the device: [0] rz, [1] r0norm2, [2] rnorm2, [3] iterations, [4] pq
+struct PcgScalars { double rz, r0n2, rn2, pq; int iters; int done; };
+
+// one-CTA vector kernels over the N = NA*m reduced unknowns (replicated on every rank)
+__device__ __forceinline__ double block_sum_1024(double v, double* sh)
+{
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double r = sh[lane];
+    r = warp_sum(r);
+    return r;   // every thread
+}
+
+// r = e_, x = 0, z = M^-1 r, p = z, rz = r'z, r0n2 = r'r
+template <int NA>
+__global__ void __launch_bounds__(1024) k_pcg_init(int m, const double* __restrict__ ebar, const double* __restrict__ Minv,
+                                                   double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                   double* __restrict__ p, PcgScalars* __restrict__ sc, double rtol)
+{
+    __shared__ double sh[32];
+    const int N = NA * m;
+    double rz = 0.0, rr = 0.0;
+    for (int t = threadIdx.x; t < N; t += 1024) {
+        const int j = t / NA, row = t % NA;
+        double zz = 0.0;
+#pragma unroll
+        for (int c = 0; c < NA; c++) zz += Minv[(size_t)NA * NA * j + row + NA * c] * ebar[(size_t)NA * j + c];
+        const double rv = ebar[t];
+        x[t] = 0.0; r[t] = rv; z[t] = zz; p[t] = zz;
+        rz += rv * zz; rr += rv * rv;
+    }
+    rz = block_sum_1024(rz, sh);
+    rr = block_sum_1024(rr, sh);
+    if (threadIdx.x == 0) {
+        sc->rz = rz; sc->r0n2 = rr; sc->rn2 = rr; sc->pq = 0.0; sc->iters = 0;
+        sc->done = (rr == 0.0) ? 1 : 0;
+        (void)rtol;
+    }
+}
+
+// q = U* p - wq;  alpha = rz / p'q;  x += alpha p;  r -= alpha q;  z = M^-1 r;
+// beta = r'z / rz;  p = z + beta p;  stop flag when |r| <= rtol |r0|
+template <int NA>
+__global__ void __launch_bounds__(1024) k_pcg_update(int m, const double* __restrict__ Ud, const double* __restrict__ Minv,
+                                                     const double* __restrict__ wq, double* __restrict__ x,
+                                                     double* __restrict__ r, double* __restrict__ z, double* __restrict__ p,
+                                                     double* __restrict__ q, PcgScalars* __restrict__ sc, double rtol)
+{
+    __shared__ double sh[32];
+    if (sc->done) return;
+    const int N = NA * m;
+    double pq = 0.0;
+    for (int t = threadIdx.x; t < N; t += 1024) {
+        const int j = t / NA, row = t % NA;
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < NA; c++) v += Ud[(size_t)NA * NA * j + row + NA * c] * p[(size_t)NA * j + c];
+        v -= wq[t];
+        q[t] = v;
+        pq += p[t] * v;
+    }
+    pq = block_sum_1024(pq, sh);
+    const double rz = sc->rz;
+    if (!(pq > 0.0)) {           // breakdown (p in the null space): stop with the current x
+        __syncthreads();
+        if (threadIdx.x == 0) { sc->done = 2; sc->pq = pq; }
+        return;
+    }
+    const double alpha = rz / pq;
+    double rr = 0.0;
+    for (int t = threadIdx.x; t < N; t += 1024) {
+        x[t] += alpha * p[t];
+        const double rv = r[t] - alpha * q[t];
+        r[t] = rv;
+        rr += rv * rv;
+    }
+    rr = block_sum_1024(rr, sh);
+    __syncthreads();
+    double rz_new = 0.0;
+    for (int t = threadIdx.x; t < N; t += 1024) {
+        const int j = t / NA, row = t % NA;
+        double zz = 0.0;
+#pragma unroll
+        for (int c = 0; c < NA; c++) zz += Minv[(size_t)NA * NA * j + row + NA * c] * r[(size_t)NA * j + c];
+        z[t] = zz;
+        rz_new += r[t] * zz;
+    }
+    rz_new = block_sum_1024(rz_new, sh);
+    const double beta = rz_new / rz;
+    for (int t = threadIdx.x; t < N; t += 1024) p[t] = z[t] + beta * p[t];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc->rz = rz_new; sc->rn2 = rr; sc->pq = pq; sc->iters += 1;
+        if (rr <= rtol * rtol * sc->r0n2) sc->done = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 3 (mex_bundle_3_db_new.c:100-146): db_i = V*_i^-1 (eB_i - sum_j W_ij' da_j) with the
+// reference's association order and (by default) only 6 camera rows (:113-120); b_new = b + db;
+// per-point share of db'(lambda db + eB) (bundle_euclid.m:215-217).
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__global__ void k_backsub(int n, const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
+                          const int* __restrict__ pt_cam, const double* __restrict__ W,
+                          const double* __restrict__ Vinv, const double* __restrict__ eB,
+                          const double* __restrict__ da, const double* __restrict__ b, double lambda, int all_rows,
+                          double* __restrict__ db, double* __restrict__ b_new, double* __restrict__ denom_pt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double w0 = eB[(size_t)3 * i], w1 = eB[(size_t)3 * i + 1], w2 = eB[(size_t)3 * i + 2];
+    const double g0 = w0, g1 = w1, g2 = w2;
+    const int nrow = all_rows ? NA : 6;
+    for (int q = pt_ptr[i]; q < pt_ptr[i + 1]; q++) {
+        const double* Wo = W + (size_t)3 * NA * pt_obs[q];
+        const double* dj = da + (size_t)NA * pt_cam[q];
+        double s0 = VLG_M(Wo[0], dj[0]), s1 = VLG_M(Wo[NA], dj[0]), s2 = VLG_M(Wo[2 * NA], dj[0]);
+        for (int r = 1; r < nrow; r++) {
+            const double d = dj[r];
+            s0 = VLG_P(s0, VLG_M(Wo[r], d));
+            s1 = VLG_P(s1, VLG_M(Wo[r + NA], d));
+            s2 = VLG_P(s2, VLG_M(Wo[r + 2 * NA], d));
+        }
+        w0 = VLG_S(w0, s0); w1 = VLG_S(w1, s1); w2 = VLG_S(w2, s2);
+    }
+    const double* Vi = Vinv + (size_t)9 * i;
+    const double d0 = VLG_P(VLG_P(VLG_M(Vi[0], w0), VLG_M(Vi[3], w1)), VLG_M(Vi[6], w2));
+    const double d1 = VLG_P(VLG_P(VLG_M(Vi[1], w0), VLG_M(Vi[4], w1)), VLG_M(Vi[7], w2));
+    const double d2 = VLG_P(VLG_P(VLG_M(Vi[2], w0), VLG_M(Vi[5], w1)), VLG_M(Vi[8], w2));
+    db[(size_t)3 * i] = d0; db[(size_t)3 * i + 1] = d1; db[(size_t)3 * i + 2] = d2;
+    b_new[(size_t)3 * i] = VLG_P(b[(size_t)3 * i], d0);
+    b_new[(size_t)3 * i + 1] = VLG_P(b[(size_t)3 * i + 1], d1);
+    b_new[(size_t)3 * i + 2] = VLG_P(b[(size_t)3 * i + 2], d2);
+    denom_pt[i] = d0 * (lambda * d0 + g0) + d1 * (lambda * d1 + g1) + d2 * (lambda * d2 + g2);
+}
+
+// new residual at (a_new, b_new): per-observation squared error (mex_bundle_3_db_new.c:149-166
+// + bundle_euclid.m:205,210).  C-order: the camera is (nearly) warp-uniform.
+template <int NA>
+__global__ void k_new_cost(int64_t nobs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_pt,
+                           const int* __restrict__ obs_cam, const double* __restrict__ K4,
+                           const double* __restrict__ a_new, const double* __restrict__ b_new,
+                           const double* __restrict__ rtab_new /* [m][9] */, double* __restrict__ cost_obs)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nobs) return;
+    const int i = obs_pt[o], j = obs_cam[o];
+    double R[9], al[NA], Kl[4];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = __ldg(rtab_new + (size_t)9 * j + k);
+#pragma unroll
+    for (int k = 3; k < NA; k++) al[k] = __ldg(a_new + (size_t)NA * j + k);
+#pragma unroll
+    for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
+    double fx, fy, cx, cy, x, y;
+    effective_K<NA>(Kl, al, fx, fy, cx, cy);
+    project_R(R, al[3], al[4], al[5], fx, fy, cx, cy, b_new[(size_t)3 * i], b_new[(size_t)3 * i + 1],
+              b_new[(size_t)3 * i + 2], x, y);
+    const double2 xy = obs_xy[o];
+    const double e0 = VLG_S(xy.x, x), e1 = VLG_S(xy.y, y);
+    cost_obs[o] = e0 * e0 + e1 * e1;
+}
+
+// rotation tables on the device (VLG_BA_RTABLE_DEVICE): 4 matrices per camera for stage 1,
+// or 1 (base only) for the new cost.
+template <int NA>
+__global__ void k_rtab(int m, const double* __restrict__ a, int nmat, double* __restrict__ rtab)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * nmat) return;
+    const int j = t / nmat, k = t % nmat;
+    double w0 = a[(size_t)NA * j], w1 = a[(size_t)NA * j + 1], w2 = a[(size_t)NA * j + 2];
+    if (k == 1) w0 = VLG_P(w0, kFdStep);
+    if (k == 2) w1 = VLG_P(w1, kFdStep);
+    if (k == 3) w2 = VLG_P(w2, kFdStep);
+    double R[9];
+    rodrigues_dev(w0, w1, w2, R);
+#pragma unroll
+    for (int q = 0; q < 9; q++) rtab[(size_t)9 * t + q] = R[q];
+}
+
+__global__ void k_axpy1(int N, const double* __restrict__ a, const double* __restrict__ da, double* __restrict__ a_new)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < N) a_new[t] = VLG_P(a[t], da[t]);
+}
+
+// da'(lambda da + eA) over the N reduced unknowns, one CTA
+__global__ void __launch_bounds__(1024) k_denom_cam(int N, const double* __restrict__ da, const double* __restrict__ eA,
+                                                    double lambda, double* __restrict__ out)
+{
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int t = threadIdx.x; t < N; t += 1024) v += da[t] * (lambda * da[t] + eA[t]);
+    v = block_sum_1024(v, sh);
+    if (threadIdx.x == 0) *out = v;
+}
+
+}  // namespace vlgba

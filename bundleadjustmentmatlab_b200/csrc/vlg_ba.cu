@@ -1,0 +1,524 @@
+// vlg_ba.cu -- host side of libvlgba.so: context, problem set-up, the LM driver of
+// bundle_euclid.m:111-267 and the C ABI declared in include/vlg_ba.h.
+//
+// Host code is plain C-style C++ calling the CUDA kernels of ba_kernels.cuh; no torch, no
+// CPU fallback (vlg_ba_create fails without a device).  NCCL is bound lazily with dlopen so
+// that the single-GPU library has no NCCL dependency.
+#include "../../include/vlg_ba.h"
+#include "ba_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+using namespace vlgba;
+
+// ------------------------------------------------------------------------------------------
+// NCCL, bound at run time
+// ------------------------------------------------------------------------------------------
+namespace {
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclFloat64 = 8, kNcclSum = 0;
+
+bool nccl_load()
+{
+    if (g_nccl.h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return false;
+    g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(nccl_comm))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+
+char g_create_error[512] = "";
+
+enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_COUNT };
+const char* kTimerNames[T_COUNT] = {"stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt",
+                                    "pcg_sweep_cam", "stage3"};
+
+struct KTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double total_ms = 0.0;
+    int64_t count = 0;
+};
+
+}  // namespace
+
+struct vlg_ba_ctx {
+    vlg_ba_opts opt;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = "";
+    // problem
+    int m = 0, n = 0, na = 6;
+    int64_t nobs = 0;
+    double num_vis = 0.0;
+    bool have_problem = false;
+    int nchunks = 0, chunk_size = 256;
+    bool use_chol = false;
+    int Np = 0;               // padded order of S
+    int64_t nblocks = 0, npairs = 0;
+    // host copies
+    std::vector<double> h_K, h_a, h_a_new, h_rtab, h_rtab_new, h_da;
+    std::vector<int32_t> h_obs_pt, h_obs_cam;
+    std::vector<double> h_obs_xy;
+    std::vector<int32_t> h_blk_j, h_blk_k;
+    // device: structure
+    double2 *obs_xy = nullptr, *pt_xy = nullptr;
+    int *obs_pt = nullptr, *obs_cam = nullptr, *cam_ptr = nullptr, *pt_ptr = nullptr, *pt_obs = nullptr, *pt_cam = nullptr;
+    int *chunk_cam = nullptr, *chunk_begin = nullptr, *chunk_end = nullptr, *cam_chunk_ptr = nullptr;
+    unsigned char* cam_fixed = nullptr;
+    int *blk_j = nullptr, *blk_k = nullptr;
+    int64_t* blk_ptr = nullptr;
+    int2* pairs = nullptr;
+    // device: parameters
+    double *K4 = nullptr, *a = nullptr, *b = nullptr, *a_new = nullptr, *b_new = nullptr, *rtab = nullptr, *rtab_new = nullptr;
+    // device: stage 1 (red1 = U | eA | cost | nvis contiguous for one all-reduce)
+    double *red1 = nullptr, *U = nullptr, *eA = nullptr, *scal1 = nullptr;
+    double *W = nullptr, *Upart = nullptr, *V = nullptr, *eB = nullptr, *cost_pt = nullptr, *red_part = nullptr;
+    // device: stage 2
+    double *Ud = nullptr, *Vinv = nullptr, *Spart = nullptr, *S = nullptr;
+    double *red2 = nullptr, *Sjj = nullptr, *ebar = nullptr;   // red2 = per-camera sums [m][NU], all-reduced
+    double *Minv = nullptr, *da = nullptr;
+    double *pr = nullptr, *pz = nullptr, *pp = nullptr, *pq = nullptr, *wq = nullptr, *tvec = nullptr, *qpart = nullptr;
+    PcgScalars* pcg_sc = nullptr;
+    // device: stage 3 (scal3 = new_cost | denom_pt_sum | denom_cam)
+    double *db = nullptr, *denom_pt = nullptr, *cost_obs = nullptr, *scal3 = nullptr;
+    // pinned host scalars
+    double* h_pin = nullptr;
+    PcgScalars* h_pcg = nullptr;
+    // LM state
+    double lambda = 1e-3, nu = 2.0;
+    int iter = 1, iter2 = 0;
+    bool s1_valid = false, s2_valid = false, s3_valid = false;
+    double old_cost = 0.0;
+    double s2_lambda = 0.0;
+    int last_solver = 0, last_pcg_iters = 0;
+    double last_pcg_relres = 0.0;
+    // multi-GPU
+    nccl_comm comm = nullptr;
+    int rank = 0, nranks = 1;
+    // accounting
+    int64_t launches = 0;
+    bool timers_on = false;
+    KTimer timers[T_COUNT];
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_sw[2] = {nullptr, nullptr};
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+int fail(vlg_ba_ctx* c, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, VLG_BA_ECUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CHK(call)                        \
+    do {                                 \
+        int r_ = (call);                 \
+        if (r_ != VLG_BA_OK) return r_;  \
+    } while (0)
+
+template <class T>
+int dalloc(vlg_ba_ctx* ctx, T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, VLG_BA_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    ctx->allocs.push_back(q);
+    *p = (T*)q;
+    return VLG_BA_OK;
+}
+
+void free_problem(vlg_ba_ctx* ctx)
+{
+    for (void* p : ctx->allocs) cudaFree(p);
+    ctx->allocs.clear();
+    ctx->have_problem = false;
+    ctx->s1_valid = ctx->s2_valid = ctx->s3_valid = false;
+}
+
+template <class T>
+int upload(vlg_ba_ctx* ctx, T* dst, const T* src, size_t count)
+{
+    if (count) CU(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return VLG_BA_OK;
+}
+
+template <class T>
+int download(vlg_ba_ctx* ctx, T* dst, const T* src, size_t count)
+{
+    if (count && dst) CU(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return VLG_BA_OK;
+}
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- kernel timers ------------------------------------------------------------------------
+struct TimedScope {
+    vlg_ba_ctx* c;
+    int id;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    TimedScope(vlg_ba_ctx* ctx, int tid) : c(ctx), id(tid)
+    {
+        if (!c->timers_on) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        e0 = get(); e1 = get();
+        cudaEventRecord(e0, c->stream);
+    }
+    ~TimedScope()
+    {
+        if (!e0) return;
+        cudaEventRecord(e1, c->stream);
+        c->timers[id].pending.push_back({e0, e1});
+    }
+};
+
+void resolve_timers(vlg_ba_ctx* c)
+{
+    cudaStreamSynchronize(c->stream);
+    for (int t = 0; t < T_COUNT; t++) {
+        for (auto& pr : c->timers[t].pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+                c->timers[t].total_ms += ms;
+                c->timers[t].count += 1;
+            }
+            c->ev_pool.push_back(pr.first);
+            c->ev_pool.push_back(pr.second);
+        }
+        c->timers[t].pending.clear();
+    }
+}
+
+// ---- host rotation table: vl_rodrigues with the host libm (bit parity with the CPU reference) ----
+// Same statement as the reference's dependency (VLFeat vl_rodrigues, call site
+// reproject_point.h:44); compiled with -ffp-contract=off.
+void rodrigues_host(double w0, double w1, double w2, double* R)
+{
+    double th = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    if (th < 1e-6) {
+        R[0] = 1.0; R[3] = 0.0; R[6] = 0.0;
+        R[1] = 0.0; R[4] = 1.0; R[7] = 0.0;
+        R[2] = 0.0; R[5] = 0.0; R[8] = 1.0;
+        return;
+    }
+    double x = w0 / th, y = w1 / th, z = w2 / th;
+    double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+    double sth = sin(th), cth = cos(th), mcth = 1.0 - cth;
+    R[0] = 1.0 - mcth * (yy + zz);
+    R[1] = sth * z + mcth * xy;
+    R[2] = -sth * y + mcth * xz;
+    R[3] = -sth * z + mcth * xy;
+    R[4] = 1.0 - mcth * (zz + xx);
+    R[5] = sth * x + mcth * yz;
+    R[6] = sth * y + mcth * xz;
+    R[7] = -sth * x + mcth * yz;
+    R[8] = 1.0 - mcth * (xx + yy);
+}
+
+void rtab_host(int m, int na, const double* a, int nmat, double* out)
+{
+    const double h = 1e-10;
+    for (int j = 0; j < m; j++) {
+        const double* w = a + (size_t)na * j;
+        for (int k = 0; k < nmat; k++) {
+            double w0 = w[0], w1 = w[1], w2 = w[2];
+            if (k == 1) w0 = w0 + h;
+            if (k == 2) w1 = w1 + h;
+            if (k == 3) w2 = w2 + h;
+            rodrigues_host(w0, w1, w2, out + ((size_t)j * nmat + k) * 9);
+        }
+    }
+}
+
+// ---- all-reduce helper -----------------------------------------------------------------------
+int allreduce(vlg_ba_ctx* ctx, double* buf, size_t count)
+{
+    if (ctx->nranks <= 1 || count == 0) return VLG_BA_OK;
+    int r = g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (r != 0) return fail(ctx, VLG_BA_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return VLG_BA_OK;
+}
+
+int reduce_to(vlg_ba_ctx* ctx, const double* in, size_t n, double* out)
+{
+    k_reduce_partial<<<kRedBlocks, kRedThreads, 0, ctx->stream>>>(in, n, ctx->red_part);
+    k_reduce_final<<<1, kRedThreads, 0, ctx->stream>>>(ctx->red_part, kRedBlocks, out);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return VLG_BA_OK;
+}
+
+// ---- problem set-up ----------------------------------------------------------------------------
+int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* a, const double* b, int64_t nobs,
+                  const double* obs_xy, const int32_t* obs_pt, const int32_t* obs_cam, const double* pivot)
+{
+    const vlg_ba_opts& o = ctx->opt;
+    if (m <= 0 || n < 0 || nobs < 0) return fail(ctx, VLG_BA_EINVAL, "bad sizes m=%d n=%d nobs=%lld", m, n, (long long)nobs);
+    if (!K || !a || (n > 0 && !b)) return fail(ctx, VLG_BA_EINVAL, "K, a and b are required");
+    if (nobs >= (int64_t)1 << 31) return fail(ctx, VLG_BA_EINVAL, "nobs must be < 2^31 per context");
+    const int na = 6 + o.num_variableK;
+    if (!(o.num_variableK == 0 || o.num_variableK == 1 || o.num_variableK == 4))
+        return fail(ctx, VLG_BA_EINVAL, "num_variableK must be 0, 1 or 4");
+    // validate list order (ascending i + n*j) and ranges
+    for (int64_t t = 0; t < nobs; t++) {
+        if (obs_pt[t] < 0 || obs_pt[t] >= n || obs_cam[t] < 0 || obs_cam[t] >= m)
+            return fail(ctx, VLG_BA_EINVAL, "observation %lld out of range (pt %d, cam %d)", (long long)t, obs_pt[t], obs_cam[t]);
+        if (t > 0) {
+            const int64_t k0 = (int64_t)obs_pt[t - 1] + (int64_t)n * obs_cam[t - 1], k1 = (int64_t)obs_pt[t] + (int64_t)n * obs_cam[t];
+            if (k1 <= k0) return fail(ctx, VLG_BA_EINVAL, "observation list must be strictly ascending in i + n*j (at %lld)", (long long)t);
+        }
+    }
+    free_problem(ctx);
+    CU(cudaSetDevice(ctx->device));
+    ctx->m = m; ctx->n = n; ctx->na = na; ctx->nobs = nobs;
+    ctx->num_vis = (double)nobs;
+    const size_t N = (size_t)na * m;
+
+    ctx->h_K.assign(K, K + 4 * (size_t)m);
+    ctx->h_a.assign(a, a + N);
+    ctx->h_a_new.assign(N, 0.0);
+    ctx->h_da.assign(N, 0.0);
+    ctx->h_rtab.assign((size_t)36 * m, 0.0);
+    ctx->h_rtab_new.assign((size_t)9 * m, 0.0);
+    ctx->h_obs_pt.assign(obs_pt, obs_pt + nobs);
+    ctx->h_obs_cam.assign(obs_cam, obs_cam + nobs);
+    ctx->h_obs_xy.assign(obs_xy, obs_xy + 2 * nobs);
+
+    // CSR by camera and by point
+    std::vector<int> cam_ptr(m + 1, 0), pt_ptr(n + 1, 0), pt_obs(nobs), pt_cam(nobs);
+    std::vector<double> pt_xy(2 * (size_t)nobs);
+    for (int64_t t = 0; t < nobs; t++) { cam_ptr[obs_cam[t] + 1]++; pt_ptr[obs_pt[t] + 1]++; }
+    for (int j = 0; j < m; j++) cam_ptr[j + 1] += cam_ptr[j];
+    for (int i = 0; i < n; i++) pt_ptr[i + 1] += pt_ptr[i];
+    {
+        std::vector<int> fill(pt_ptr.begin(), pt_ptr.end() - 1);
+        for (int64_t t = 0; t < nobs; t++) {
+            const int q = fill[obs_pt[t]]++;
+            pt_obs[q] = (int)t; pt_cam[q] = obs_cam[t];
+            pt_xy[2 * (size_t)q] = obs_xy[2 * t]; pt_xy[2 * (size_t)q + 1] = obs_xy[2 * t + 1];
+        }
+    }
+    // chunks of the camera segments
+    int cs;
+    if (o.order == VLG_BA_ORDER_REFERENCE) cs = 1 << 30;
+    else {
+        int64_t want = nobs / (148 * 8);
+        cs = (int)std::min<int64_t>(256, std::max<int64_t>(32, (want + 31) / 32 * 32));
+    }
+    ctx->chunk_size = cs;
+    std::vector<int> chunk_cam, chunk_begin, chunk_end, cam_chunk_ptr(m + 1, 0);
+    for (int j = 0; j < m; j++) {
+        for (int64_t s = cam_ptr[j]; s < cam_ptr[j + 1]; s += cs) {
+            chunk_cam.push_back(j);
+            chunk_begin.push_back((int)s);
+            chunk_end.push_back((int)std::min<int64_t>(s + cs, cam_ptr[j + 1]));
+        }
+        cam_chunk_ptr[j + 1] = (int)chunk_cam.size();
+    }
+    ctx->nchunks = (int)chunk_cam.size();
+
+    std::vector<unsigned char> fixed(m, 0);
+    for (int j = 0; j < m; j++) fixed[j] = (o.fix_motion || (pivot && pivot[j] != 0.0)) ? 1 : 0;
+
+    ctx->use_chol = (o.solver == VLG_BA_SOLVER_CHOL) || (o.solver == VLG_BA_SOLVER_AUTO && m <= o.chol_max_cams);
+    ctx->Np = (int)((N + kNB - 1) / kNB * kNB);
+
+    // block structure of S: cameras j <= k sharing a point; pair lists in ascending point order
+    std::vector<int64_t> blk_ptr;
+    std::vector<int2> pairs;
+    ctx->h_blk_j.clear(); ctx->h_blk_k.clear();
+    if (ctx->use_chol) {
+        if ((int64_t)m * m > ((int64_t)1 << 28)) return fail(ctx, VLG_BA_EINVAL, "explicit Schur/Cholesky path supports m <= 16384 cameras");
+        std::vector<int64_t> cnt((size_t)m * m + 1, 0);
+        for (int i = 0; i < n; i++)
+            for (int qa = pt_ptr[i]; qa < pt_ptr[i + 1]; qa++)
+                for (int qb = qa; qb < pt_ptr[i + 1]; qb++) cnt[(size_t)pt_cam[qa] * m + pt_cam[qb] + 1]++;
+        // diagonal blocks always exist (S_jj = U*_j even without observations)
+        std::vector<int64_t> slot((size_t)m * m, -1);
+        blk_ptr.push_back(0);
+        for (int j = 0; j < m; j++)
+            for (int k = j; k < m; k++) {
+                const int64_t c = cnt[(size_t)j * m + k + 1];
+                if (c > 0 || j == k) {
+                    slot[(size_t)j * m + k] = (int64_t)ctx->h_blk_j.size();
+                    ctx->h_blk_j.push_back(j); ctx->h_blk_k.push_back(k);
+                    blk_ptr.push_back(blk_ptr.back() + c);
+                }
+            }
+        pairs.resize((size_t)blk_ptr.back());
+        std::vector<int64_t> fill(blk_ptr.begin(), blk_ptr.end() - 1);
+        for (int i = 0; i < n; i++)
+            for (int qa = pt_ptr[i]; qa < pt_ptr[i + 1]; qa++)
+                for (int qb = qa; qb < pt_ptr[i + 1]; qb++) {
+                    const int64_t s = slot[(size_t)pt_cam[qa] * m + pt_cam[qb]];
+                    pairs[(size_t)fill[s]++] = make_int2(pt_obs[qa], pt_obs[qb]);
+                }
+        ctx->nblocks = (int64_t)ctx->h_blk_j.size();
+        ctx->npairs = (int64_t)pairs.size();
+    } else {
+        ctx->nblocks = 0; ctx->npairs = 0;
+    }
+
+    const int NU = nu_of(na);
+    // ---- device allocations
+    CHK(dalloc(ctx, &ctx->obs_xy, (size_t)nobs)); CHK(dalloc(ctx, &ctx->pt_xy, (size_t)nobs));
+    CHK(dalloc(ctx, &ctx->obs_pt, (size_t)nobs)); CHK(dalloc(ctx, &ctx->obs_cam, (size_t)nobs));
+    CHK(dalloc(ctx, &ctx->cam_ptr, (size_t)m + 1)); CHK(dalloc(ctx, &ctx->pt_ptr, (size_t)n + 1));
+    CHK(dalloc(ctx, &ctx->pt_obs, (size_t)nobs)); CHK(dalloc(ctx, &ctx->pt_cam, (size_t)nobs));
+    CHK(dalloc(ctx, &ctx->chunk_cam, (size_t)ctx->nchunks)); CHK(dalloc(ctx, &ctx->chunk_begin, (size_t)ctx->nchunks));
+    CHK(dalloc(ctx, &ctx->chunk_end, (size_t)ctx->nchunks)); CHK(dalloc(ctx, &ctx->cam_chunk_ptr, (size_t)m + 1));
+    CHK(dalloc(ctx, &ctx->cam_fixed, (size_t)m));
+    CHK(dalloc(ctx, &ctx->K4, (size_t)4 * m)); CHK(dalloc(ctx, &ctx->a, N)); CHK(dalloc(ctx, &ctx->a_new, N));
+    CHK(dalloc(ctx, &ctx->b, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->b_new, (size_t)3 * n));
+    CHK(dalloc(ctx, &ctx->rtab, (size_t)36 * m)); CHK(dalloc(ctx, &ctx->rtab_new, (size_t)9 * m));
+    CHK(dalloc(ctx, &ctx->red1, (size_t)na * N + N + 2));
+    ctx->U = ctx->red1; ctx->eA = ctx->red1 + (size_t)na * N; ctx->scal1 = ctx->eA + N;
+    CHK(dalloc(ctx, &ctx->W, (size_t)3 * na * nobs)); CHK(dalloc(ctx, &ctx->Upart, (size_t)NU * ctx->nchunks));
+    CHK(dalloc(ctx, &ctx->V, (size_t)9 * n)); CHK(dalloc(ctx, &ctx->eB, (size_t)3 * n));
+    CHK(dalloc(ctx, &ctx->cost_pt, (size_t)n)); CHK(dalloc(ctx, &ctx->red_part, (size_t)kRedBlocks));
+    CHK(dalloc(ctx, &ctx->Ud, (size_t)na * N)); CHK(dalloc(ctx, &ctx->Vinv, (size_t)9 * n));
+    CHK(dalloc(ctx, &ctx->Spart, (size_t)NU * ctx->nchunks));
+    CHK(dalloc(ctx, &ctx->red2, (size_t)NU * m));
+    CHK(dalloc(ctx, &ctx->Sjj, (size_t)na * N)); CHK(dalloc(ctx, &ctx->ebar, N));
+    CHK(dalloc(ctx, &ctx->Minv, (size_t)na * N)); CHK(dalloc(ctx, &ctx->da, N));
+    CHK(dalloc(ctx, &ctx->pr, N)); CHK(dalloc(ctx, &ctx->pz, N)); CHK(dalloc(ctx, &ctx->pp, N)); CHK(dalloc(ctx, &ctx->pq, N));
+    CHK(dalloc(ctx, &ctx->wq, N)); CHK(dalloc(ctx, &ctx->tvec, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->qpart, (size_t)na * ctx->nchunks));
+    CHK(dalloc(ctx, &ctx->pcg_sc, 1));
+    CHK(dalloc(ctx, &ctx->db, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->denom_pt, (size_t)n));
+    CHK(dalloc(ctx, &ctx->cost_obs, (size_t)nobs)); CHK(dalloc(ctx, &ctx->scal3, 4));
+    if (ctx->use_chol) {
+        CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));
+        CHK(dalloc(ctx, &ctx->blk_j, (size_t)ctx->nblocks)); CHK(dalloc(ctx, &ctx->blk_k, (size_t)ctx->nblocks));
+        CHK(dalloc(ctx, &ctx->blk_ptr, (size_t)ctx->nblocks + 1)); CHK(dalloc(ctx, &ctx->pairs, (size_t)ctx->npairs));
+        CHK(upload(ctx, ctx->blk_j, ctx->h_blk_j.data(), (size_t)ctx->nblocks));
+        CHK(upload(ctx, ctx->blk_k, ctx->h_blk_k.data(), (size_t)ctx->nblocks));
+        CHK(upload(ctx, ctx->blk_ptr, blk_ptr.data(), (size_t)ctx->nblocks + 1));
+        CHK(upload(ctx, ctx->pairs, pairs.data(), (size_t)ctx->npairs));
+    }
+    CHK(upload(ctx, (double*)ctx->obs_xy, obs_xy, 2 * (size_t)nobs));
+    CHK(upload(ctx, (double*)ctx->pt_xy, pt_xy.data(), 2 * (size_t)nobs));
+    CHK(upload(ctx, ctx->obs_pt, obs_pt, (size_t)nobs)); CHK(upload(ctx, ctx->obs_cam, obs_cam, (size_t)nobs));
+    CHK(upload(ctx, ctx->cam_ptr, cam_ptr.data(), (size_t)m + 1)); CHK(upload(ctx, ctx->pt_ptr, pt_ptr.data(), (size_t)n + 1));
+    CHK(upload(ctx, ctx->pt_obs, pt_obs.data(), (size_t)nobs)); CHK(upload(ctx, ctx->pt_cam, pt_cam.data(), (size_t)nobs));
+    CHK(upload(ctx, ctx->chunk_cam, chunk_cam.data(), (size_t)ctx->nchunks));
+    CHK(upload(ctx, ctx->chunk_begin, chunk_begin.data(), (size_t)ctx->nchunks));
+    CHK(upload(ctx, ctx->chunk_end, chunk_end.data(), (size_t)ctx->nchunks));
+    CHK(upload(ctx, ctx->cam_chunk_ptr, cam_chunk_ptr.data(), (size_t)m + 1));
+    CHK(upload(ctx, ctx->cam_fixed, fixed.data(), (size_t)m));
+    CHK(upload(ctx, ctx->K4, K, (size_t)4 * m)); CHK(upload(ctx, ctx->a, a, N)); CHK(upload(ctx, ctx->b, b, (size_t)3 * n));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_problem = true;
+    ctx->lambda = o.lambda0; ctx->nu = o.nu0; ctx->iter = 1; ctx->iter2 = 0;
+    ctx->s1_valid = ctx->s2_valid = ctx->s3_valid = false;
+    return VLG_BA_OK;
+}
+
+// ---- stage launches, templated on NA -----------------------------------------------------------
+template <int NA>
+int run_rtab(vlg_ba_ctx* ctx, const std::vector<double>& h_a, const double* d_a, int nmat, std::vector<double>& h_tab, double* d_tab)
+{
+    if (ctx->opt.rtable == VLG_BA_RTABLE_HOST_LIBM) {
+        rtab_host(ctx->m, NA, h_a.data(), nmat, h_tab.data());
+        CHK(upload(ctx, d_tab, h_tab.data(), (size_t)9 * nmat * ctx->m));
+    } else {
+        k_rtab<NA><<<cdiv((int64_t)ctx->m * nmat, 128), 128, 0, ctx->stream>>>(ctx->m, d_a, nmat, d_tab);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return VLG_BA_OK;
+}
+
+template <int NA>
+int run_stage1(vlg_ba_ctx* ctx, double* diag_X, double* diag_A, double* diag_B, double* diag_e)
+{
+    constexpr int NU = nu_of(NA);
+    const bool diag = diag_X || diag_A || diag_B || diag_e;
+    CHK(run_rtab<NA>(ctx, ctx->h_a, ctx->a, 4, ctx->h_rtab, ctx->rtab));
+    Stage1Args p;
+    p.m = ctx->m; p.n = ctx->n; p.nchunks = ctx->nchunks;
+    p.obs_xy = ctx->obs_xy; p.obs_pt = ctx->obs_pt;
+    p.chunk_cam = ctx->chunk_cam; p.chunk_begin = ctx->chunk_begin; p.chunk_end = ctx->chunk_end;
+    p.K4 = ctx->K4; p.a = ctx->a; p.b = ctx->b; p.rtab = ctx->rtab; p.cam_fixed = ctx->cam_fixed;
+    p.fix_structure = ctx->opt.fix_structure;
+    p.W = ctx->W; p.Upart = ctx->Upart;
+    p.dX_hat = diag_X; p.dA = diag_A; p.dB = diag_B; p.de = diag_e;
+    const size_t smem = (size_t)kWarpsPerBlock * (36 + NA + 4 + 32 * NU + 32 * 3 * NA) * sizeof(double);
+    if (ctx->nchunks > 0) {
+        TimedScope ts(ctx, T_STAGE1_CAM);
+        if (diag) {
+            CU(cudaFuncSetAttribute(k_stage1_cam<NA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_stage1_cam<NA, true><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, smem, ctx->stream>>>(p);
+        } else {
+            CU(cudaFuncSetAttribute(k_stage1_cam<NA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_stage1_cam<NA, false><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, smem, ctx->stream>>>(p);
+        }
+        ctx->launches++;
+    }
+    k_stage1_cam_finalize<NA><<<cdiv((int64_t)ctx->m * NU, 128), 128, 0, ctx->stream>>>(ctx->m, ctx->cam_chunk_ptr, ctx->Upart,
+                                                                                         ctx->cam_fixed, ctx->U, ctx->eA);
+    ctx->launches++;
+    if (ctx->n > 0) {
+        TimedScope ts(ctx, T_STAGE1_PT);
+        k_stage1_pt<NA><<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->pt_ptr, ctx->pt_cam, ctx->pt_xy, ctx->K4, ctx->a,
+                                                                    ctx->b, ctx->rtab, ctx->opt.fix_structure, ctx->V, ctx->eB,
+                                                                    ctx->cost_pt);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    CHK(reduce_to(ctx, ctx->cost_pt, (size_t)ctx->n, ctx->scal1));
+    return VLG_BA_OK;
+}
+
+}  // namespace
+
+// The remaining host logic (stage 2 solve paths, stage 3, LM driver, C ABI) follows in
+// vlg_ba_host.inl to keep this translation unit readable.
+#include "vlg_ba_host.inl"

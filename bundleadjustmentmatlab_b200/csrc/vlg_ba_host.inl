@@ -1,0 +1,681 @@
+// vlg_ba_host.inl -- included by vlg_ba.cu: stage 2 / stage 3 launch sequences, the LM
+// driver (bundle_euclid.m:111-267) and the extern "C" entry points of include/vlg_ba.h.
+
+namespace {
+
+__global__ void k_gather_xy(int64_t nobs, const int* __restrict__ pt_obs, const double2* __restrict__ obs_xy,
+                            double2* __restrict__ pt_xy)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nobs) pt_xy[q] = obs_xy[pt_obs[q]];
+}
+
+int* pcg_done_ptr(vlg_ba_ctx* ctx) { return (int*)((char*)ctx->pcg_sc + offsetof(PcgScalars, done)); }
+
+// damping + V*^-1 + camera-keyed Schur sums + (Cholesky: S, factor, solve | PCG)  ->  da
+template <int NA>
+int run_stage2(vlg_ba_ctx* ctx, double lambda)
+{
+    constexpr int NU = nu_of(NA);
+    const int m = ctx->m, n = ctx->n, N = NA * m;
+    {
+        TimedScope ts(ctx, T_VINV);
+        k_damp_U<NA><<<cdiv((int64_t)m * NA * NA, 256), 256, 0, ctx->stream>>>(m, lambda, ctx->U, ctx->Ud);
+        ctx->launches++;
+        if (n > 0) {
+            k_vinv_damp<<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, lambda, ctx->V, ctx->Vinv);
+            ctx->launches++;
+        }
+    }
+    {
+        TimedScope ts(ctx, T_SCHUR);
+        if (ctx->nchunks > 0) {
+            k_cam_schur_diag<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+                ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->eB, ctx->Spart);
+            ctx->launches++;
+        }
+        k_cam_sum_partials<<<cdiv((int64_t)m * NU, 128), 128, 0, ctx->stream>>>(m, NU, ctx->cam_chunk_ptr, ctx->Spart, nullptr, ctx->red2);
+        ctx->launches++;
+    }
+    CHK(allreduce(ctx, ctx->red2, (size_t)NU * m));
+    k_cam_schur_finalize<NA><<<cdiv(m, 64), 64, 0, ctx->stream>>>(m, ctx->red2, ctx->Ud, ctx->eA, ctx->Sjj, ctx->ebar,
+                                                                  ctx->use_chol ? nullptr : ctx->Minv);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    if (ctx->use_chol) {
+        const int Np = ctx->Np, nb = Np / kNB;
+        {
+            TimedScope ts(ctx, T_SCHUR_BLK);
+            CU(cudaMemsetAsync(ctx->S, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
+            if (ctx->nblocks > 0) {
+                k_schur_blocks<NA><<<cdiv(ctx->nblocks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+                    (int)ctx->nblocks, Np, ctx->rank == 0 ? 1 : 0, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt,
+                    ctx->W, ctx->Vinv, ctx->Ud, ctx->S);
+                ctx->launches++;
+            }
+        }
+        CHK(allreduce(ctx, ctx->S, (size_t)Np * Np));
+        {
+            TimedScope ts(ctx, T_CHOL);
+            for (int kb = 0; kb < nb; kb++) {
+                k_chol_potrf<<<1, dim3(kNB, kNB), 0, ctx->stream>>>(ctx->S, Np, kb);
+                ctx->launches++;
+                const int rem = nb - kb - 1;
+                if (rem > 0) {
+                    k_chol_trsm<<<rem, kNB, 0, ctx->stream>>>(ctx->S, Np, kb);
+                    k_chol_syrk<<<dim3(rem, rem), 256, 0, ctx->stream>>>(ctx->S, Np, kb);
+                    ctx->launches += 2;
+                }
+            }
+            const size_t smem = sizeof(double) * (size_t)Np;
+            CU(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            k_chol_solve<<<1, 1024, smem, ctx->stream>>>(ctx->S, Np, Np, N, ctx->ebar, ctx->da);
+            ctx->launches++;
+        }
+        CU(cudaGetLastError());
+        ctx->last_solver = VLG_BA_SOLVER_CHOL;
+        ctx->last_pcg_iters = 0; ctx->last_pcg_relres = 0.0;
+    } else {
+        const double rtol = ctx->opt.pcg_rtol;
+        int* done = pcg_done_ptr(ctx);
+        k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol);
+        ctx->launches++;
+        int launched = 0;
+        const int batch = 8;
+        while (launched < ctx->opt.pcg_max_iter) {
+            for (int it = 0; it < batch && launched < ctx->opt.pcg_max_iter; it++, launched++) {
+                if (n > 0) {
+                    TimedScope ts(ctx, T_SWEEP_PT);
+                    k_sweep_pt<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W, ctx->Vinv,
+                                                                         ctx->pp, done, ctx->tvec);
+                    ctx->launches++;
+                }
+                if (ctx->nchunks > 0) {
+                    TimedScope ts(ctx, T_SWEEP_CAM);
+                    k_sweep_cam<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+                        ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->tvec, done, ctx->qpart);
+                    ctx->launches++;
+                }
+                k_cam_sum_partials<<<cdiv((int64_t)m * NA, 128), 128, 0, ctx->stream>>>(m, NA, ctx->cam_chunk_ptr, ctx->qpart, done, ctx->wq);
+                ctx->launches++;
+                CHK(allreduce(ctx, ctx->wq, (size_t)N));
+                k_pcg_update<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Ud, ctx->Minv, ctx->wq, ctx->da, ctx->pr, ctx->pz, ctx->pp,
+                                                              ctx->pq, ctx->pcg_sc, rtol);
+                ctx->launches++;
+            }
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (ctx->h_pcg->done) break;
+        }
+        if (!ctx->h_pcg->done) {
+            CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->last_solver = VLG_BA_SOLVER_PCG;
+        ctx->last_pcg_iters = ctx->h_pcg->iters;
+        ctx->last_pcg_relres = ctx->h_pcg->r0n2 > 0.0 ? sqrt(ctx->h_pcg->rn2 / ctx->h_pcg->r0n2) : 0.0;
+    }
+    return VLG_BA_OK;
+}
+
+// db, a_new, b_new, new cost and dp'(lambda dp + g)
+template <int NA>
+int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
+{
+    const int m = ctx->m, n = ctx->n, N = NA * m;
+    if (ctx->opt.rtable == VLG_BA_RTABLE_HOST_LIBM) {
+        // a_new = a + da on the host (same IEEE add as mex_bundle_3_db_new.c:137-140) so that the
+        // rotation matrices of the candidate come from the host libm
+        CHK(download(ctx, ctx->h_da.data(), ctx->da, (size_t)N));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int t = 0; t < N; t++) ctx->h_a_new[t] = ctx->h_a[t] + ctx->h_da[t];
+        CHK(upload(ctx, ctx->a_new, ctx->h_a_new.data(), (size_t)N));
+    } else {
+        k_axpy1<<<cdiv(N, 256), 256, 0, ctx->stream>>>(N, ctx->a, ctx->da, ctx->a_new);
+        ctx->launches++;
+    }
+    CHK(run_rtab<NA>(ctx, ctx->h_a_new, ctx->a_new, 1, ctx->h_rtab_new, ctx->rtab_new));
+    {
+        TimedScope ts(ctx, T_STAGE3);
+        if (n > 0) {
+            k_backsub<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W, ctx->Vinv, ctx->eB,
+                                                                ctx->da, ctx->b, lambda, ctx->opt.backsub_all_rows, ctx->db,
+                                                                ctx->b_new, ctx->denom_pt);
+            ctx->launches++;
+        }
+        if (ctx->nobs > 0) {
+            k_new_cost<NA><<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->obs_xy, ctx->obs_pt, ctx->obs_cam, ctx->K4,
+                                                                         ctx->a_new, ctx->b_new, ctx->rtab_new, ctx->cost_obs);
+            ctx->launches++;
+        }
+    }
+    CU(cudaGetLastError());
+    CHK(reduce_to(ctx, ctx->cost_obs, (size_t)ctx->nobs, ctx->scal3));
+    CHK(reduce_to(ctx, ctx->denom_pt, (size_t)n, ctx->scal3 + 1));
+    CHK(allreduce(ctx, ctx->scal3, 2));
+    k_denom_cam<<<1, 1024, 0, ctx->stream>>>(N, ctx->da, ctx->eA, lambda, ctx->scal3 + 2);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_pin, ctx->scal3, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *new_cost = ctx->h_pin[0];
+    // dp = [da; db], g = [eA; eB] (bundle_euclid.m:215-217)
+    *denom = ctx->h_pin[2] + ctx->h_pin[1];
+    if (ctx->opt.rtable != VLG_BA_RTABLE_HOST_LIBM) {
+        CHK(download(ctx, ctx->h_a_new.data(), ctx->a_new, (size_t)N));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return VLG_BA_OK;
+}
+
+#define DISPATCH_NA(ctx, call)                                                   \
+    ((ctx)->na == 6 ? call<6> : (ctx)->na == 7 ? call<7> : call<10>)
+
+int do_stage1(vlg_ba_ctx* ctx)
+{
+    if (!ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // nvis travels with the cost in the same all-reduce (num_vis, bundle_euclid.m:82)
+    const double nv = (double)ctx->nobs;
+    CHK(upload(ctx, ctx->scal1 + 1, &nv, 1));
+    CHK(DISPATCH_NA(ctx, run_stage1)(ctx, nullptr, nullptr, nullptr, nullptr));
+    CHK(allreduce(ctx, ctx->red1, (size_t)ctx->na * ctx->na * ctx->m + (size_t)ctx->na * ctx->m + 2));
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_pin + 4, ctx->scal1, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->old_cost = ctx->h_pin[4];
+    ctx->num_vis = ctx->h_pin[5];
+    ctx->s1_valid = true; ctx->s2_valid = false; ctx->s3_valid = false;
+    return VLG_BA_OK;
+}
+
+int do_stage2(vlg_ba_ctx* ctx, double lambda)
+{
+    if (!ctx->s1_valid) return fail(ctx, VLG_BA_ESTATE, "stage2 needs stage1 at the current state");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->s1_valid) {}
+    CHK(DISPATCH_NA(ctx, run_stage2)(ctx, lambda));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->s2_valid = true; ctx->s2_lambda = lambda; ctx->s3_valid = false;
+    return VLG_BA_OK;
+}
+
+int do_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
+{
+    if (!ctx->s2_valid) return fail(ctx, VLG_BA_ESTATE, "stage3 needs stage2");
+    CU(cudaSetDevice(ctx->device));
+    CHK(DISPATCH_NA(ctx, run_stage3)(ctx, lambda, new_cost, denom));
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->s3_valid = true;
+    return VLG_BA_OK;
+}
+
+// one trip of the while loop, bundle_euclid.m:139-241
+int do_trial(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
+{
+    const double lambda = ctx->lambda;
+    bool fresh1 = false;
+    if (!ctx->s1_valid) { CHK(do_stage1(ctx)); fresh1 = true; }   // a rejected step left (a,b) unchanged: mex1 would give the same bits
+    else CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    const double old_cost = ctx->old_cost;
+    CHK(do_stage2(ctx, lambda));
+    double new_cost = 0.0, denom = 0.0;
+    CHK(do_stage3(ctx, lambda, &new_cost, &denom));
+    const double rho = (old_cost - new_cost) / denom;                       // :217
+    const bool accept = (old_cost - new_cost) > 0;                          // :218
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->old_cost = old_cost; info->new_cost = new_cost; info->denom = denom; info->rho = rho;
+        info->lambda_used = lambda; info->accepted = accept ? 1 : 0;
+        info->solver_used = ctx->last_solver; info->pcg_iters = ctx->last_pcg_iters; info->pcg_relres = ctx->last_pcg_relres;
+        float ms = 0.f;
+        if (fresh1 && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) info->ms_stage1 = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) info->ms_schur = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) info->ms_solve = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) info->ms_stage3 = ms;
+    }
+    if (!isfinite(new_cost) && !isfinite(old_cost)) return fail(ctx, VLG_BA_ENUM, "non-finite cost");
+    if (accept) {
+        std::swap(ctx->a, ctx->a_new);
+        std::swap(ctx->b, ctx->b_new);
+        ctx->h_a.swap(ctx->h_a_new);
+        const double f = 1 - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
+        ctx->lambda = lambda * std::max(1.0 / 3.0, f);                      // :227
+        ctx->nu = 2.0;
+        ctx->iter += 1;
+        ctx->iter2 = 0;
+        ctx->s1_valid = false;
+    } else {
+        ctx->lambda = lambda * ctx->nu;                                     // :238-240
+        ctx->nu = 2 * ctx->nu;
+        ctx->iter2 += 1;
+    }
+    ctx->s2_valid = false; ctx->s3_valid = false;
+    if (info) { info->lambda_next = ctx->lambda; info->nu_next = ctx->nu; }
+    return VLG_BA_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+void vlg_ba_opts_default(vlg_ba_opts* o)
+{
+    memset(o, 0, sizeof(*o));
+    o->num_variableK = 4;
+    o->lambda0 = 0.001; o->nu0 = 2.0; o->max_iter = 20; o->max_iter2 = 10; o->rel_tol = 1e-3; o->abs_tol = 1e-20;
+    o->backsub_all_rows = 0;
+    o->solver = VLG_BA_SOLVER_AUTO; o->chol_max_cams = 300; o->pcg_rtol = 1e-10; o->pcg_max_iter = 1000;
+    o->rtable = VLG_BA_RTABLE_HOST_LIBM; o->order = VLG_BA_ORDER_CHUNKED; o->device = -1; o->verbose = 0;
+}
+
+const char* vlg_ba_version(void) { return "vlgba 0.1 (sm_100a, fp64)"; }
+
+const char* vlg_ba_last_error(const vlg_ba_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int vlg_ba_create(const vlg_ba_opts* opts, vlg_ba_ctx** out)
+{
+    vlg_ba_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, VLG_BA_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VLG_BA_ECUDA, "no CUDA device (%s): this library has no CPU fallback", cudaGetErrorString(e));
+    vlg_ba_ctx* c = new vlg_ba_ctx();
+    if (opts) c->opt = *opts; else vlg_ba_opts_default(&c->opt);
+    int dev = c->opt.device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= ndev) { delete c; return fail(nullptr, VLG_BA_EINVAL, "device %d of %d", dev, ndev); }
+    c->device = dev;
+    ctx = c;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_pin, 16 * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_pcg, sizeof(PcgScalars)) != cudaSuccess) {
+        int r = fail(nullptr, VLG_BA_ECUDA, "context set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return r;
+    }
+    for (int k = 0; k < 5; k++) cudaEventCreate(&c->ev[k]);
+    for (int k = 0; k < 2; k++) cudaEventCreate(&c->ev_sw[k]);
+    memset(c->h_pcg, 0, sizeof(PcgScalars));
+    (void)ctx;
+    *out = c;
+    return VLG_BA_OK;
+}
+
+void vlg_ba_destroy(vlg_ba_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    free_problem(ctx);
+    for (int t = 0; t < T_COUNT; t++)
+        for (auto& pr : ctx->timers[t].pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int k = 0; k < 5; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (int k = 0; k < 2; k++) if (ctx->ev_sw[k]) cudaEventDestroy(ctx->ev_sw[k]);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->h_pcg) cudaFreeHost(ctx->h_pcg);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int vlg_ba_nccl_unique_id(void* unique_id_128)
+{
+    if (!nccl_load()) return fail(nullptr, VLG_BA_ENCCL, "libnccl.so.2 not found");
+    nccl_uid id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, VLG_BA_ENCCL, "ncclGetUniqueId failed (%d)", r);
+    memcpy(unique_id_128, &id, sizeof(id));
+    return VLG_BA_OK;
+}
+
+int vlg_ba_set_comm(vlg_ba_ctx* ctx, int rank, int nranks, const void* unique_id_128)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    if (nranks <= 1) { ctx->rank = 0; ctx->nranks = 1; return VLG_BA_OK; }
+    if (!nccl_load()) return fail(ctx, VLG_BA_ENCCL, "libnccl.so.2 not found");
+    CU(cudaSetDevice(ctx->device));
+    nccl_uid id;
+    memcpy(&id, unique_id_128, sizeof(id));
+    int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0) return fail(ctx, VLG_BA_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    ctx->rank = rank; ctx->nranks = nranks;
+    return VLG_BA_OK;
+}
+
+int vlg_ba_set_problem_sparse(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* a, const double* b,
+                              int64_t nobs, const double* obs_xy, const int32_t* obs_pt, const int32_t* obs_cam,
+                              const double* pivot)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    if (nobs > 0 && (!obs_xy || !obs_pt || !obs_cam)) return fail(ctx, VLG_BA_EINVAL, "observation list is NULL");
+    return build_problem(ctx, m, n, K, a, b, nobs, obs_xy, obs_pt, obs_cam, pivot);
+}
+
+// visibility compaction: {(i,j): visible(i,j) != 0} in ascending i + n*j, exactly the cells the
+// reference treats as visible (mex_bundle_1_XABeUVWeAeB.c:196)
+int vlg_ba_set_problem_dense(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* a, const double* b,
+                             const double* X, const double* visible, const double* pivot)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    if (m <= 0 || n < 0 || (n > 0 && (!X || !visible))) return fail(ctx, VLG_BA_EINVAL, "X and visible are required");
+    std::vector<double> xy;
+    std::vector<int32_t> pt, cam;
+    for (int j = 0; j < m; j++)
+        for (int i = 0; i < n; i++) {
+            const size_t c = (size_t)i + (size_t)n * j;
+            if (visible[c] != 0.0) {
+                xy.push_back(X[2 * c]); xy.push_back(X[2 * c + 1]);
+                pt.push_back(i); cam.push_back(j);
+            }
+        }
+    return build_problem(ctx, m, n, K, a, b, (int64_t)pt.size(), xy.data(), pt.data(), cam.data(), pivot);
+}
+
+int vlg_ba_set_num_vis(vlg_ba_ctx* ctx, double num_vis)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    ctx->num_vis = num_vis;
+    return VLG_BA_OK;
+}
+
+int64_t vlg_ba_nobs(const vlg_ba_ctx* ctx) { return ctx ? ctx->nobs : 0; }
+
+int vlg_ba_get_obs(vlg_ba_ctx* ctx, double* obs_xy, int32_t* obs_pt, int32_t* obs_cam)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    if (obs_xy) memcpy(obs_xy, ctx->h_obs_xy.data(), sizeof(double) * 2 * (size_t)ctx->nobs);
+    if (obs_pt) memcpy(obs_pt, ctx->h_obs_pt.data(), sizeof(int32_t) * (size_t)ctx->nobs);
+    if (obs_cam) memcpy(obs_cam, ctx->h_obs_cam.data(), sizeof(int32_t) * (size_t)ctx->nobs);
+    return VLG_BA_OK;
+}
+
+int vlg_ba_set_state(vlg_ba_ctx* ctx, const double* a, const double* b, double lambda, double nu)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    CU(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)ctx->na * ctx->m;
+    if (a) { ctx->h_a.assign(a, a + N); CHK(upload(ctx, ctx->a, a, N)); }
+    if (b) CHK(upload(ctx, ctx->b, b, (size_t)3 * ctx->n));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (lambda > 0) ctx->lambda = lambda;
+    if (nu > 0) ctx->nu = nu;
+    if (a || b) ctx->s1_valid = ctx->s2_valid = ctx->s3_valid = false;
+    return VLG_BA_OK;
+}
+
+int vlg_ba_get_state(vlg_ba_ctx* ctx, double* a, double* b, double* lambda, double* nu, int* iter, int* iter2)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    CU(cudaSetDevice(ctx->device));
+    CHK(download(ctx, a, ctx->a, (size_t)ctx->na * ctx->m));
+    CHK(download(ctx, b, ctx->b, (size_t)3 * ctx->n));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (lambda) *lambda = ctx->lambda;
+    if (nu) *nu = ctx->nu;
+    if (iter) *iter = ctx->iter;
+    if (iter2) *iter2 = ctx->iter2;
+    return VLG_BA_OK;
+}
+
+int vlg_ba_stage1(vlg_ba_ctx* ctx, double* cost)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    CHK(do_stage1(ctx));
+    if (cost) *cost = ctx->old_cost;
+    return VLG_BA_OK;
+}
+
+int vlg_ba_get_blocks(vlg_ba_ctx* ctx, double* U, double* V, double* W, double* eA, double* eB)
+{
+    if (!ctx || !ctx->s1_valid) return fail(ctx, VLG_BA_ESTATE, "stage1 has not run at the current state");
+    CU(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)ctx->na * ctx->m;
+    CHK(download(ctx, U, ctx->U, (size_t)ctx->na * N));
+    CHK(download(ctx, V, ctx->V, (size_t)9 * ctx->n));
+    CHK(download(ctx, W, ctx->W, (size_t)3 * ctx->na * ctx->nobs));
+    CHK(download(ctx, eA, ctx->eA, N));
+    CHK(download(ctx, eB, ctx->eB, (size_t)3 * ctx->n));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VLG_BA_OK;
+}
+
+int vlg_ba_get_jacobians(vlg_ba_ctx* ctx, double* X_hat, double* A, double* B, double* e)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    CU(cudaSetDevice(ctx->device));
+    const size_t no = (size_t)ctx->nobs, na = (size_t)ctx->na;
+    double *dX = nullptr, *dA = nullptr, *dB = nullptr, *de = nullptr;
+    CU(cudaMalloc(&dX, sizeof(double) * std::max<size_t>(2 * no, 1)));
+    CU(cudaMalloc(&dA, sizeof(double) * std::max<size_t>(2 * na * no, 1)));
+    CU(cudaMalloc(&dB, sizeof(double) * std::max<size_t>(6 * no, 1)));
+    CU(cudaMalloc(&de, sizeof(double) * std::max<size_t>(2 * no, 1)));
+    int r = DISPATCH_NA(ctx, run_stage1)(ctx, dX, dA, dB, de);
+    if (r == VLG_BA_OK) r = download(ctx, X_hat, dX, 2 * no);
+    if (r == VLG_BA_OK) r = download(ctx, A, dA, 2 * na * no);
+    if (r == VLG_BA_OK) r = download(ctx, B, dB, 6 * no);
+    if (r == VLG_BA_OK) r = download(ctx, e, de, 2 * no);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(dX); cudaFree(dA); cudaFree(dB); cudaFree(de);
+    ctx->s1_valid = false; ctx->s2_valid = false; ctx->s3_valid = false;   // the launch rewrote local (un-reduced) sums
+    return r;
+}
+
+int vlg_ba_stage2(vlg_ba_ctx* ctx, double lambda)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    return do_stage2(ctx, lambda);
+}
+
+int vlg_ba_get_reduced(vlg_ba_ctx* ctx, double* Vinv, double* S, double* e_, double* da)
+{
+    if (!ctx || !ctx->s2_valid) return fail(ctx, VLG_BA_ESTATE, "stage2 has not run");
+    CU(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)ctx->na * ctx->m;
+    CHK(download(ctx, Vinv, ctx->Vinv, (size_t)9 * ctx->n));
+    CHK(download(ctx, e_, ctx->ebar, N));
+    CHK(download(ctx, da, ctx->da, N));
+    if (S) {
+        if (!ctx->use_chol) return fail(ctx, VLG_BA_ESTATE, "S is only formed on the Cholesky path");
+        // note: after the factorisation the lower triangle of the device S holds L; S itself is
+        // re-assembled here from the same kernels so that tests can compare it with mex2's output
+        const int Np = ctx->Np;
+        double* tmp = nullptr;
+        CU(cudaMalloc(&tmp, sizeof(double) * (size_t)Np * Np));
+        CU(cudaMemsetAsync(tmp, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
+        if (ctx->nblocks > 0) {
+            const int g = cdiv(ctx->nblocks, kWarpsPerBlock), th = kWarpsPerBlock * 32;
+            if (ctx->na == 6) k_schur_blocks<6><<<g, th, 0, ctx->stream>>>((int)ctx->nblocks, Np, 1, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->Ud, tmp);
+            else if (ctx->na == 7) k_schur_blocks<7><<<g, th, 0, ctx->stream>>>((int)ctx->nblocks, Np, 1, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->Ud, tmp);
+            else k_schur_blocks<10><<<g, th, 0, ctx->stream>>>((int)ctx->nblocks, Np, 1, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->Ud, tmp);
+        }
+        cudaError_t e = cudaMemcpy2DAsync(S, sizeof(double) * N, tmp, sizeof(double) * (size_t)Np, sizeof(double) * N, N,
+                                          cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return fail(ctx, VLG_BA_ECUDA, "copy of S: %s", cudaGetErrorString(e));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VLG_BA_OK;
+}
+
+int vlg_ba_set_da(vlg_ba_ctx* ctx, const double* da)
+{
+    if (!ctx || !ctx->s2_valid) return fail(ctx, VLG_BA_ESTATE, "stage2 has not run");
+    CU(cudaSetDevice(ctx->device));
+    CHK(upload(ctx, ctx->da, da, (size_t)ctx->na * ctx->m));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VLG_BA_OK;
+}
+
+int vlg_ba_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    double nc = 0, dn = 0;
+    CHK(do_stage3(ctx, lambda, &nc, &dn));
+    if (new_cost) *new_cost = nc;
+    if (denom) *denom = dn;
+    return VLG_BA_OK;
+}
+
+int vlg_ba_get_update(vlg_ba_ctx* ctx, double* db, double* a_new, double* b_new)
+{
+    if (!ctx || !ctx->s3_valid) return fail(ctx, VLG_BA_ESTATE, "stage3 has not run");
+    CU(cudaSetDevice(ctx->device));
+    CHK(download(ctx, db, ctx->db, (size_t)3 * ctx->n));
+    CHK(download(ctx, a_new, ctx->a_new, (size_t)ctx->na * ctx->m));
+    CHK(download(ctx, b_new, ctx->b_new, (size_t)3 * ctx->n));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VLG_BA_OK;
+}
+
+int vlg_ba_trial_step(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    return do_trial(ctx, info);
+}
+
+int vlg_ba_solve(vlg_ba_ctx* ctx, double* K_, double* Te_, double* w_, double* Xe_, const double* Xe4, double* error_,
+                 int* n_error)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    const vlg_ba_opts& o = ctx->opt;
+    std::vector<double> err((size_t)std::max(o.max_iter, 2) + 2, 0.0);
+    bool any = false;
+    ctx->lambda = o.lambda0; ctx->nu = o.nu0; ctx->iter = 1; ctx->iter2 = 0;     // bundle_euclid.m:111-119
+    for (;;) {
+        const int it = ctx->iter;
+        bool go = it < o.max_iter && ctx->iter2 < o.max_iter2;                   // :120-123
+        if (go && it >= 3) go = err[it - 1] > o.abs_tol && (err[it - 2] - err[it - 1]) > o.rel_tol * err[it - 2];
+        if (!go) break;
+        vlg_ba_trial_info info;
+        CHK(do_trial(ctx, &info));
+        if (info.accepted) {
+            err[it - 1] = info.old_cost / ctx->num_vis;                          // :219-220,229-231
+            err[it] = info.new_cost / ctx->num_vis;
+            any = true;
+            if (o.verbose) printf("iter %d: error= %.5g -> %.5g\n", it, err[it - 1], err[it]);
+        }
+    }
+    const int m = ctx->m, n = ctx->n, na = ctx->na;
+    std::vector<double> a((size_t)na * m), b((size_t)3 * n);
+    CHK(vlg_ba_get_state(ctx, a.data(), b.data(), nullptr, nullptr, nullptr, nullptr));
+    for (int j = 0; j < m; j++) {                                                // :256-267
+        if (K_) {
+            for (int k = 0; k < 4; k++) K_[4 * (size_t)j + k] = ctx->h_K[4 * (size_t)j + k];
+            if (o.num_variableK == 1) { K_[4 * (size_t)j] = a[(size_t)na * j + 6]; K_[4 * (size_t)j + 1] = a[(size_t)na * j + 6]; }
+            if (o.num_variableK == 4) for (int k = 0; k < 4; k++) K_[4 * (size_t)j + k] = a[(size_t)na * j + 6 + k];
+        }
+        for (int k = 0; k < 3; k++) {
+            if (w_) w_[3 * (size_t)j + k] = a[(size_t)na * j + k];
+            if (Te_) Te_[3 * (size_t)j + k] = a[(size_t)na * j + 3 + k];
+        }
+    }
+    if (Xe_)
+        for (int i = 0; i < n; i++) {
+            for (int k = 0; k < 3; k++) Xe_[4 * (size_t)i + k] = b[3 * (size_t)i + k];
+            Xe_[4 * (size_t)i + 3] = Xe4 ? Xe4[i] : 1.0;
+        }
+    const int ne = any ? ctx->iter : 0;
+    if (error_) for (int k = 0; k < ne; k++) error_[k] = err[k];
+    if (n_error) *n_error = ne;
+    return VLG_BA_OK;
+}
+
+int vlg_ba_trial_step_host(vlg_ba_ctx* ctx, const double* a, const double* b, const double* obs_xy, double lambda,
+                           double* a_new, double* b_new, vlg_ba_trial_info* info)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    CU(cudaSetDevice(ctx->device));
+    if (obs_xy && ctx->nobs > 0) {
+        CHK(upload(ctx, (double*)ctx->obs_xy, obs_xy, 2 * (size_t)ctx->nobs));
+        k_gather_xy<<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->pt_obs, ctx->obs_xy, ctx->pt_xy);
+        ctx->launches++;
+    }
+    CHK(vlg_ba_set_state(ctx, a, b, lambda, -1.0));
+    ctx->s1_valid = false;
+    // the candidate always lands in (a_new, b_new) on the device; fetch before do_trial swaps on accept
+    const double lam = ctx->lambda;
+    CHK(do_stage1(ctx));
+    CHK(do_stage2(ctx, lam));
+    double nc = 0, dn = 0;
+    CHK(do_stage3(ctx, lam, &nc, &dn));
+    CHK(download(ctx, a_new, ctx->a_new, (size_t)ctx->na * ctx->m));
+    CHK(download(ctx, b_new, ctx->b_new, (size_t)3 * ctx->n));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->old_cost = ctx->old_cost; info->new_cost = nc; info->denom = dn; info->rho = (ctx->old_cost - nc) / dn;
+        info->lambda_used = lam; info->accepted = (ctx->old_cost - nc) > 0;
+        info->solver_used = ctx->last_solver; info->pcg_iters = ctx->last_pcg_iters; info->pcg_relres = ctx->last_pcg_relres;
+    }
+    return VLG_BA_OK;
+}
+
+int vlg_ba_get_schur_structure(vlg_ba_ctx* ctx, int64_t* n_blocks, int32_t* blk_j, int32_t* blk_k)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    if (!ctx->use_chol) return fail(ctx, VLG_BA_ESTATE, "block structure is only built on the Cholesky path");
+    if (n_blocks) *n_blocks = ctx->nblocks;
+    if (blk_j) memcpy(blk_j, ctx->h_blk_j.data(), sizeof(int32_t) * (size_t)ctx->nblocks);
+    if (blk_k) memcpy(blk_k, ctx->h_blk_k.data(), sizeof(int32_t) * (size_t)ctx->nblocks);
+    return VLG_BA_OK;
+}
+
+int64_t vlg_ba_kernel_launches(const vlg_ba_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vlg_ba_reset_timers(vlg_ba_ctx* ctx, int enable)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    resolve_timers(ctx);
+    for (int t = 0; t < T_COUNT; t++) { ctx->timers[t].total_ms = 0.0; ctx->timers[t].count = 0; }
+    ctx->timers_on = enable != 0;
+    return VLG_BA_OK;
+}
+
+int vlg_ba_kernel_time(vlg_ba_ctx* ctx, const char* name, double* avg_ms, int64_t* count)
+{
+    if (!ctx || !name) return VLG_BA_EINVAL;
+    resolve_timers(ctx);
+    for (int t = 0; t < T_COUNT; t++)
+        if (strcmp(name, kTimerNames[t]) == 0) {
+            if (avg_ms) *avg_ms = ctx->timers[t].count ? ctx->timers[t].total_ms / (double)ctx->timers[t].count : 0.0;
+            if (count) *count = ctx->timers[t].count;
+            return VLG_BA_OK;
+        }
+    return fail(ctx, VLG_BA_EINVAL, "unknown kernel group '%s'", name);
+}
+
+int vlg_ba_timer_start(vlg_ba_ctx* ctx)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->ev_sw[0], ctx->stream));
+    return VLG_BA_OK;
+}
+
+int vlg_ba_timer_stop(vlg_ba_ctx* ctx, float* elapsed_ms)
+{
+    if (!ctx) return VLG_BA_EINVAL;
+    CU(cudaEventRecord(ctx->ev_sw[1], ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev_sw[1]));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev_sw[0], ctx->ev_sw[1]));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return VLG_BA_OK;
+}
+
+}  // extern "C"

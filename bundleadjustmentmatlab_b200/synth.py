@@ -134,8 +134,11 @@ def _tracks(m: int, n: int, nobs: int, rng) -> tuple[np.ndarray, np.ndarray]:
 
 
 def make_problem(m: int, n: int, nobs: int, seed: int = 0, noise_px: float = 0.5,
-                 num_variableK: int = 0) -> Problem:
+                 point_seed: int | None = None) -> Problem:
+    """`seed` fixes the cameras; `point_seed` (default: continue the same stream) fixes the points,
+    tracks and image noise -- shards of one scene share `seed` and differ in `point_seed`."""
     rng = np.random.default_rng(seed)
+    cam_noise = np.random.default_rng([seed, 7])
     depth = 100.0
     K = np.tile(np.array([[500.0], [500.0], [250.0], [250.0]]), (1, m))
     # cameras on an arc of radius `depth` around the scene centre (0,0,depth), looking inwards
@@ -150,6 +153,10 @@ def make_problem(m: int, n: int, nobs: int, seed: int = 0, noise_px: float = 0.5
     R = rodrigues(w_true)
     Te_true = -np.einsum("mij,jm->im", R, cpos)
     Te_true[:, 0] = 0.0
+    w0 = w_true + cam_noise.normal(0, 1e-3, size=w_true.shape)
+    T0 = Te_true + cam_noise.normal(0, 1e-4 * depth, size=Te_true.shape)
+    if point_seed is not None:
+        rng = np.random.default_rng([seed, 1000 + point_seed])
     # points in a ball of radius 25 around the centre: inside every camera's frustum
     d = rng.normal(size=(3, n))
     d /= np.linalg.norm(d, axis=0)
@@ -161,8 +168,6 @@ def make_problem(m: int, n: int, nobs: int, seed: int = 0, noise_px: float = 0.5
     xy = project(K, w_true, Te_true, X_true, pt, cam)
     xy += rng.normal(0.0, noise_px, size=xy.shape)
 
-    w0 = w_true + rng.normal(0, 1e-3, size=w_true.shape)
-    T0 = Te_true + rng.normal(0, 1e-4 * depth, size=Te_true.shape)
     X0 = X_true + rng.normal(0, 1e-3 * depth, size=X_true.shape)
     w0[:, 0] = 0.0
     T0[:, 0] = 0.0
@@ -170,9 +175,9 @@ def make_problem(m: int, n: int, nobs: int, seed: int = 0, noise_px: float = 0.5
     return Problem(m, n, K, w0, T0, Xe, np.ascontiguousarray(xy), pt, cam, w_true, Te_true, X_true)
 
 
-def make_config(name: str, seed: int = 0, scale: float = 1.0) -> Problem:
+def make_config(name: str, seed: int = 0, scale: float = 1.0, point_seed: int | None = None) -> Problem:
     m, n, nobs = CONFIGS[name]
     if scale != 1.0:
         n = max(int(n * scale), 8)
         nobs = max(int(nobs * scale), 2 * n)
-    return make_problem(m, n, nobs, seed)
+    return make_problem(m, n, nobs, seed, point_seed=point_seed)

@@ -1,0 +1,179 @@
+/*
+ * vlg_ba.h -- C ABI of the B200-native bundle adjuster (libvlgba.so).
+ *
+ * Drop-in boundary for the Levenberg-Marquardt Euclidean bundle-adjustment hot path of
+ * caomw/BundleAdjustmentMatlab (VLG, toolbox/bundle).  Every entry point states the
+ * reference interface it replaces (file:line relative to the reference tree).  Plain C:
+ * pointers and sizes only, host pointers in and out (caller-owned), device memory owned by
+ * the context.  Every call returns 0 on success or a negative VLG_BA_E* code;
+ * vlg_ba_last_error() gives the text.  There is NO CPU fallback: without a CUDA device
+ * vlg_ba_create() fails with VLG_BA_ECUDA.
+ *
+ * Array conventions (all double, MATLAB column-major, exactly as the reference's mex
+ * files receive them):
+ *   K  4 x m   [fx fy cx cy]' per camera             (bundle_euclid.m:5)
+ *   a  num_a x m, num_a = 6 + num_variableK: [w; Te; K-part]   (bundle_euclid.m:89-96)
+ *   b  3 x n   point coordinates                      (bundle_euclid.m:99)
+ *   X  2 x n x m measured image points, visible n x m (bundle_euclid.m:81,102)
+ * Sparse form of (X, visible): an observation list in the reference's traversal order,
+ * ascending i + n*j (mex_bundle_1_XABeUVWeAeB.c:192-196): obs_xy 2 x nobs, obs_pt[nobs]
+ * (point i), obs_cam[nobs] (camera j).
+ * Block outputs on the list: W is (num_a x 3) column-major per observation, in list order
+ * (the reference's dense W(:,:,i,j), mex_bundle_1_XABeUVWeAeB.c:165, restricted to visible
+ * cells); U num_a x num_a x m; V 3 x 3 x n; eA num_a x m; eB 3 x n.
+ */
+#ifndef VLG_BA_H
+#define VLG_BA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLG_BA_OK        0
+#define VLG_BA_EINVAL   -1   /* bad argument / shape */
+#define VLG_BA_ECUDA    -2   /* CUDA runtime error or no device */
+#define VLG_BA_ESTATE   -3   /* call out of order (e.g. stage2 before stage1) */
+#define VLG_BA_ENOMEM   -4
+#define VLG_BA_ENCCL    -5   /* NCCL missing or failed */
+#define VLG_BA_ENUM     -6   /* numerical breakdown (non-finite cost, PCG breakdown) */
+
+enum { VLG_BA_SOLVER_AUTO = 0, VLG_BA_SOLVER_CHOL = 1, VLG_BA_SOLVER_PCG = 2 };
+enum { VLG_BA_RTABLE_HOST_LIBM = 0, VLG_BA_RTABLE_DEVICE = 1 };
+enum { VLG_BA_ORDER_CHUNKED = 0, VLG_BA_ORDER_REFERENCE = 1 };
+
+/* Options.  Defaults (vlg_ba_opts_default) are the constants hard-coded in
+ * bundle_euclid.m:111-123 and mex_bundle_1_XABeUVWeAeB.c:23,52. */
+typedef struct vlg_ba_opts {
+    int    num_variableK;     /* 0 'fix_calibration', 1 'fix_principal', 4 default  (bundle_euclid.m:49,66-69) */
+    int    fix_structure;     /* bundle_euclid.m:140-144 */
+    int    fix_motion;        /* bundle_euclid.m:145-149 */
+    double lambda0;           /* 1e-3   bundle_euclid.m:111 */
+    double nu0;               /* 2      bundle_euclid.m:112 */
+    int    max_iter;          /* 20     bundle_euclid.m:117 */
+    int    max_iter2;         /* 10     bundle_euclid.m:118 */
+    double rel_tol;           /* 1e-3   bundle_euclid.m:123 */
+    double abs_tol;           /* 1e-20  bundle_euclid.m:123 */
+    int    backsub_all_rows;  /* 0 = reference behaviour: only 6 camera rows enter db (mex_bundle_3_db_new.c:113-120) */
+    int    solver;            /* VLG_BA_SOLVER_*: dense Cholesky of S, or block-Jacobi PCG on the implicit S */
+    int    chol_max_cams;     /* AUTO picks Cholesky when m <= this (default 300) */
+    double pcg_rtol;          /* relative residual stop for PCG (default 1e-10) */
+    int    pcg_max_iter;      /* default 1000 */
+    int    rtable;            /* VLG_BA_RTABLE_*: who evaluates vl_rodrigues' sin/cos (host libm = bit parity with the CPU reference) */
+    int    order;             /* VLG_BA_ORDER_*: REFERENCE = U/eA accumulated in the reference's exact order (slow), CHUNKED = fixed 256-observation chunks (default) */
+    int    device;            /* CUDA device ordinal; -1 = current device */
+    int    verbose;           /* 'verbose': print "iter k: error= a -> b" (bundle_euclid.m:221-224) */
+} vlg_ba_opts;
+
+typedef struct vlg_ba_ctx vlg_ba_ctx;
+
+/* What one trip of the LM loop (bundle_euclid.m:139-241) did. */
+typedef struct vlg_ba_trial_info {
+    double old_cost;      /* e'e          bundle_euclid.m:209 */
+    double new_cost;      /* e_new'e_new  bundle_euclid.m:210 */
+    double denom;         /* dp'(lambda dp + g)  bundle_euclid.m:217 */
+    double rho;
+    double lambda_used;
+    double lambda_next;
+    double nu_next;
+    int    accepted;
+    int    solver_used;   /* VLG_BA_SOLVER_CHOL or VLG_BA_SOLVER_PCG */
+    int    pcg_iters;
+    double pcg_relres;
+    float  ms_stage1;     /* residual + Jacobian + U,V,W,eA,eB       (mex1) */
+    float  ms_schur;      /* damping, V*^-1, S / e_ / preconditioner (bundle_euclid.m:162-184 + mex2) */
+    float  ms_solve;      /* da                                       (bundle_euclid.m:193) */
+    float  ms_stage3;     /* db, update, new residual                 (mex3 + :205-210) */
+} vlg_ba_trial_info;
+
+void vlg_ba_opts_default(vlg_ba_opts *opts);
+const char *vlg_ba_version(void);
+
+/* Context: one per host thread / GPU. */
+int  vlg_ba_create(const vlg_ba_opts *opts, vlg_ba_ctx **out);
+void vlg_ba_destroy(vlg_ba_ctx *ctx);
+const char *vlg_ba_last_error(const vlg_ba_ctx *ctx);      /* ctx may be NULL: error of a failed create */
+
+/* Multi-GPU: one context per rank holding a point shard.  `unique_id` is the
+ * 128-byte ncclUniqueId obtained from vlg_ba_nccl_unique_id() on rank 0 and broadcast by
+ * the caller.  After this call the per-camera sums and scalars are all-reduced over ranks. */
+int  vlg_ba_nccl_unique_id(void *unique_id_128);
+int  vlg_ba_set_comm(vlg_ba_ctx *ctx, int rank, int nranks, const void *unique_id_128);
+
+/* Problem definition.  Replaces the argument packing of bundle_euclid.m:81-102 and the
+ * positional inputs of mex_bundle_1_XABeUVWeAeB.c:76-83.  `pivot` (m doubles or NULL) is
+ * the 'fix_pivot' mask (bundle_euclid.m:150-154); non-zero = camera held fixed. */
+int  vlg_ba_set_problem_dense(vlg_ba_ctx *ctx, int m, int n, const double *K, const double *a,
+                              const double *b, const double *X, const double *visible,
+                              const double *pivot);
+int  vlg_ba_set_problem_sparse(vlg_ba_ctx *ctx, int m, int n, const double *K, const double *a,
+                               const double *b, int64_t nobs, const double *obs_xy,
+                               const int32_t *obs_pt, const int32_t *obs_cam, const double *pivot);
+/* n_total_obs: num_vis over ALL ranks (bundle_euclid.m:82); defaults to the local count. */
+int  vlg_ba_set_num_vis(vlg_ba_ctx *ctx, double num_vis);
+
+int64_t vlg_ba_nobs(const vlg_ba_ctx *ctx);
+/* Observation list as compacted from a dense problem (visibility indexing, bit-exact). */
+int  vlg_ba_get_obs(vlg_ba_ctx *ctx, double *obs_xy, int32_t *obs_pt, int32_t *obs_cam);
+
+/* LM state (a, b, lambda, nu, iter, iter2): bundle_euclid.m:111-119.  NULL = leave/skip. */
+int  vlg_ba_set_state(vlg_ba_ctx *ctx, const double *a, const double *b, double lambda, double nu);
+int  vlg_ba_get_state(vlg_ba_ctx *ctx, double *a, double *b, double *lambda, double *nu,
+                      int *iter, int *iter2);
+
+/* Stage 1 == mex_bundle_1_XABeUVWeAeB (mex_bundle_1_XABeUVWeAeB.c:72-337) at the current
+ * (a, b), followed by the fix_* zeroing of bundle_euclid.m:140-154.  Results stay on the
+ * device; the getters copy what the caller asks for (NULL = skip). */
+int  vlg_ba_stage1(vlg_ba_ctx *ctx, double *cost);
+int  vlg_ba_get_blocks(vlg_ba_ctx *ctx, double *U, double *V, double *W, double *eA, double *eB);
+/* Per-observation X_hat (2), A (2 x num_a), B (2 x 3), e (2) in list order: recomputed by a
+ * diagnostic launch of the same device code (mex1 outputs pout[0..3] restricted to visible cells). */
+int  vlg_ba_get_jacobians(vlg_ba_ctx *ctx, double *X_hat, double *A, double *B, double *e);
+
+/* Stage 2 == damping + pinv(V*) + Y + mex_bundle_2_Se_ (bundle_euclid.m:162-192,
+ * mex_bundle_2_Se_.c:72-155) for the given lambda, then da (bundle_euclid.m:193).
+ * S (num_a*m)^2 is only formed (and returned) on the Cholesky path. */
+int  vlg_ba_stage2(vlg_ba_ctx *ctx, double lambda);
+int  vlg_ba_get_reduced(vlg_ba_ctx *ctx, double *Vinv, double *S, double *e_, double *da);
+/* Teacher forcing: overwrite da before stage 3 (e.g. with the oracle's pinv(S)*e_). */
+int  vlg_ba_set_da(vlg_ba_ctx *ctx, const double *da);
+
+/* Stage 3 == mex_bundle_3_db_new (mex_bundle_3_db_new.c:100-166) + the new cost
+ * (bundle_euclid.m:205-210) + dp'(lambda dp + g) (bundle_euclid.m:215-217). */
+int  vlg_ba_stage3(vlg_ba_ctx *ctx, double lambda, double *new_cost, double *denom);
+int  vlg_ba_get_update(vlg_ba_ctx *ctx, double *db, double *a_new, double *b_new);
+
+/* One whole trip of the while loop, bundle_euclid.m:139-241, including accept/reject and
+ * the lambda/nu update; state advances inside the context. */
+int  vlg_ba_trial_step(vlg_ba_ctx *ctx, vlg_ba_trial_info *info);
+
+/* The whole of bundle_euclid.m:111-267 on the device.  error_ must hold max_iter doubles;
+ * *n_error receives its length (may be 0: bundle_euclid.m:119).  Outputs as :256-267;
+ * Xe4 (n doubles or NULL) is Xe(4,:) passed through. */
+int  vlg_ba_solve(vlg_ba_ctx *ctx, double *K_, double *Te_, double *w_, double *Xe_,
+                  const double *Xe4, double *error_, int *n_error);
+
+/* End-to-end convenience used by the mex wrapper and bench.py's e2e leg: host buffers in,
+ * one LM trial step, host buffers out (H2D of a, b and the observation list, D2H of a_new,
+ * b_new and the costs all inside the call). */
+int  vlg_ba_trial_step_host(vlg_ba_ctx *ctx, const double *a, const double *b,
+                            const double *obs_xy, double lambda,
+                            double *a_new, double *b_new, vlg_ba_trial_info *info);
+
+/* Introspection for tests and benches. */
+int  vlg_ba_get_schur_structure(vlg_ba_ctx *ctx, int64_t *n_blocks, int32_t *blk_j, int32_t *blk_k);
+int64_t vlg_ba_kernel_launches(const vlg_ba_ctx *ctx);
+/* Average device time (ms) and launch count of a named kernel group since the last reset:
+ * "stage1_cam", "stage1_pt", "vinv", "schur", "chol", "pcg_sweep_pt", "pcg_sweep_cam", "stage3". */
+int  vlg_ba_kernel_time(vlg_ba_ctx *ctx, const char *name, double *avg_ms, int64_t *count);
+int  vlg_ba_reset_timers(vlg_ba_ctx *ctx, int enable);
+/* CUDA-event stopwatch on the context's own stream (bench.py times its region with it). */
+int  vlg_ba_timer_start(vlg_ba_ctx *ctx);
+int  vlg_ba_timer_stop(vlg_ba_ctx *ctx, float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

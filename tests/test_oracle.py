@@ -1,0 +1,130 @@
+"""CPU tests: the oracle (oracle_sparse.c + lm.py) against the golden vectors produced by the
+reference's own C (tests/golden/make_golden.py) and, where /root/reference is present, against
+the reference build itself."""
+import os
+
+import numpy as np
+import pytest
+
+from bundleadjustmentmatlab_b200 import synth
+from oracle import lm
+
+from common import golden_names, golden_opts, load_golden, oracle_options
+
+HAVE_REF = os.path.exists(os.path.join(os.path.dirname(lm.__file__), "_ref", "libvlgref.so"))
+
+
+def _ab(g):
+    return np.array(g["t_a"][0]), np.array(g["t_b"][0])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_sparse_oracle_stage1_bitwise_vs_golden(name):
+    g = load_golden(name)
+    a, b = _ab(g)
+    obs = lm.ObsList(int(g["m"]), int(g["n"]), g["obs_xy"], g["obs_pt"], g["obs_cam"])
+    s1 = lm.stage1_sparse(g["K"], a, b, obs)
+    for k in ("X_hat", "A", "B", "e"):
+        assert np.array_equal(s1[k], g[k]), k
+    o = oracle_options(g)
+    t = lm.lm_trial(g["K"], a, b, obs, 1e-3, o, backend="sparse")
+    for k in ("U", "V", "eA", "eB", "W", "Vinv", "S", "e_"):
+        assert np.array_equal(t["blocks"][k], g[k]), k
+    assert np.array_equal(t["da"], g["t_da"][0])
+    assert np.array_equal(t["db"], g["t_db"][0])
+    assert np.array_equal(t["a_new"], g["t_a_new"][0])
+    assert np.array_equal(t["b_new"], g["t_b_new"][0])
+    # the two costs are BLAS dot products in the reference: tolerance, not bits
+    assert abs(t["old"] - g["t_old"][0]) <= 1e-13 * g["t_old"][0]
+    assert abs(t["new"] - g["t_new"][0]) <= 1e-13 * g["t_new"][0]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_sparse_oracle_teacher_forced_trajectory(name):
+    g = load_golden(name)
+    o = oracle_options(g)
+    obs = lm.ObsList(int(g["m"]), int(g["n"]), g["obs_xy"], g["obs_pt"], g["obs_cam"])
+    for k in range(len(g["t_lam"])):
+        t = lm.lm_trial(g["K"], g["t_a"][k], g["t_b"][k], obs, float(g["t_lam"][k]), o, backend="sparse")
+        assert abs(t["new"] - g["t_new"][k]) <= 1e-12 * g["t_new"][k]
+        assert bool((t["old"] - t["new"]) > 0) == bool(g["t_accept"][k])
+
+
+def test_visibility_compaction_order():
+    P = synth.make_problem(5, 40, 150, seed=3)
+    x, vis = P.dense()
+    obs = lm.ObsList.from_dense(np.asfortranarray(x[:2]), vis)
+    assert np.array_equal(obs.pt, P.obs_pt) and np.array_equal(obs.cam, P.obs_cam)
+    assert np.array_equal(obs.xy, P.obs_xy)
+    key = obs.pt.astype(np.int64) + P.n * obs.cam.astype(np.int64)
+    assert np.all(np.diff(key) > 0)
+
+
+def test_pinv_matlab_semantics():
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(6, 6)); A = A @ A.T
+    A[2, :] = 0; A[:, 2] = 0
+    P = lm.pinv_matlab(A)
+    # an SVD-based pinv leaves rounding-level dust on the structurally zero row/column
+    assert np.all(np.abs(P[2, :]) < 1e-12) and np.all(np.abs(P[:, 2]) < 1e-12)
+    keep = [0, 1, 3, 4, 5]
+    assert np.allclose(P[np.ix_(keep, keep)], np.linalg.inv(A[np.ix_(keep, keep)]), rtol=1e-9)
+    assert np.all(lm.pinv_matlab(np.zeros((3, 3))) == 0)
+    V = np.zeros((2, 3, 3)); V[1] = np.diag([1.0, 2.0, 4.0])
+    Vi = lm.pinv3_batch(V)
+    assert np.all(Vi[0] == 0) and np.allclose(Vi[1], np.diag([1.0, 0.5, 0.25]))
+
+
+def test_camera_at_identity_has_zero_rotation_jacobian():
+    """theta < 1e-6 branch of vl_rodrigues: w = 0 and w + h*e_k both give R = I (quirk Q2)."""
+    P = synth.make_problem(4, 30, 100, seed=5)
+    a = np.vstack([P.w, P.Te]); b = P.Xe[:3].copy()
+    obs = lm.ObsList(P.m, P.n, P.obs_xy, P.obs_pt, P.obs_cam)
+    s1 = lm.stage1_sparse(P.K, a, b, obs)
+    cam0 = obs.cam == 0
+    assert cam0.any()
+    assert np.all(s1["A"][cam0][:, 0:3, :] == 0)
+    assert np.all(s1["U"][0][0:3, :] == 0) and np.all(s1["U"][0][:, 0:3] == 0)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("opts", [("fix_calibration",), (), ("fix_principal",), ("fix_calibration", "fix_motion")])
+def test_sparse_oracle_bitwise_vs_reference_build(opts):
+    P = synth.make_problem(7, 90, 420, seed=21)
+    x, vis = P.dense()
+    o = lm.parse_options(P.m, P.n, x, list(opts) + ["visibility", vis])
+    nk = o["num_variableK"]
+    a = np.zeros((6 + nk, P.m)); a[0:3] = P.w; a[3:6] = P.Te
+    if nk == 1:
+        a[6] = P.K[0]
+    elif nk == 4:
+        a[6:10] = P.K
+    b = P.Xe[:3].copy()
+    X = np.asfortranarray(x[:2])
+    obs = lm.ObsList.from_dense(X, vis)
+    t1 = lm.lm_trial(P.K, a, b, obs, 1e-3, o, backend="ref", dense=(X, np.asfortranarray(vis)))
+    t2 = lm.lm_trial(P.K, a, b, obs, 1e-3, o, backend="sparse")
+    for k in ("U", "V", "eA", "eB", "Vinv", "S", "e_"):
+        assert np.array_equal(t1["blocks"][k], t2["blocks"][k]), k
+    for k in ("da", "db", "a_new", "b_new"):
+        assert np.array_equal(t1[k], t2[k]), k
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference build (oracle/_ref) not present")
+def test_golden_files_match_a_fresh_reference_run():
+    g = load_golden("euclid_fixcal")
+    res = lm.bundle_euclid(g["K"], g["Te"], g["w"], g["Xe"], g["x"], *golden_opts(g), backend="ref")
+    assert np.array_equal(res.error_, g["error_"])
+
+
+def test_cpu_port_pcg_step_matches_exact_solve():
+    """The PCG port used as CPU arm for the large configs agrees with the pinv-based trial."""
+    P = synth.make_problem(8, 300, 1500, seed=9)
+    a = np.vstack([P.w, P.Te]); b = P.Xe[:3].copy()
+    obs = lm.ObsList(P.m, P.n, P.obs_xy, P.obs_pt, P.obs_cam)
+    o = lm.parse_options(P.m, P.n, np.ones((2, 1, 1)), ["fix_calibration", "visibility", np.zeros(0)])
+    t = lm.lm_trial(P.K, a, b, obs, 1e-3, o, backend="sparse", all_rows=True)
+    p = lm.trial_step_pcg(P.K, a, b, obs, 1e-3, pcg_rtol=1e-12)
+    assert abs(p["old"] - t["old"]) <= 1e-12 * t["old"]
+    assert abs(p["new"] - t["new"]) <= 1e-9 * t["new"]
+    assert abs(p["denom"] - t["denom"]) <= 1e-8 * abs(t["denom"])
