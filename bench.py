@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="scale points/observations per rank")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--solver", default="auto", choices=["auto", "chol", "pcg"])
-    ap.add_argument("--pcg-rtol", type=float, default=1e-10)
+    ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--rtable", default="host", choices=["host", "device"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -211,17 +211,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm
+    # ---- device-resident arm.  The steps follow the reference's LM loop (bundle_euclid.m:120-249);
+    # when its stop rule ends a solve, the next step starts a new solve from the initial estimate.
+    def lm_step():
+        if not ctx.lm_continue():
+            ctx.lm_reset(a0, b0)
+        return ctx.trial_step()
+
     infos = []
     for _ in range(args.warmup):
-        ctx.trial_step()
+        lm_step()
     barrier()
     ctx.reset_timers(True)
     l0 = ctx.kernel_launches
     with ClockSampler(local) as clk:
         ctx.timer_start()
         for _ in range(args.steps):
-            infos.append(ctx.trial_step())
+            infos.append(lm_step())
         ms = ctx.timer_stop()
         barrier()
     launches = ctx.kernel_launches - l0
@@ -247,16 +253,31 @@ def run_ours(args):
         ha, hb, hxy = pin(a0.shape), pin(b0.shape), pin(P.obs_xy.shape)
         ha_new, hb_new = pin(a0.shape), pin(b0.shape)
         ha[:] = a0; hb[:] = b0; hxy[:] = P.obs_xy
-        lam = 1e-3
+        st = {"lam": 1e-3, "nu": 2.0, "it": 1, "it2": 0, "err": []}
+        nvis = nobs_total
 
         def one():
-            nonlocal lam
-            info = ctx.trial_step_host(ha, hb, hxy, lam, ha_new, hb_new)
+            # host-side LM control, as bundle_euclid.m drives its mex calls (:120-123, :218-241)
+            e = st["err"]
+            go = st["it"] < 20 and st["it2"] < 10 and (st["it"] < 3 or (
+                e[st["it"] - 1] > 1e-20 and e[st["it"] - 2] - e[st["it"] - 1] > 1e-3 * e[st["it"] - 2]))
+            if not go:
+                ha[:] = a0; hb[:] = b0
+                st.update(lam=1e-3, nu=2.0, it=1, it2=0, err=[])
+            info = ctx.trial_step_host(ha, hb, hxy, st["lam"], ha_new, hb_new)
             if info["accepted"]:
                 ha[:] = ha_new; hb[:] = hb_new
-                lam = lam * max(1.0 / 3.0, 1 - (2 * info["rho"] - 1) ** 3)
+                st["lam"] *= max(1.0 / 3.0, 1 - (2 * info["rho"] - 1) ** 3)
+                st["nu"] = 2.0
+                e = st["err"]
+                while len(e) < st["it"] + 1:
+                    e.append(0.0)
+                e[st["it"] - 1] = info["old_cost"] / nvis
+                st["it"] += 1
+                e[st["it"] - 1] = info["new_cost"] / nvis
+                st["it2"] = 0
             else:
-                lam = lam * 2
+                st["lam"] *= st["nu"]; st["nu"] *= 2; st["it2"] += 1
         for _ in range(args.warmup):
             one()
         barrier()
@@ -320,6 +341,8 @@ def run_ours(args):
             "jacobian_schur_obs_per_sec": (nobs_total * args.steps / (js * 1e-3)) if js > 0 else None,
             "pcg_iters_mean": float(np.mean([i["pcg_iters"] for i in infos])),
             "accepted_steps": int(sum(i["accepted"] for i in infos)),
+            "pcg_iters": [int(i["pcg_iters"]) for i in infos],
+            "lambdas": [float("%.3g" % i["lambda_used"]) for i in infos],
             "cost_first_last": [infos[0]["old_cost"], infos[-1]["new_cost"]],
             "kernels": per_kernel,
         }

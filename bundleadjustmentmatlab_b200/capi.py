@@ -57,7 +57,7 @@ SYMBOLS = [
     "vlg_ba_stage1", "vlg_ba_get_blocks", "vlg_ba_get_jacobians", "vlg_ba_stage2", "vlg_ba_get_reduced",
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
-    "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop",
+    "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
 ]
 
 
@@ -250,6 +250,14 @@ class Context:
         self._ck(self._L.vlg_ba_trial_step_host(self._h, _d(a), _d(b), _d(obs_xy), C.c_double(lam), _d(a_new), _d(b_new),
                                                 C.byref(info)))
         return info.as_dict()
+
+    def lm_reset(self, a=None, b=None):
+        a = None if a is None else _c(a)
+        b = None if b is None else _c(b)
+        self._ck(self._L.vlg_ba_lm_reset(self._h, _d(a), _d(b)))
+
+    def lm_continue(self) -> bool:
+        return bool(self._L.vlg_ba_lm_continue(self._h))
 
     def solve(self, Xe4=None):
         m, n = self.m, self.n

@@ -116,6 +116,7 @@ struct vlg_ba_ctx {
     // LM state
     double lambda = 1e-3, nu = 2.0;
     int iter = 1, iter2 = 0;
+    std::vector<double> err_hist;     // error_ of bundle_euclid.m:119,229-231
     bool s1_valid = false, s2_valid = false, s3_valid = false;
     double old_cost = 0.0;
     double s2_lambda = 0.0;
@@ -457,6 +458,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->have_problem = true;
     ctx->lambda = o.lambda0; ctx->nu = o.nu0; ctx->iter = 1; ctx->iter2 = 0;
+    ctx->err_hist.clear();
     ctx->s1_valid = ctx->s2_valid = ctx->s3_valid = false;
     return VLG_BA_OK;
 }

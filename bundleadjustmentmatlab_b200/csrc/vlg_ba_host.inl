@@ -247,6 +247,9 @@ int do_trial(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
         const double f = 1 - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
         ctx->lambda = lambda * std::max(1.0 / 3.0, f);                      // :227
         ctx->nu = 2.0;
+        if ((int)ctx->err_hist.size() < ctx->iter + 1) ctx->err_hist.resize((size_t)ctx->iter + 1, 0.0);
+        ctx->err_hist[ctx->iter - 1] = old_cost / ctx->num_vis;             // :219-220,229-231
+        ctx->err_hist[ctx->iter] = new_cost / ctx->num_vis;
         ctx->iter += 1;
         ctx->iter2 = 0;
         ctx->s1_valid = false;
@@ -273,7 +276,7 @@ void vlg_ba_opts_default(vlg_ba_opts* o)
     o->num_variableK = 4;
     o->lambda0 = 0.001; o->nu0 = 2.0; o->max_iter = 20; o->max_iter2 = 10; o->rel_tol = 1e-3; o->abs_tol = 1e-20;
     o->backsub_all_rows = 0;
-    o->solver = VLG_BA_SOLVER_AUTO; o->chol_max_cams = 300; o->pcg_rtol = 1e-10; o->pcg_max_iter = 1000;
+    o->solver = VLG_BA_SOLVER_AUTO; o->chol_max_cams = 300; o->pcg_rtol = 1e-8; o->pcg_max_iter = 1000;
     o->rtable = VLG_BA_RTABLE_HOST_LIBM; o->order = VLG_BA_ORDER_CHUNKED; o->device = -1; o->verbose = 0;
 }
 
@@ -547,28 +550,42 @@ int vlg_ba_trial_step(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
     return do_trial(ctx, info);
 }
 
+int vlg_ba_lm_reset(vlg_ba_ctx* ctx, const double* a, const double* b)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    if (a || b) CHK(vlg_ba_set_state(ctx, a, b, -1.0, -1.0));
+    ctx->lambda = ctx->opt.lambda0; ctx->nu = ctx->opt.nu0; ctx->iter = 1; ctx->iter2 = 0;    // bundle_euclid.m:111-119
+    ctx->err_hist.clear();
+    return VLG_BA_OK;
+}
+
+int vlg_ba_lm_continue(const vlg_ba_ctx* ctx)
+{
+    if (!ctx || !ctx->have_problem) return 0;
+    const vlg_ba_opts& o = ctx->opt;
+    const int it = ctx->iter;
+    bool go = it < o.max_iter && ctx->iter2 < o.max_iter2;                                      // :120-123
+    if (go && it >= 3) {
+        const std::vector<double>& err = ctx->err_hist;
+        go = err[it - 1] > o.abs_tol && (err[it - 2] - err[it - 1]) > o.rel_tol * err[it - 2];
+    }
+    return go ? 1 : 0;
+}
+
 int vlg_ba_solve(vlg_ba_ctx* ctx, double* K_, double* Te_, double* w_, double* Xe_, const double* Xe4, double* error_,
                  int* n_error)
 {
     if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
     const vlg_ba_opts& o = ctx->opt;
-    std::vector<double> err((size_t)std::max(o.max_iter, 2) + 2, 0.0);
-    bool any = false;
-    ctx->lambda = o.lambda0; ctx->nu = o.nu0; ctx->iter = 1; ctx->iter2 = 0;     // bundle_euclid.m:111-119
-    for (;;) {
+    CHK(vlg_ba_lm_reset(ctx, nullptr, nullptr));
+    while (vlg_ba_lm_continue(ctx)) {
         const int it = ctx->iter;
-        bool go = it < o.max_iter && ctx->iter2 < o.max_iter2;                   // :120-123
-        if (go && it >= 3) go = err[it - 1] > o.abs_tol && (err[it - 2] - err[it - 1]) > o.rel_tol * err[it - 2];
-        if (!go) break;
         vlg_ba_trial_info info;
         CHK(do_trial(ctx, &info));
-        if (info.accepted) {
-            err[it - 1] = info.old_cost / ctx->num_vis;                          // :219-220,229-231
-            err[it] = info.new_cost / ctx->num_vis;
-            any = true;
-            if (o.verbose) printf("iter %d: error= %.5g -> %.5g\n", it, err[it - 1], err[it]);
-        }
+        if (info.accepted && o.verbose) printf("iter %d: error= %.5g -> %.5g\n", it, ctx->err_hist[it - 1], ctx->err_hist[it]);
     }
+    const bool any = !ctx->err_hist.empty();
+    const std::vector<double>& err = ctx->err_hist;
     const int m = ctx->m, n = ctx->n, na = ctx->na;
     std::vector<double> a((size_t)na * m), b((size_t)3 * n);
     CHK(vlg_ba_get_state(ctx, a.data(), b.data(), nullptr, nullptr, nullptr, nullptr));

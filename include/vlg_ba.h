@@ -59,7 +59,7 @@ typedef struct vlg_ba_opts {
     int    backsub_all_rows;  /* 0 = reference behaviour: only 6 camera rows enter db (mex_bundle_3_db_new.c:113-120) */
     int    solver;            /* VLG_BA_SOLVER_*: dense Cholesky of S, or block-Jacobi PCG on the implicit S */
     int    chol_max_cams;     /* AUTO picks Cholesky when m <= this (default 300) */
-    double pcg_rtol;          /* relative residual stop for PCG (default 1e-10) */
+    double pcg_rtol;          /* relative residual stop for PCG (default 1e-8: one-step cost within ~1e-12 of the exact solve) */
     int    pcg_max_iter;      /* default 1000 */
     int    rtable;            /* VLG_BA_RTABLE_*: who evaluates vl_rodrigues' sin/cos (host libm = bit parity with the CPU reference) */
     int    order;             /* VLG_BA_ORDER_*: REFERENCE = U/eA accumulated in the reference's exact order (slow), CHUNKED = fixed 256-observation chunks (default) */
@@ -148,6 +148,12 @@ int  vlg_ba_get_update(vlg_ba_ctx *ctx, double *db, double *a_new, double *b_new
 /* One whole trip of the while loop, bundle_euclid.m:139-241, including accept/reject and
  * the lambda/nu update; state advances inside the context. */
 int  vlg_ba_trial_step(vlg_ba_ctx *ctx, vlg_ba_trial_info *info);
+
+/* The loop control of bundle_euclid.m:111-123 for callers that drive vlg_ba_trial_step
+ * themselves: vlg_ba_lm_reset() puts the state back to (a, b, lambda0, nu0, iter=1, iter2=0,
+ * error_=[]) (a, b may be NULL = keep), vlg_ba_lm_continue() evaluates the while condition. */
+int  vlg_ba_lm_reset(vlg_ba_ctx *ctx, const double *a, const double *b);
+int  vlg_ba_lm_continue(const vlg_ba_ctx *ctx);
 
 /* The whole of bundle_euclid.m:111-267 on the device.  error_ must hold max_iter doubles;
  * *n_error receives its length (may be 0: bundle_euclid.m:119).  Outputs as :256-267;
