@@ -176,6 +176,7 @@ def algorithmic_bytes(name, P, na=6):
         "schur": no * (W + 4) + n * (72 + 24) + m * 8 * (na * (na + 1) // 2 + na),
         "stage3": no * (W + 4 + 4 + 16 + 4 + 4 + 8) + n * (72 + 24 + 24 + 24 + 24 + 8) + m * (72 + 8 * na + 32),
         "vinv": n * (72 + 72) + m * 2 * 8 * na * na,
+        "w_copy": no * (2 * W + 4),
     }
     return table.get(name)
 
@@ -232,7 +233,8 @@ def run_ours(args):
         barrier()
     launches = ctx.kernel_launches - l0
     groups = {}
-    for g in ("stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt", "pcg_sweep_cam", "stage3"):
+    for g in ("stage1_cam", "stage1_pt", "w_copy", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt", "pcg_sweep_cam",
+              "pcg_update", "stage3"):
         avg, cnt = ctx.kernel_time(g)
         groups[g] = {"avg_ms": avg, "count": cnt, "total_ms": avg * cnt}
     ctx.reset_timers(False)

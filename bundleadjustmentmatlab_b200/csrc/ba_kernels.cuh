@@ -619,9 +619,10 @@ __global__ void k_sweep_pt(int n, const int* __restrict__ pt_ptr, const int* __r
         }
     }
     const double* Vi = Vinv + (size_t)9 * i;
-    t_out[(size_t)3 * i] = Vi[0] * s0 + Vi[3] * s1 + Vi[6] * s2;
-    t_out[(size_t)3 * i + 1] = Vi[1] * s0 + Vi[4] * s1 + Vi[7] * s2;
-    t_out[(size_t)3 * i + 2] = Vi[2] * s0 + Vi[5] * s1 + Vi[8] * s2;
+    t_out[(size_t)4 * i] = Vi[0] * s0 + Vi[3] * s1 + Vi[6] * s2;      // padded to 4 doubles per point
+    t_out[(size_t)4 * i + 1] = Vi[1] * s0 + Vi[4] * s1 + Vi[7] * s2;
+    t_out[(size_t)4 * i + 2] = Vi[2] * s0 + Vi[5] * s1 + Vi[8] * s2;
+    t_out[(size_t)4 * i + 3] = 0.0;
 }
 
 // sweep 2, camera-keyed: chunk partial of sum_i W_ij t_i (one warp per chunk)
@@ -640,7 +641,7 @@ k_sweep_cam(int nchunks, const int* __restrict__ chunk_begin, const int* __restr
     for (int r = 0; r < NA; r++) acc[r] = 0.0;
     for (int o = chunk_begin[c] + lane; o < chunk_end[c]; o += 32) {
         const int i = obs_pt[o];
-        const double t0 = __ldg(t_in + (size_t)3 * i), t1 = __ldg(t_in + (size_t)3 * i + 1), t2 = __ldg(t_in + (size_t)3 * i + 2);
+        const double t0 = __ldg(t_in + (size_t)4 * i), t1 = __ldg(t_in + (size_t)4 * i + 1), t2 = __ldg(t_in + (size_t)4 * i + 2);
         const double* Wo = W + (size_t)3 * NA * o;
 #pragma unroll
         for (int r = 0; r < NA; r++) acc[r] += Wo[r] * t0 + Wo[r + NA] * t1 + Wo[r + 2 * NA] * t2;

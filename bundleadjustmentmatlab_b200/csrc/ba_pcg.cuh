@@ -1,0 +1,297 @@
+// ba_pcg.cuh -- the implicit-Schur PCG iteration, tiled for HBM streaming.
+//
+// One PCG iteration reads every W block twice (point-keyed sweep, camera-keyed sweep); at
+// Venice shape that is 2 x 720 MB and nothing else of comparable size, so the iteration is
+// HBM-bound and each sweep is built as a pure stream:
+//   * W is kept in BOTH orders: C-order (written by stage 1) and a P-order copy Wp made once per
+//     LM trial step by k_w_to_porder, so that each sweep reads one contiguous range per CTA;
+//   * a CTA owns one tile (<= 256 observations: whole points for sweep 1, one chunk of one camera
+//     for sweep 2) and pulls it into shared memory with ONE TMA bulk copy
+//     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), several CTAs per SM keep
+//     >100 KB per SM in flight; the small gathers (p_j, t_i) overlap the bulk copy;
+//   * the 6m-vector algebra of an iteration is one cooperative kernel (two grid syncs).
+// All reductions have a fixed shape (in-order per point, xor tree per warp, in-order over warps
+// and chunks), so results are bit-reproducible run to run.
+#pragma once
+#include "ba_kernels.cuh"
+#include <cooperative_groups.h>
+
+namespace vlgba {
+
+namespace cg = cooperative_groups;
+
+constexpr int kTileObs = 256;
+
+// ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier) -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+// global -> shared, contiguous, bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Pulls `count` doubles (a whole tile) into shared memory.  TMA when the tile is 16-byte
+// granular, otherwise (NA = 7 with an odd observation count/offset) a plain coalesced copy.
+template <int NW>
+__device__ __forceinline__ void load_tile(double* dst, const double* src, int nob, uint64_t* bar)
+{
+    const uint32_t bytes = (uint32_t)nob * NW * 8u;
+    const bool tma_ok = (bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u);
+    if (tma_ok) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(dst, src, bytes, bar);
+        }
+    } else {
+        for (int t = threadIdx.x; t < nob * NW; t += blockDim.x) dst[t] = src[t];
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void wait_tile(const double* src, int nob, uint64_t* bar)
+{
+    const uint32_t bytes = (uint32_t)nob * NW * 8u;
+    const bool tma_ok = (bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u);
+    if (tma_ok) mbar_wait(bar, 0);
+    else __syncthreads();
+}
+
+// ---- P-order copy of W: Wp[q] = W[pt_obs[q]] ---------------------------------------------------
+template <int NA>
+__global__ void __launch_bounds__(256) k_w_to_porder(int64_t nobs, const int* __restrict__ pt_obs,
+                                                     const double* __restrict__ W, double* __restrict__ Wp)
+{
+    constexpr int NW = 3 * NA;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nobs * NW) return;
+    const int64_t q = t / NW;
+    const int k = (int)(t - q * NW);
+    Wp[t] = W[(size_t)pt_obs[q] * NW + k];
+}
+
+// ---- sweep 1, point-keyed: t_i = V*_i^-1 sum_j W_ij' p_j ---------------------------------------
+// tile = points [ptile_first[b], ptile_first[b+1]) with <= 256 observations in all
+template <int NA>
+__global__ void __launch_bounds__(kTileObs)
+k_sweep_pt_tiled(const int* __restrict__ ptile_first, const int* __restrict__ pt_ptr, const int* __restrict__ pt_cam,
+                 const double* __restrict__ Wp, const double* __restrict__ Vinv, const double* __restrict__ p,
+                 const int* __restrict__ done, double* __restrict__ t_out)
+{
+    constexpr int NW = 3 * NA;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* wt = reinterpret_cast<double*>(smraw);            // kTileObs x NW
+    double* sv = wt + kTileObs * NW;                          // kTileObs x 3
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sv + kTileObs * 3);
+    if (done && *done) return;
+    const int tid = threadIdx.x;
+    const int p0 = ptile_first[blockIdx.x], p1 = ptile_first[blockIdx.x + 1];
+    const int q0 = pt_ptr[p0];
+    const int nob = pt_ptr[p1] - q0;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    const double* src = Wp + (size_t)q0 * NW;
+    load_tile<NW>(wt, src, nob, bar);
+    double pj[NA];
+    if (tid < nob) {
+        const double* pp = p + (size_t)NA * pt_cam[q0 + tid];
+#pragma unroll
+        for (int r = 0; r < NA; r++) pj[r] = __ldg(pp + r);
+    }
+    wait_tile<NW>(src, nob, bar);
+    if (tid < nob) {
+        const double* w = wt + tid * NW;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < NA; r++) {
+            s0 += w[r] * pj[r]; s1 += w[r + NA] * pj[r]; s2 += w[r + 2 * NA] * pj[r];
+        }
+        sv[tid * 3] = s0; sv[tid * 3 + 1] = s1; sv[tid * 3 + 2] = s2;
+    }
+    __syncthreads();
+    if (tid < p1 - p0) {
+        const int i = p0 + tid;
+        const int o0 = pt_ptr[i] - q0, o1 = pt_ptr[i + 1] - q0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int o = o0; o < o1; o++) { s0 += sv[o * 3]; s1 += sv[o * 3 + 1]; s2 += sv[o * 3 + 2]; }
+        const double* Vi = Vinv + (size_t)9 * i;
+        // t is stored padded to 4 doubles per point: the camera sweep gathers one aligned
+        // 32-byte sector per observation
+        double4 tv;
+        tv.x = Vi[0] * s0 + Vi[3] * s1 + Vi[6] * s2;
+        tv.y = Vi[1] * s0 + Vi[4] * s1 + Vi[7] * s2;
+        tv.z = Vi[2] * s0 + Vi[5] * s1 + Vi[8] * s2;
+        tv.w = 0.0;
+        reinterpret_cast<double4*>(t_out)[i] = tv;
+    }
+}
+
+// ---- sweep 2, camera-keyed: chunk partial of sum_i W_ij t_i ------------------------------------
+// one CTA per chunk (<= 256 observations of one camera, contiguous in C-order W)
+template <int NA>
+__global__ void __launch_bounds__(kTileObs)
+k_sweep_cam_tiled(const int* __restrict__ chunk_begin, const int* __restrict__ chunk_end, const int* __restrict__ obs_pt,
+                  const double* __restrict__ W, const double* __restrict__ t_in, const int* __restrict__ done,
+                  double* __restrict__ part /* [nchunks][NA] */)
+{
+    constexpr int NW = 3 * NA;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* wt = reinterpret_cast<double*>(smraw);            // kTileObs x NW
+    double* red = wt + kTileObs * NW;                         // 8 warps x NA
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 8 * NA);
+    if (done && *done) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int beg = chunk_begin[blockIdx.x];
+    const int nob = chunk_end[blockIdx.x] - beg;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    const double* src = W + (size_t)beg * NW;
+    load_tile<NW>(wt, src, nob, bar);
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    if (tid < nob) {
+        const int i = obs_pt[beg + tid];
+        const double2 ta = __ldg(reinterpret_cast<const double2*>(t_in) + 2 * (size_t)i);
+        const double2 tb = __ldg(reinterpret_cast<const double2*>(t_in) + 2 * (size_t)i + 1);
+        t0 = ta.x; t1 = ta.y; t2 = tb.x;
+    }
+    wait_tile<NW>(src, nob, bar);
+    double acc[NA];
+#pragma unroll
+    for (int r = 0; r < NA; r++) acc[r] = 0.0;
+    if (tid < nob) {
+        const double* w = wt + tid * NW;
+#pragma unroll
+        for (int r = 0; r < NA; r++) acc[r] = w[r] * t0 + w[r + NA] * t1 + w[r + 2 * NA] * t2;
+    }
+#pragma unroll
+    for (int r = 0; r < NA; r++) {
+        const double v = warp_sum(acc[r]);
+        if (lane == 0) red[warp * NA + r] = v;
+    }
+    __syncthreads();
+    if (tid < NA) {
+        double s = 0.0;
+        const int nw = (nob + 31) >> 5;
+        for (int w = 0; w < nw; w++) s += red[w * NA + tid];
+        part[(size_t)NA * blockIdx.x + tid] = s;
+    }
+}
+
+// ---- the vector algebra of one PCG iteration, one cooperative kernel ---------------------------
+// one thread per camera (its NA unknowns stay in registers through the three phases):
+//   q = U* p - W V*^-1 W' p ;  alpha = r'z / p'q ;  x += alpha p ;  r -= alpha q ;
+//   z = M^-1 r ;  beta = r'z_new / r'z ;  p = z + beta p ;  stop when |r| <= rtol |r0|
+__device__ __forceinline__ double block_sum_fixed(double v, double* sh)
+{
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nw; w++) s += sh[w];
+    return s;   // every thread, same order
+}
+
+template <int NA>
+__global__ void __launch_bounds__(128)
+k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __restrict__ qpart,
+                  const double* __restrict__ wq, const double* __restrict__ Ud, const double* __restrict__ Minv,
+                  double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                  PcgScalars* __restrict__ sc, double* __restrict__ blkpart /* 3 * gridDim.x */, double rtol)
+{
+    __shared__ double sh[32];
+    cg::grid_group grid = cg::this_grid();
+    if (sc->done) return;                         // uniform: sc is only written after the last grid sync
+    const double rz = sc->rz, r0n2 = sc->r0n2;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = gridDim.x;
+    double pj[NA], qj[NA], rj[NA], zj[NA];
+    double pq = 0.0;
+    if (j < m) {
+#pragma unroll
+        for (int k = 0; k < NA; k++) pj[k] = p[(size_t)NA * j + k];
+#pragma unroll
+        for (int row = 0; row < NA; row++) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < NA; c++) v += Ud[(size_t)NA * NA * j + row + NA * c] * pj[c];
+            double w = 0.0;
+            if (wq) w = wq[(size_t)NA * j + row];
+            else for (int c = cam_chunk_ptr[j]; c < cam_chunk_ptr[j + 1]; c++) w += qpart[(size_t)NA * c + row];
+            qj[row] = v - w;
+            pq += pj[row] * qj[row];
+        }
+    }
+    pq = block_sum_fixed(pq, sh);
+    if (threadIdx.x == 0) blkpart[blockIdx.x] = pq;
+    grid.sync();
+    pq = 0.0;
+    for (int b = 0; b < nb; b++) pq += __ldcg(blkpart + b);
+    if (!(pq > 0.0)) {                            // breakdown: every thread sees the same pq
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->done = 2; sc->pq = pq; }
+        return;
+    }
+    const double alpha = rz / pq;
+    double rzn = 0.0, rr = 0.0;
+    if (j < m) {
+#pragma unroll
+        for (int k = 0; k < NA; k++) {
+            x[(size_t)NA * j + k] += alpha * pj[k];
+            rj[k] = r[(size_t)NA * j + k] - alpha * qj[k];
+            r[(size_t)NA * j + k] = rj[k];
+            rr += rj[k] * rj[k];
+        }
+#pragma unroll
+        for (int row = 0; row < NA; row++) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < NA; c++) v += Minv[(size_t)NA * NA * j + row + NA * c] * rj[c];
+            zj[row] = v;
+            rzn += rj[row] * v;
+        }
+    }
+    rzn = block_sum_fixed(rzn, sh);
+    rr = block_sum_fixed(rr, sh);
+    if (threadIdx.x == 0) { blkpart[nb + 2 * blockIdx.x] = rzn; blkpart[nb + 2 * blockIdx.x + 1] = rr; }
+    grid.sync();
+    rzn = 0.0; rr = 0.0;
+    for (int b = 0; b < nb; b++) { rzn += __ldcg(blkpart + nb + 2 * b); rr += __ldcg(blkpart + nb + 2 * b + 1); }
+    const double beta = rzn / rz;
+    if (j < m) {
+#pragma unroll
+        for (int k = 0; k < NA; k++) p[(size_t)NA * j + k] = zj[k] + beta * pj[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rz = rzn; sc->rn2 = rr; sc->pq = pq; sc->iters += 1;
+        if (rr <= rtol * rtol * r0n2) sc->done = 1;
+    }
+}
+
+}  // namespace vlgba

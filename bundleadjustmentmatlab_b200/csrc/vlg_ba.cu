@@ -6,6 +6,7 @@
 // that the single-GPU library has no NCCL dependency.
 #include "../../include/vlg_ba.h"
 #include "ba_kernels.cuh"
+#include "ba_pcg.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -58,9 +59,9 @@ bool nccl_load()
 
 char g_create_error[512] = "";
 
-enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_COUNT };
+enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_COUNT };
 const char* kTimerNames[T_COUNT] = {"stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt",
-                                    "pcg_sweep_cam", "stage3"};
+                                    "pcg_sweep_cam", "stage3", "pcg_update", "w_copy"};
 
 struct KTimer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -97,6 +98,11 @@ struct vlg_ba_ctx {
     int *blk_j = nullptr, *blk_k = nullptr;
     int64_t* blk_ptr = nullptr;
     int2* pairs = nullptr;
+    int* ptile_first = nullptr;      // point tiles of the PCG point sweep
+    int nptiles = 0;
+    bool tiled_ok = false;           // every track fits one tile
+    double *Wp = nullptr, *blkpart = nullptr;
+    int coop_grid = 0;               // 0 = cooperative update kernel not usable
     // device: parameters
     double *K4 = nullptr, *a = nullptr, *b = nullptr, *a_new = nullptr, *b_new = nullptr, *rtab = nullptr, *rtab_new = nullptr;
     // device: stage 1 (red1 = U | eA | cost | nvis contiguous for one all-reduce)
@@ -408,6 +414,24 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         ctx->nblocks = 0; ctx->npairs = 0;
     }
 
+    // point tiles for the PCG point sweep: consecutive whole points, <= kTileObs observations
+    std::vector<int> ptile_first;
+    ctx->tiled_ok = !ctx->use_chol;
+    if (!ctx->use_chol) {
+        int64_t acc = 0;
+        int cntp = 0;
+        ptile_first.push_back(0);
+        for (int i = 0; i < n; i++) {
+            const int t = pt_ptr[i + 1] - pt_ptr[i];
+            if (t > kTileObs) { ctx->tiled_ok = false; break; }
+            if (acc + t > kTileObs || cntp == kTileObs) { ptile_first.push_back(i); acc = 0; cntp = 0; }
+            acc += t; cntp++;
+        }
+        ptile_first.push_back(n);
+        if (n == 0) ctx->tiled_ok = false;
+    }
+    ctx->nptiles = ctx->tiled_ok ? (int)ptile_first.size() - 1 : 0;
+
     const int NU = nu_of(na);
     // ---- device allocations
     CHK(dalloc(ctx, &ctx->obs_xy, (size_t)nobs)); CHK(dalloc(ctx, &ctx->pt_xy, (size_t)nobs));
@@ -431,10 +455,24 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(dalloc(ctx, &ctx->Sjj, (size_t)na * N)); CHK(dalloc(ctx, &ctx->ebar, N));
     CHK(dalloc(ctx, &ctx->Minv, (size_t)na * N)); CHK(dalloc(ctx, &ctx->da, N));
     CHK(dalloc(ctx, &ctx->pr, N)); CHK(dalloc(ctx, &ctx->pz, N)); CHK(dalloc(ctx, &ctx->pp, N)); CHK(dalloc(ctx, &ctx->pq, N));
-    CHK(dalloc(ctx, &ctx->wq, N)); CHK(dalloc(ctx, &ctx->tvec, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->qpart, (size_t)na * ctx->nchunks));
+    CHK(dalloc(ctx, &ctx->wq, N)); CHK(dalloc(ctx, &ctx->tvec, (size_t)4 * n)); CHK(dalloc(ctx, &ctx->qpart, (size_t)na * ctx->nchunks));
     CHK(dalloc(ctx, &ctx->pcg_sc, 1));
     CHK(dalloc(ctx, &ctx->db, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->denom_pt, (size_t)n));
     CHK(dalloc(ctx, &ctx->cost_obs, (size_t)nobs)); CHK(dalloc(ctx, &ctx->scal3, 4));
+    ctx->coop_grid = 0;
+    if (!ctx->use_chol) {
+        int coop = 0, nsm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+        const int g = cdiv(m, 128);
+        if (coop && g <= nsm * 8) ctx->coop_grid = g;
+        CHK(dalloc(ctx, &ctx->blkpart, (size_t)3 * std::max(g, 1)));
+        if (ctx->tiled_ok) {
+            CHK(dalloc(ctx, &ctx->Wp, (size_t)3 * na * nobs));
+            CHK(dalloc(ctx, &ctx->ptile_first, ptile_first.size()));
+            CHK(upload(ctx, ctx->ptile_first, ptile_first.data(), ptile_first.size()));
+        }
+    }
     if (ctx->use_chol) {
         CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));
         CHK(dalloc(ctx, &ctx->blk_j, (size_t)ctx->nblocks)); CHK(dalloc(ctx, &ctx->blk_k, (size_t)ctx->nblocks));
@@ -512,6 +550,11 @@ int run_stage1(vlg_ba_ctx* ctx, double* diag_X, double* diag_A, double* diag_B, 
         k_stage1_pt<NA><<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->pt_ptr, ctx->pt_cam, ctx->pt_xy, ctx->K4, ctx->a,
                                                                     ctx->b, ctx->rtab, ctx->opt.fix_structure, ctx->V, ctx->eB,
                                                                     ctx->cost_pt);
+        ctx->launches++;
+    }
+    if (ctx->tiled_ok && ctx->nobs > 0 && !diag) {
+        TimedScope ts(ctx, T_W_COPY);
+        k_w_to_porder<NA><<<cdiv(ctx->nobs * 3 * NA, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->pt_obs, ctx->W, ctx->Wp);
         ctx->launches++;
     }
     CU(cudaGetLastError());

@@ -82,28 +82,66 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         int* done = pcg_done_ptr(ctx);
         k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol);
         ctx->launches++;
+        CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(double) * (kTileObs * 3 * NA + kTileObs * 3) + 16)));
+        CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(double) * (kTileObs * 3 * NA + 8 * NA) + 16)));
         int launched = 0;
         const int batch = 8;
         while (launched < ctx->opt.pcg_max_iter) {
             for (int it = 0; it < batch && launched < ctx->opt.pcg_max_iter; it++, launched++) {
+                constexpr int NW = 3 * NA;
+                const size_t sm_pt = sizeof(double) * (kTileObs * NW + kTileObs * 3) + 16;
+                const size_t sm_cam = sizeof(double) * (kTileObs * NW + 8 * NA) + 16;
+                const bool tiled_cam = ctx->chunk_size <= kTileObs;
                 if (n > 0) {
                     TimedScope ts(ctx, T_SWEEP_PT);
-                    k_sweep_pt<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W, ctx->Vinv,
-                                                                         ctx->pp, done, ctx->tvec);
+                    if (ctx->tiled_ok) {
+                        k_sweep_pt_tiled<NA><<<ctx->nptiles, kTileObs, sm_pt, ctx->stream>>>(ctx->ptile_first, ctx->pt_ptr, ctx->pt_cam,
+                                                                                          ctx->Wp, ctx->Vinv, ctx->pp, done, ctx->tvec);
+                    } else {
+                        k_sweep_pt<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W,
+                                                                             ctx->Vinv, ctx->pp, done, ctx->tvec);
+                    }
                     ctx->launches++;
                 }
                 if (ctx->nchunks > 0) {
                     TimedScope ts(ctx, T_SWEEP_CAM);
-                    k_sweep_cam<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
-                        ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->tvec, done, ctx->qpart);
+                    if (tiled_cam) {
+                        k_sweep_cam_tiled<NA><<<ctx->nchunks, kTileObs, sm_cam, ctx->stream>>>(ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt,
+                                                                                             ctx->W, ctx->tvec, done, ctx->qpart);
+                    } else {
+                        k_sweep_cam<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+                            ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->tvec, done, ctx->qpart);
+                    }
                     ctx->launches++;
                 }
-                k_cam_sum_partials<<<cdiv((int64_t)m * NA, 128), 128, 0, ctx->stream>>>(m, NA, ctx->cam_chunk_ptr, ctx->qpart, done, ctx->wq);
-                ctx->launches++;
-                CHK(allreduce(ctx, ctx->wq, (size_t)N));
-                k_pcg_update<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Ud, ctx->Minv, ctx->wq, ctx->da, ctx->pr, ctx->pz, ctx->pp,
-                                                              ctx->pq, ctx->pcg_sc, rtol);
-                ctx->launches++;
+                const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0;
+                if (need_wq) {
+                    k_cam_sum_partials<<<cdiv((int64_t)m * NA, 128), 128, 0, ctx->stream>>>(m, NA, ctx->cam_chunk_ptr, ctx->qpart, done, ctx->wq);
+                    ctx->launches++;
+                    CHK(allreduce(ctx, ctx->wq, (size_t)N));
+                }
+                {
+                    TimedScope ts(ctx, T_PCG_UPDATE);
+                    if (ctx->coop_grid > 0) {
+                        int m_ = m;
+                        const int* ccp = ctx->cam_chunk_ptr;
+                        const double* qp = ctx->qpart;
+                        const double* wqp = need_wq ? ctx->wq : nullptr;
+                        const double* ud = ctx->Ud;
+                        const double* mi = ctx->Minv;
+                        double *xx = ctx->da, *rr = ctx->pr, *ppv = ctx->pp, *bp = ctx->blkpart;
+                        PcgScalars* sc = ctx->pcg_sc;
+                        double rt = rtol;
+                        void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt};
+                        CU(cudaLaunchCooperativeKernel((void*)k_pcg_update_coop<NA>, dim3(ctx->coop_grid), dim3(128), args, 0, ctx->stream));
+                    } else {
+                        k_pcg_update<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Ud, ctx->Minv, ctx->wq, ctx->da, ctx->pr, ctx->pz, ctx->pp,
+                                                                      ctx->pq, ctx->pcg_sc, rtol);
+                    }
+                    ctx->launches++;
+                }
             }
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
