@@ -95,3 +95,56 @@ def bundle_euclid_sparse(K, Te, w, Xe, obs_xy, obs_pt, obs_cam, *options, **ctx_
     finally:
         ctx.close()
     return K_.T.copy(), Te_.T.copy(), w_.T.copy(), Xe_.T.copy(), err
+
+
+# ------------------------------------------------------------------------------------------
+# The three mex stages under their reference names, dense Fortran-ordered arrays in and out
+# exactly as bundle_euclid.m:139,192,204 passes them (drop-in / parity use).
+# ------------------------------------------------------------------------------------------
+import ctypes as _C
+
+
+def _F(x):
+    return np.asfortranarray(x, dtype=np.float64)
+
+
+def _check(r):
+    if r != 0:
+        raise capi.VlgBaError(f"libvlgba error {r}: {capi.lib().vlg_ba_last_error(None).decode()}")
+
+
+def mex_bundle_1_XABeUVWeAeB(K, a, b, X, visible):
+    """[X_hat A B e U V W eA eB] = mex_bundle_1_XABeUVWeAeB(K, a, b, X, visible)."""
+    K, a, b, X, visible = _F(K), _F(a), _F(b), _F(X), _F(visible)
+    na, m = a.shape
+    n = b.shape[1]
+    o = [np.zeros(s, order="F") for s in ((2, n, m), (2, na, n, m), (2, 3, n, m), (2, n, m), (na, na, m), (3, 3, n),
+                                          (na, 3, n, m), (na, m), (3, n))]
+    _check(capi.lib().vlg_ba_mex1_dense(_C.c_int(m), _C.c_int(n), _C.c_int(na), capi._d(K), capi._d(a), capi._d(b),
+                                        capi._d(X), capi._d(visible), *[capi._d(t) for t in o]))
+    return tuple(o)
+
+
+def mex_bundle_2_Se_(Y, W, U_, eA, eB):
+    """[S e_] = mex_bundle_2_Se_(Y, W, U_, eA, eB)."""
+    Y, W, U_, eA, eB = _F(Y), _F(W), _F(U_), _F(eA), _F(eB)
+    na, m = eA.shape
+    n = eB.shape[1]
+    S = np.zeros((na * m, na * m), order="F"); e_ = np.zeros(na * m)
+    _check(capi.lib().vlg_ba_mex2_dense(_C.c_int(m), _C.c_int(n), _C.c_int(na), capi._d(Y), capi._d(W), capi._d(U_),
+                                        capi._d(eA), capi._d(eB), capi._d(S), capi._d(e_)))
+    return S, e_
+
+
+def mex_bundle_3_db_new(W, da, eB, V_inv, K, a, b, X, visible):
+    """[db a_new b_new X_hat] = mex_bundle_3_db_new(W, da, eB, V_inv, K, a, b, X, visible)."""
+    W, eB, V_inv, K, a, b, X, visible = _F(W), _F(eB), _F(V_inv), _F(K), _F(a), _F(b), _F(X), _F(visible)
+    da = np.ascontiguousarray(da, dtype=np.float64).reshape(-1)
+    na, m = a.shape
+    n = b.shape[1]
+    db = np.zeros((3, n), order="F"); a_new = np.zeros((na, m), order="F"); b_new = np.zeros((3, n), order="F")
+    X_hat = np.zeros((2, n, m), order="F")
+    _check(capi.lib().vlg_ba_mex3_dense(_C.c_int(m), _C.c_int(n), _C.c_int(na), capi._d(W), capi._d(da), capi._d(eB),
+                                        capi._d(V_inv), capi._d(K), capi._d(a), capi._d(b), capi._d(X), capi._d(visible),
+                                        capi._d(db), capi._d(a_new), capi._d(b_new), capi._d(X_hat)))
+    return db, a_new, b_new, X_hat

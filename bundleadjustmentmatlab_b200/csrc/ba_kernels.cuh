@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_schur_blocks(int nblocks, int N, int add_U, const int* __restrict__ blk_j, const int* __restrict__ blk_k,
                const int64_t* __restrict__ blk_ptr, const int2* __restrict__ pairs,
                const int* __restrict__ obs_pt, const double* __restrict__ W, const double* __restrict__ Vinv,
-               const double* __restrict__ Ud, double* __restrict__ S)
+               const double* __restrict__ Ud, double* __restrict__ S, const double* __restrict__ Yext = nullptr)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bidx = blockIdx.x * kWarpsPerBlock + warp;
@@ -419,13 +419,18 @@ k_schur_blocks(int nblocks, int N, int add_U, const int* __restrict__ blk_j, con
         for (int t = 0; t < 3 * NA; t++) Wj[t] = W[(size_t)3 * NA * pr.x + t];
 #pragma unroll
         for (int t = 0; t < 3 * NA; t++) Wk[t] = W[(size_t)3 * NA * pr.y + t];
+        if (Yext) {                 // mex2 drop-in: Y is an input (mex_bundle_2_Se_.c:21)
 #pragma unroll
-        for (int t = 0; t < 9; t++) Vi[t] = __ldg(Vinv + (size_t)9 * i + t);
+            for (int t = 0; t < 3 * NA; t++) Y[t] = Yext[(size_t)3 * NA * pr.x + t];
+        } else {
 #pragma unroll
-        for (int cc = 0; cc < 3; cc++)
+            for (int t = 0; t < 9; t++) Vi[t] = __ldg(Vinv + (size_t)9 * i + t);
 #pragma unroll
-            for (int r = 0; r < NA; r++)
-                Y[r + NA * cc] = Wj[r] * Vi[3 * cc] + Wj[r + NA] * Vi[1 + 3 * cc] + Wj[r + 2 * NA] * Vi[2 + 3 * cc];
+            for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+                for (int r = 0; r < NA; r++)
+                    Y[r + NA * cc] = Wj[r] * Vi[3 * cc] + Wj[r + NA] * Vi[1 + 3 * cc] + Wj[r + 2 * NA] * Vi[2 + 3 * cc];
+        }
 #pragma unroll
         for (int col = 0; col < NA; col++)
 #pragma unroll
@@ -449,6 +454,25 @@ k_schur_blocks(int nblocks, int N, int add_U, const int* __restrict__ blk_j, con
             if (j != k) S[(size_t)(NA * k + col) + (size_t)N * (NA * j + row)] = v;
         }
     }
+}
+
+// e_j = eA_j - sum_i Y_ij eB_i with Y given (mex2 drop-in, mex_bundle_2_Se_.c:132-155): one
+// thread per (camera, row), ascending i -- the reference's order.
+template <int NA>
+__global__ void k_ebar_from_Y(int m, const int* __restrict__ cam_ptr, const int* __restrict__ obs_pt,
+                              const double* __restrict__ Y, const double* __restrict__ eA,
+                              const double* __restrict__ eB, double* __restrict__ ebar)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * NA) return;
+    const int j = t / NA, row = t % NA;
+    double s = 0.0;
+    for (int o = cam_ptr[j]; o < cam_ptr[j + 1]; o++) {
+        const double* Yo = Y + (size_t)3 * NA * o;
+        const double* g = eB + (size_t)3 * obs_pt[o];
+        s = VLG_P(s, VLG_P(VLG_P(VLG_M(Yo[row], g[0]), VLG_M(Yo[row + NA], g[1])), VLG_M(Yo[row + 2 * NA], g[2])));
+    }
+    ebar[t] = VLG_S(eA[t], s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -799,7 +823,8 @@ template <int NA>
 __global__ void k_new_cost(int64_t nobs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_pt,
                            const int* __restrict__ obs_cam, const double* __restrict__ K4,
                            const double* __restrict__ a_new, const double* __restrict__ b_new,
-                           const double* __restrict__ rtab_new /* [m][9] */, double* __restrict__ cost_obs)
+                           const double* __restrict__ rtab_new /* [m][9] */, double* __restrict__ cost_obs,
+                           double* __restrict__ xhat_out /* optional [nobs][2] */)
 {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= nobs) return;
@@ -818,6 +843,7 @@ __global__ void k_new_cost(int64_t nobs, const double2* __restrict__ obs_xy, con
     const double2 xy = obs_xy[o];
     const double e0 = VLG_S(xy.x, x), e1 = VLG_S(xy.y, y);
     cost_obs[o] = e0 * e0 + e1 * e1;
+    if (xhat_out) { xhat_out[2 * o] = x; xhat_out[2 * o + 1] = y; }
 }
 
 // rotation tables on the device (VLG_BA_RTABLE_DEVICE): 4 matrices per camera for stage 1,

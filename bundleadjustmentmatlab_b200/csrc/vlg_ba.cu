@@ -116,6 +116,7 @@ struct vlg_ba_ctx {
     PcgScalars* pcg_sc = nullptr;
     // device: stage 3 (scal3 = new_cost | denom_pt_sum | denom_cam)
     double *db = nullptr, *denom_pt = nullptr, *cost_obs = nullptr, *scal3 = nullptr;
+    double* xhat_out = nullptr;      // optional per-observation X_hat_new (dense mex3 drop-in)
     // pinned host scalars
     double* h_pin = nullptr;
     PcgScalars* h_pcg = nullptr;

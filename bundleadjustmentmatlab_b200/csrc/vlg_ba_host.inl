@@ -186,7 +186,7 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
         }
         if (ctx->nobs > 0) {
             k_new_cost<NA><<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->obs_xy, ctx->obs_pt, ctx->obs_cam, ctx->K4,
-                                                                         ctx->a_new, ctx->b_new, ctx->rtab_new, ctx->cost_obs);
+                                                                         ctx->a_new, ctx->b_new, ctx->rtab_new, ctx->cost_obs, ctx->xhat_out);
             ctx->launches++;
         }
     }
@@ -732,5 +732,7 @@ int vlg_ba_timer_stop(vlg_ba_ctx* ctx, float* elapsed_ms)
     if (elapsed_ms) *elapsed_ms = ms;
     return VLG_BA_OK;
 }
+
+#include "vlg_ba_dense.inl"
 
 }  // extern "C"

@@ -168,6 +168,31 @@ int  vlg_ba_trial_step_host(vlg_ba_ctx *ctx, const double *a, const double *b,
                             const double *obs_xy, double lambda,
                             double *a_new, double *b_new, vlg_ba_trial_info *info);
 
+/* ---- dense drop-ins: the exact argument layout of the reference's three mexFunctions -------
+ * Stateless (context created and destroyed inside); used by mex/mex_bundle_*.c so that the
+ * reference's bundle_euclid.m runs unmodified on the GPU.  Output pointers may be NULL.
+ *   mex1: [X_hat A B e U V W eA eB] = mex_bundle_1_XABeUVWeAeB(K, a, b, X, visible)
+ *         (mex_bundle_1_XABeUVWeAeB.c:76-83 inputs, :136-175 outputs)
+ *   mex2: [S e_] = mex_bundle_2_Se_(Y, W, U_, eA, eB)          (mex_bundle_2_Se_.c:21-27,:59-66)
+ *   mex3: [db a_new b_new X_hat] = mex_bundle_3_db_new(W, da, eB, V_inv, K, a, b, X, visible)
+ *         (mex_bundle_3_db_new.c:18-29,:67-86) */
+int  vlg_ba_mex1_dense(int m, int n, int num_a, const double *K, const double *a, const double *b,
+                       const double *X, const double *visible, double *X_hat, double *A, double *B,
+                       double *e, double *U, double *V, double *W, double *eA, double *eB);
+int  vlg_ba_mex2_dense(int m, int n, int num_a, const double *Y, const double *W, const double *U_,
+                       const double *eA, const double *eB, double *S, double *e_);
+int  vlg_ba_mex3_dense(int m, int n, int num_a, const double *W, const double *da, const double *eB,
+                       const double *Vinv, const double *K, const double *a, const double *b,
+                       const double *X, const double *visible, double *db, double *a_new,
+                       double *b_new, double *X_hat);
+/* [K_ Te_ w_ Xe_ error_] = bundle_euclid(K, Te, w, Xe, x, ...) (bundle_euclid.m:1-269) in one
+ * call: K 4xm, Te 3xm, w 3xm, Xe 4xn, x 3xnxm, visible nxm or NULL (derive from x,
+ * bundle_euclid.m:50), pivot m or NULL; error_ holds max_iter doubles. */
+int  vlg_ba_bundle_euclid(const vlg_ba_opts *opts, int m, int n, const double *K, const double *Te,
+                          const double *w, const double *Xe, const double *x, const double *visible,
+                          const double *pivot, double *K_, double *Te_, double *w_, double *Xe_,
+                          double *error_, int *n_error);
+
 /* Introspection for tests and benches. */
 int  vlg_ba_get_schur_structure(vlg_ba_ctx *ctx, int64_t *n_blocks, int32_t *blk_j, int32_t *blk_k);
 int64_t vlg_ba_kernel_launches(const vlg_ba_ctx *ctx);

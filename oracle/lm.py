@@ -70,6 +70,15 @@ def ref_lib():
     return _ref
 
 
+def use_ref_library(path=None):
+    """Point the ``ref`` back end at another library exporting vlgref_stage1/2/3 (the flat
+    wrappers of ref_glue.c).  tests/test_mex_dropin.py uses this to run the restated
+    bundle_euclid.m driver over the GPU mex drop-ins (mex/_build/libvlgmex_shim.so) instead of
+    the reference's own mex files; ``None`` restores the reference build."""
+    global _ref
+    _ref = None if path is None else C.CDLL(path)
+
+
 def _d(x):
     return x.ctypes.data_as(_dp)
 

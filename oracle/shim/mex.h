@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <stdio.h>
 
 typedef size_t mwSize;
 typedef size_t mwIndex;
@@ -56,6 +57,16 @@ static inline mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity cpl
     mwSize d[2];
     d[0] = m; d[1] = n;
     return mxCreateNumericArray(2, d, mxDOUBLE_CLASS, cplx);
+}
+static inline void *mxCalloc(size_t n, size_t size) { return calloc(n ? n : 1, size); }
+static inline void mxFree(void *p) { free(p); }
+/* last error raised through mexErrMsgIdAndTxt (tests read it; MATLAB would throw) */
+static char vlg_shim_last_error[512];
+static inline void mexErrMsgIdAndTxt(const char *id, const char *msg)
+{
+    snprintf(vlg_shim_last_error, sizeof(vlg_shim_last_error), "%s: %s", id, msg);
+    fprintf(stderr, "mexErrMsgIdAndTxt: %s\n", vlg_shim_last_error);
+    abort();
 }
 static inline void mxDestroyArray(mxArray *a)
 {

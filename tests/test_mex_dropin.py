@@ -1,0 +1,142 @@
+"""The drop-in boundary: the GPU mex wrappers (mex/*.c, compiled against the test shim mex.h)
+called exactly as bundle_euclid.m:139,192,204 calls the reference's mex files."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bundleadjustmentmatlab_b200 import bundle, capi
+from oracle import lm
+
+from common import golden_names, golden_opts, load_golden, oracle_options, rel
+from conftest import ROOT
+
+SHIM = os.path.join(ROOT, "mex", "_build", "libvlgmex_shim.so")
+
+
+def build_shim():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "mex"), "shim"], check=True, stdout=subprocess.DEVNULL)
+    return SHIM
+
+
+def test_mex_wrappers_compile_and_export():
+    """CPU: the four wrappers compile against a mex.h and export their entry points."""
+    L = C.CDLL(build_shim())
+    for s in ("vlgref_mex1", "vlgref_mex2", "vlgref_mex3", "vlggpu_mex_euclid", "vlgref_stage1", "vlgref_stage2", "vlgref_stage3"):
+        assert hasattr(L, s), s
+
+
+def dense_from_golden(g, key, block_shape):
+    n, m = int(g["n"]), int(g["m"])
+    out = np.zeros(block_shape + (n, m), order="F")
+    src = g[key]
+    pt, cam = g["obs_pt"], g["obs_cam"]
+    if len(block_shape) == 1:
+        out[:, pt, cam] = src.T
+    else:
+        out[:, :, pt, cam] = np.transpose(src, (2, 1, 0))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_names())
+def test_mex1_dense_outputs_bit_exact(name):
+    g = load_golden(name)
+    a = g["t_a"][0]; b = g["t_b"][0]
+    X = np.asfortranarray(g["x"][:2]); vis = np.asfortranarray(g["visible"])
+    X_hat, A, B, e, U, V, W, eA, eB = bundle.mex_bundle_1_XABeUVWeAeB(g["K"], a, b, X, vis)
+    na = a.shape[0]
+    assert np.array_equal(A, dense_from_golden(g, "A", (2, na)))
+    assert np.array_equal(B, dense_from_golden(g, "B", (2, 3)))
+    assert np.array_equal(e, dense_from_golden(g, "e", (2,)))
+    # mex1 itself does not apply fix_* (bundle_euclid.m:140-154 does): compare the blocks on cases without them
+    if not any(o in g["options"] for o in ("fix_structure", "fix_motion", "fix_pivot")):
+        assert np.array_equal(W, dense_from_golden(g, "W", (na, 3)))
+        assert np.array_equal(np.transpose(U, (2, 1, 0)), g["U"]) and np.array_equal(eA.T, g["eA"])
+        assert np.array_equal(np.transpose(V, (2, 1, 0)), g["V"]) and np.array_equal(eB.T, g["eB"])
+    xh = dense_from_golden(g, "X_hat", (2,))
+    inv = vis == 0
+    assert np.array_equal(X_hat[:, ~inv], xh[:, ~inv]) and np.array_equal(X_hat[:, inv], X[:, inv])
+
+
+@pytest.mark.gpu
+def test_mex2_mex3_dense_vs_reference_values():
+    g = load_golden("euclid_fixcal")
+    a = g["t_a"][0]; b = g["t_b"][0]
+    X = np.asfortranarray(g["x"][:2]); vis = np.asfortranarray(g["visible"])
+    obs = lm.ObsList.from_dense(X, vis)
+    o = oracle_options(g)
+    t = lm.lm_trial(g["K"], a, b, obs, 1e-3, o, backend="sparse")
+    na, m, n = 6, int(g["m"]), int(g["n"])
+    Wd = dense_from_golden(g, "W", (na, 3))
+    Vinv = np.asfortranarray(np.transpose(g["Vinv"], (2, 1, 0)))
+    Y = np.zeros_like(Wd)
+    for c in range(3):
+        Y[:, c] = Wd[:, 0] * Vinv[0, c][None, :, None] + Wd[:, 1] * Vinv[1, c][None, :, None] + Wd[:, 2] * Vinv[2, c][None, :, None]
+    U_ = np.asfortranarray(np.transpose(g["U"], (2, 1, 0)).copy())
+    for k in range(na):
+        U_[k, k, :] = (1 + 1e-3) * U_[k, k, :]
+    S, e_ = bundle.mex_bundle_2_Se_(Y, Wd, U_, g["eA"].T, g["eB"].T)
+    assert np.array_equal(e_, g["e_"])
+    assert np.abs(S - g["S"]).max() <= 1e-13 * np.abs(g["S"]).max()
+    db, a_new, b_new, X_hat = bundle.mex_bundle_3_db_new(Wd, g["t_da"][0], g["eB"].T, Vinv, g["K"], a, b, X, vis)
+    assert np.array_equal(db, g["t_db"][0]) and np.array_equal(a_new, g["t_a_new"][0]) and np.array_equal(b_new, g["t_b_new"][0])
+    e_new = (X - X_hat)[:, vis != 0]
+    assert rel(float((e_new ** 2).sum()), float(g["t_new"][0])) <= 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["euclid_fixcal", "euclid_fixpivot", "euclid_fixstructure"])
+def test_reference_driver_over_gpu_mex_wrappers(name):
+    """bundle_euclid.m (restated line by line in oracle/lm.py) running UNMODIFIED over the GPU
+    mex drop-ins instead of the reference's mex files."""
+    g = load_golden(name)
+    lm.use_ref_library(build_shim())
+    try:
+        res = lm.bundle_euclid(g["K"], g["Te"], g["w"], g["Xe"], g["x"], *golden_opts(g), backend="ref")
+    finally:
+        lm.use_ref_library(None)
+    ref = g["error_"]
+    assert len(res.error_) == len(ref)
+    assert rel(res.error_[0], ref[0]) <= 1e-13 and rel(res.error_[1], ref[1]) <= 1e-9
+    assert rel(np.sqrt(res.error_[-1]), np.sqrt(ref[-1])) <= 1e-6
+
+
+class MxArray(C.Structure):
+    _fields_ = [("pr", C.POINTER(C.c_double)), ("ndim", C.c_size_t), ("dims", C.c_size_t * 8), ("owns", C.c_int)]
+
+
+def mx(arr):
+    arr = np.asfortranarray(arr, dtype=np.float64)
+    a = MxArray()
+    a.pr = arr.ctypes.data_as(C.POINTER(C.c_double))
+    a.ndim = max(arr.ndim, 2)
+    shp = list(arr.shape) + [1] * (8 - arr.ndim)
+    if arr.ndim == 1:
+        shp = [arr.shape[0], 1] + [1] * 6
+    for k in range(8):
+        a.dims[k] = shp[k]
+    a.owns = 0
+    a._keep = arr
+    return a
+
+
+@pytest.mark.gpu
+def test_fused_mex_entry_point():
+    """mex_bundle_euclid_gpu: [K_ Te_ w_ Xe_ error_] in one call, through its mexFunction."""
+    g = load_golden("euclid_fixcal")
+    L = C.CDLL(build_shim())
+    ins = [mx(g["K"]), mx(g["Te"]), mx(g["w"]), mx(g["Xe"]), mx(g["x"]), mx(g["visible"]), mx(np.zeros((0, 0))),
+           mx(np.array([0.0, 0.0, 0.0, 0.0]))]
+    pin = (C.POINTER(MxArray) * 8)(*[C.pointer(t) for t in ins])
+    pout = (C.POINTER(MxArray) * 5)()
+    L.vlggpu_mex_euclid(C.c_int(5), pout, C.c_int(8), pin)
+    ne = int(pout[4].contents.dims[1])
+    err = np.array([pout[4].contents.pr[k] for k in range(ne)])
+    ref = g["error_"]
+    assert ne == len(ref) and rel(err[0], ref[0]) <= 1e-12 and rel(np.sqrt(err[-1]), np.sqrt(ref[-1])) <= 1e-6
+    n = int(g["n"])
+    Xe_ = np.array([pout[3].contents.pr[k] for k in range(4 * n)]).reshape(n, 4).T
+    assert np.array_equal(Xe_[3], g["Xe"][3]) and np.abs(Xe_ - g["Xe_"]).max() <= 1e-4
