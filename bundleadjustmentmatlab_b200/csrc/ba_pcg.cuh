@@ -219,12 +219,19 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* sh)
     return s;   // every thread, same order
 }
 
+// Deflation space: the 4 gauge directions the cost cannot see (world translation x3, scale) --
+// exactly the 4 eigenvalues ~lambda that stall block-Jacobi PCG on S.
+constexpr int kDefl = 4;
+struct DeflScalars { double Einv[kDefl * kDefl]; double c0[kDefl]; };
+
 template <int NA>
 __global__ void __launch_bounds__(128)
 k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __restrict__ qpart,
                   const double* __restrict__ wq, const double* __restrict__ Ud, const double* __restrict__ Minv,
                   double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
-                  PcgScalars* __restrict__ sc, double* __restrict__ blkpart /* 3 * gridDim.x */, double rtol)
+                  PcgScalars* __restrict__ sc, double* __restrict__ blkpart /* 11 * gridDim.x */, double rtol,
+                  const double* __restrict__ Z /* [kDefl][N] or NULL */, const double* __restrict__ SZ,
+                  const DeflScalars* __restrict__ ds)
 {
     __shared__ double sh[32];
     cg::grid_group grid = cg::this_grid();
@@ -232,8 +239,12 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     const double rz = sc->rz, r0n2 = sc->r0n2;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = gridDim.x;
+    const size_t N = (size_t)NA * m;
+    constexpr int ND = 1 + 2 * kDefl;             // p'w, Z'w, SZ'p
     double pj[NA], qj[NA], rj[NA], zj[NA];
-    double pq = 0.0;
+    double dots[ND];
+#pragma unroll
+    for (int k = 0; k < ND; k++) dots[k] = 0.0;
     if (j < m) {
 #pragma unroll
         for (int k = 0; k < NA; k++) pj[k] = p[(size_t)NA * j + k];
@@ -246,14 +257,42 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
             if (wq) w = wq[(size_t)NA * j + row];
             else for (int c = cam_chunk_ptr[j]; c < cam_chunk_ptr[j + 1]; c++) w += qpart[(size_t)NA * c + row];
             qj[row] = v - w;
-            pq += pj[row] * qj[row];
+            dots[0] += pj[row] * qj[row];
+        }
+        if (Z) {
+#pragma unroll
+            for (int d = 0; d < kDefl; d++)
+#pragma unroll
+                for (int k = 0; k < NA; k++) {
+                    dots[1 + d] += Z[d * N + (size_t)NA * j + k] * qj[k];
+                    dots[1 + kDefl + d] += SZ[d * N + (size_t)NA * j + k] * pj[k];
+                }
         }
     }
-    pq = block_sum_fixed(pq, sh);
-    if (threadIdx.x == 0) blkpart[blockIdx.x] = pq;
+    const int nd = Z ? ND : 1;
+    for (int k = 0; k < nd; k++) {
+        const double v = block_sum_fixed(dots[k], sh);
+        if (threadIdx.x == 0) blkpart[(size_t)k * nb + blockIdx.x] = v;
+    }
     grid.sync();
-    pq = 0.0;
-    for (int b = 0; b < nb; b++) pq += __ldcg(blkpart + b);
+    for (int k = 0; k < nd; k++) {
+        double v = 0.0;
+        for (int b = 0; b < nb; b++) v += __ldcg(blkpart + (size_t)k * nb + b);
+        dots[k] = v;
+    }
+    // deflated operator: w <- P S p = S p - SZ Einv Z' S p ;  p'(P S p) = p'Sp - (SZ'p)' Einv (Z'Sp)
+    double y[kDefl];
+    double pq = dots[0];
+    if (Z) {
+#pragma unroll
+        for (int d = 0; d < kDefl; d++) {
+            double v = 0.0;
+#pragma unroll
+            for (int e = 0; e < kDefl; e++) v += ds->Einv[d + kDefl * e] * dots[1 + e];
+            y[d] = v;
+            pq -= dots[1 + kDefl + d] * v;
+        }
+    }
     if (!(pq > 0.0)) {                            // breakdown: every thread sees the same pq
         if (blockIdx.x == 0 && threadIdx.x == 0) { sc->done = 2; sc->pq = pq; }
         return;
@@ -261,6 +300,12 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     const double alpha = rz / pq;
     double rzn = 0.0, rr = 0.0;
     if (j < m) {
+        if (Z) {
+#pragma unroll
+            for (int d = 0; d < kDefl; d++)
+#pragma unroll
+                for (int k = 0; k < NA; k++) qj[k] -= SZ[d * N + (size_t)NA * j + k] * y[d];
+        }
 #pragma unroll
         for (int k = 0; k < NA; k++) {
             x[(size_t)NA * j + k] += alpha * pj[k];
@@ -279,10 +324,11 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     }
     rzn = block_sum_fixed(rzn, sh);
     rr = block_sum_fixed(rr, sh);
-    if (threadIdx.x == 0) { blkpart[nb + 2 * blockIdx.x] = rzn; blkpart[nb + 2 * blockIdx.x + 1] = rr; }
+    double* bp2 = blkpart + (size_t)ND * nb;
+    if (threadIdx.x == 0) { bp2[2 * blockIdx.x] = rzn; bp2[2 * blockIdx.x + 1] = rr; }
     grid.sync();
     rzn = 0.0; rr = 0.0;
-    for (int b = 0; b < nb; b++) { rzn += __ldcg(blkpart + nb + 2 * b); rr += __ldcg(blkpart + nb + 2 * b + 1); }
+    for (int b = 0; b < nb; b++) { rzn += __ldcg(bp2 + 2 * b); rr += __ldcg(bp2 + 2 * b + 1); }
     const double beta = rzn / rz;
     if (j < m) {
 #pragma unroll
@@ -291,6 +337,134 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->rz = rzn; sc->rn2 = rr; sc->pq = pq; sc->iters += 1;
         if (rr <= rtol * rtol * r0n2) sc->done = 1;
+    }
+}
+
+// gauge vectors restricted to the cameras: world translation by e_d moves T_j by -R_j e_d,
+// scaling the world scales T_j; rotations and intrinsics do not move.  Z = [kDefl][N].
+template <int NA>
+__global__ void k_gauge_vectors(int m, const double* __restrict__ a, const double* __restrict__ rtab,
+                                const unsigned char* __restrict__ cam_fixed, const int* __restrict__ cam_chunk_ptr,
+                                double* __restrict__ Z)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const size_t N = (size_t)NA * m;
+    const double* R = rtab + (size_t)36 * j;
+    for (int d = 0; d < kDefl; d++)
+        for (int k = 0; k < NA; k++) Z[d * N + (size_t)NA * j + k] = 0.0;
+    // rows of S that are structurally zero (fixed or unobserved cameras) must stay out of the
+    // deflation space: pinv(S) leaves them at zero (bundle_euclid.m:145-154,193)
+    if (cam_fixed[j] || cam_chunk_ptr[j + 1] == cam_chunk_ptr[j]) return;
+    for (int d = 0; d < 3; d++)
+        for (int r = 0; r < 3; r++) Z[d * N + (size_t)NA * j + 3 + r] = -R[r + 3 * d];
+    for (int r = 0; r < 3; r++) Z[3 * N + (size_t)NA * j + 3 + r] = a[(size_t)NA * j + 3 + r];
+}
+
+// out = S v for one vector from the sweep partials: out_j = U*_j v_j - (W V*^-1 W' v)_j
+template <int NA>
+__global__ void k_apply_S_finalize(int m, const int* __restrict__ cam_chunk_ptr, const double* __restrict__ qpart,
+                                   const double* __restrict__ wq, const double* __restrict__ Ud,
+                                   const double* __restrict__ v, double* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * NA) return;
+    const int j = t / NA, row = t % NA;
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NA; c++) s += Ud[(size_t)NA * NA * j + row + NA * c] * v[(size_t)NA * j + c];
+    double w = 0.0;
+    if (wq) w = wq[t];
+    else for (int c = cam_chunk_ptr[j]; c < cam_chunk_ptr[j + 1]; c++) w += qpart[(size_t)NA * c + row];
+    out[t] = s - w;
+}
+
+// E = Z'SZ, Einv, c0 = Z'b; then the deflated start: x^ = 0, r = b - SZ Einv c0, z = M^-1 r, p = z.
+// The stop test stays relative to |b| (the reduced right-hand side).
+template <int NA>
+__global__ void __launch_bounds__(1024)
+k_pcg_init_defl(int m, const double* __restrict__ ebar, const double* __restrict__ Minv, const double* __restrict__ Z,
+                const double* __restrict__ SZ, DeflScalars* __restrict__ ds, double* __restrict__ x,
+                double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, PcgScalars* __restrict__ sc)
+{
+    __shared__ double sh[32];
+    __shared__ double E[kDefl * kDefl], Ei[kDefl * kDefl], c0[kDefl], y0[kDefl];
+    const int N = NA * m;
+    for (int d = 0; d < kDefl; d++)
+        for (int e = d; e < kDefl; e++) {
+            double v = 0.0;
+            for (int t = threadIdx.x; t < N; t += 1024) v += 0.5 * (Z[(size_t)d * N + t] * SZ[(size_t)e * N + t] + Z[(size_t)e * N + t] * SZ[(size_t)d * N + t]);
+            v = block_sum_1024(v, sh);
+            if (threadIdx.x == 0) { E[d + kDefl * e] = v; E[e + kDefl * d] = v; }
+        }
+    for (int d = 0; d < kDefl; d++) {
+        double v = 0.0;
+        for (int t = threadIdx.x; t < N; t += 1024) v += Z[(size_t)d * N + t] * ebar[t];
+        v = block_sum_1024(v, sh);
+        if (threadIdx.x == 0) c0[d] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sym_pinv<kDefl>(E, Ei);
+        for (int d = 0; d < kDefl; d++) {
+            double v = 0.0;
+            for (int e = 0; e < kDefl; e++) v += Ei[d + kDefl * e] * c0[e];
+            y0[d] = v;
+            ds->c0[d] = c0[d];
+        }
+        for (int k = 0; k < kDefl * kDefl; k++) ds->Einv[k] = Ei[k];
+    }
+    __syncthreads();
+    double rz = 0.0, bb = 0.0;
+    for (int t = threadIdx.x; t < N; t += 1024) {
+        double rv = ebar[t];
+        bb += rv * rv;
+        for (int d = 0; d < kDefl; d++) rv -= SZ[(size_t)d * N + t] * y0[d];
+        r[t] = rv; x[t] = 0.0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < N; t += 1024) {
+        const int j = t / NA, row = t % NA;
+        double zz = 0.0;
+#pragma unroll
+        for (int c = 0; c < NA; c++) zz += Minv[(size_t)NA * NA * j + row + NA * c] * r[(size_t)NA * j + c];
+        z[t] = zz; p[t] = zz;
+        rz += r[t] * zz;
+    }
+    rz = block_sum_1024(rz, sh);
+    bb = block_sum_1024(bb, sh);
+    if (threadIdx.x == 0) {
+        sc->rz = rz; sc->r0n2 = bb; sc->rn2 = bb; sc->pq = 0.0; sc->iters = 0;
+        sc->done = (bb == 0.0 || rz == 0.0) ? 1 : 0;
+    }
+}
+
+// x = x^ + Z Einv (Z'b - SZ'x^)
+template <int NA>
+__global__ void __launch_bounds__(1024)
+k_pcg_defl_final(int m, const double* __restrict__ Z, const double* __restrict__ SZ, const DeflScalars* __restrict__ ds,
+                 double* __restrict__ x)
+{
+    __shared__ double sh[32];
+    __shared__ double y[kDefl];
+    const int N = NA * m;
+    double g[kDefl];
+    for (int d = 0; d < kDefl; d++) {
+        double v = 0.0;
+        for (int t = threadIdx.x; t < N; t += 1024) v += SZ[(size_t)d * N + t] * x[t];
+        g[d] = ds->c0[d] - block_sum_1024(v, sh);
+    }
+    if (threadIdx.x == 0)
+        for (int d = 0; d < kDefl; d++) {
+            double v = 0.0;
+            for (int e = 0; e < kDefl; e++) v += ds->Einv[d + kDefl * e] * g[e];
+            y[d] = v;
+        }
+    __syncthreads();
+    for (int t = threadIdx.x; t < N; t += 1024) {
+        double v = x[t];
+        for (int d = 0; d < kDefl; d++) v += Z[(size_t)d * N + t] * y[d];
+        x[t] = v;
     }
 }
 

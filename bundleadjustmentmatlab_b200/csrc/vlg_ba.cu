@@ -102,6 +102,8 @@ struct vlg_ba_ctx {
     int nptiles = 0;
     bool tiled_ok = false;           // every track fits one tile
     double *Wp = nullptr, *blkpart = nullptr;
+    double *Zd = nullptr, *SZd = nullptr;   // deflation vectors [4][N] and S*Z
+    DeflScalars* defl_sc = nullptr;
     int coop_grid = 0;               // 0 = cooperative update kernel not usable
     // device: parameters
     double *K4 = nullptr, *a = nullptr, *b = nullptr, *a_new = nullptr, *b_new = nullptr, *rtab = nullptr, *rtab_new = nullptr;
@@ -467,7 +469,8 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
         const int g = cdiv(m, 128);
         if (coop && g <= nsm * 8) ctx->coop_grid = g;
-        CHK(dalloc(ctx, &ctx->blkpart, (size_t)3 * std::max(g, 1)));
+        CHK(dalloc(ctx, &ctx->blkpart, (size_t)11 * std::max(g, 1)));
+        CHK(dalloc(ctx, &ctx->Zd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->SZd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->defl_sc, 1));
         if (ctx->tiled_ok) {
             CHK(dalloc(ctx, &ctx->Wp, (size_t)3 * na * nobs));
             CHK(dalloc(ctx, &ctx->ptile_first, ptile_first.size()));

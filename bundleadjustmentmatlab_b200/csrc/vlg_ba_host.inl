@@ -80,48 +80,65 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
     } else {
         const double rtol = ctx->opt.pcg_rtol;
         int* done = pcg_done_ptr(ctx);
-        k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol);
+        constexpr int NW = 3 * NA;
+        const size_t sm_pt = sizeof(double) * (kTileObs * NW + kTileObs * 3) + 16;
+        const size_t sm_cam = sizeof(double) * (kTileObs * NW + 8 * NA) + 16;
+        const bool tiled_cam = ctx->chunk_size <= kTileObs;
+        const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0;
+        CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pt));
+        CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cam));
+        // the two sweeps of W V*^-1 W' v: chunk partials land in qpart (and, all-reduced, in wq)
+        auto sweeps = [&](const double* v, const int* dn) -> int {
+            if (n > 0) {
+                TimedScope ts(ctx, T_SWEEP_PT);
+                if (ctx->tiled_ok)
+                    k_sweep_pt_tiled<NA><<<ctx->nptiles, kTileObs, sm_pt, ctx->stream>>>(ctx->ptile_first, ctx->pt_ptr, ctx->pt_cam,
+                                                                                      ctx->Wp, ctx->Vinv, v, dn, ctx->tvec);
+                else
+                    k_sweep_pt<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W, ctx->Vinv,
+                                                                         v, dn, ctx->tvec);
+                ctx->launches++;
+            }
+            if (ctx->nchunks > 0) {
+                TimedScope ts(ctx, T_SWEEP_CAM);
+                if (tiled_cam)
+                    k_sweep_cam_tiled<NA><<<ctx->nchunks, kTileObs, sm_cam, ctx->stream>>>(ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt,
+                                                                                         ctx->W, ctx->tvec, dn, ctx->qpart);
+                else
+                    k_sweep_cam<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+                        ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->tvec, dn, ctx->qpart);
+                ctx->launches++;
+            }
+            if (need_wq) {
+                k_cam_sum_partials<<<cdiv((int64_t)m * NA, 128), 128, 0, ctx->stream>>>(m, NA, ctx->cam_chunk_ptr, ctx->qpart, dn, ctx->wq);
+                ctx->launches++;
+                CHK(allreduce(ctx, ctx->wq, (size_t)N));
+            }
+            CU(cudaGetLastError());
+            return VLG_BA_OK;
+        };
+        const bool defl = ctx->opt.pcg_deflate && ctx->coop_grid > 0 && !ctx->opt.fix_structure;
+        if (defl) {
+            k_gauge_vectors<NA><<<cdiv(m, 128), 128, 0, ctx->stream>>>(m, ctx->a, ctx->rtab, ctx->cam_fixed, ctx->cam_chunk_ptr, ctx->Zd);
+            ctx->launches++;
+            for (int d = 0; d < kDefl; d++) {
+                CHK(sweeps(ctx->Zd + (size_t)d * N, nullptr));
+                k_apply_S_finalize<NA><<<cdiv((int64_t)N, 128), 128, 0, ctx->stream>>>(m, ctx->cam_chunk_ptr, ctx->qpart,
+                                                                                    need_wq ? ctx->wq : nullptr, ctx->Ud,
+                                                                                    ctx->Zd + (size_t)d * N, ctx->SZd + (size_t)d * N);
+                ctx->launches++;
+            }
+            k_pcg_init_defl<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->Zd, ctx->SZd, ctx->defl_sc, ctx->da, ctx->pr,
+                                                           ctx->pz, ctx->pp, ctx->pcg_sc);
+        } else {
+            k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol);
+        }
         ctx->launches++;
-        CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(sizeof(double) * (kTileObs * 3 * NA + kTileObs * 3) + 16)));
-        CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(sizeof(double) * (kTileObs * 3 * NA + 8 * NA) + 16)));
         int launched = 0;
         const int batch = 8;
         while (launched < ctx->opt.pcg_max_iter) {
             for (int it = 0; it < batch && launched < ctx->opt.pcg_max_iter; it++, launched++) {
-                constexpr int NW = 3 * NA;
-                const size_t sm_pt = sizeof(double) * (kTileObs * NW + kTileObs * 3) + 16;
-                const size_t sm_cam = sizeof(double) * (kTileObs * NW + 8 * NA) + 16;
-                const bool tiled_cam = ctx->chunk_size <= kTileObs;
-                if (n > 0) {
-                    TimedScope ts(ctx, T_SWEEP_PT);
-                    if (ctx->tiled_ok) {
-                        k_sweep_pt_tiled<NA><<<ctx->nptiles, kTileObs, sm_pt, ctx->stream>>>(ctx->ptile_first, ctx->pt_ptr, ctx->pt_cam,
-                                                                                          ctx->Wp, ctx->Vinv, ctx->pp, done, ctx->tvec);
-                    } else {
-                        k_sweep_pt<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W,
-                                                                             ctx->Vinv, ctx->pp, done, ctx->tvec);
-                    }
-                    ctx->launches++;
-                }
-                if (ctx->nchunks > 0) {
-                    TimedScope ts(ctx, T_SWEEP_CAM);
-                    if (tiled_cam) {
-                        k_sweep_cam_tiled<NA><<<ctx->nchunks, kTileObs, sm_cam, ctx->stream>>>(ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt,
-                                                                                             ctx->W, ctx->tvec, done, ctx->qpart);
-                    } else {
-                        k_sweep_cam<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
-                            ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->tvec, done, ctx->qpart);
-                    }
-                    ctx->launches++;
-                }
-                const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0;
-                if (need_wq) {
-                    k_cam_sum_partials<<<cdiv((int64_t)m * NA, 128), 128, 0, ctx->stream>>>(m, NA, ctx->cam_chunk_ptr, ctx->qpart, done, ctx->wq);
-                    ctx->launches++;
-                    CHK(allreduce(ctx, ctx->wq, (size_t)N));
-                }
+                CHK(sweeps(ctx->pp, done));
                 {
                     TimedScope ts(ctx, T_PCG_UPDATE);
                     if (ctx->coop_grid > 0) {
@@ -134,7 +151,10 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                         double *xx = ctx->da, *rr = ctx->pr, *ppv = ctx->pp, *bp = ctx->blkpart;
                         PcgScalars* sc = ctx->pcg_sc;
                         double rt = rtol;
-                        void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt};
+                        const double* zz = defl ? ctx->Zd : nullptr;
+                        const double* sz = defl ? ctx->SZd : nullptr;
+                        const DeflScalars* dsc = ctx->defl_sc;
+                        void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt, &zz, &sz, &dsc};
                         CU(cudaLaunchCooperativeKernel((void*)k_pcg_update_coop<NA>, dim3(ctx->coop_grid), dim3(128), args, 0, ctx->stream));
                     } else {
                         k_pcg_update<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Ud, ctx->Minv, ctx->wq, ctx->da, ctx->pr, ctx->pz, ctx->pp,
@@ -151,6 +171,11 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         if (!ctx->h_pcg->done) {
             CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
+        }
+        if (defl) {
+            k_pcg_defl_final<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Zd, ctx->SZd, ctx->defl_sc, ctx->da);
+            ctx->launches++;
+            CU(cudaGetLastError());
         }
         ctx->last_solver = VLG_BA_SOLVER_PCG;
         ctx->last_pcg_iters = ctx->h_pcg->iters;
@@ -316,6 +341,7 @@ void vlg_ba_opts_default(vlg_ba_opts* o)
     o->backsub_all_rows = 0;
     o->solver = VLG_BA_SOLVER_AUTO; o->chol_max_cams = 300; o->pcg_rtol = 1e-8; o->pcg_max_iter = 1000;
     o->rtable = VLG_BA_RTABLE_HOST_LIBM; o->order = VLG_BA_ORDER_CHUNKED; o->device = -1; o->verbose = 0;
+    o->pcg_deflate = 1;
 }
 
 const char* vlg_ba_version(void) { return "vlgba 0.1 (sm_100a, fp64)"; }

@@ -65,6 +65,7 @@ typedef struct vlg_ba_opts {
     int    order;             /* VLG_BA_ORDER_*: REFERENCE = U/eA accumulated in the reference's exact order (slow), CHUNKED = fixed 256-observation chunks (default) */
     int    device;            /* CUDA device ordinal; -1 = current device */
     int    verbose;           /* 'verbose': print "iter k: error= a -> b" (bundle_euclid.m:221-224) */
+    int    pcg_deflate;       /* 1 (default): deflate the 4 gauge directions (world translation, scale) in PCG */
 } vlg_ba_opts;
 
 typedef struct vlg_ba_ctx vlg_ba_ctx;

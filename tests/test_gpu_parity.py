@@ -207,6 +207,28 @@ def test_default_pcg_tolerance_meets_the_cost_bar():
     ctx.close()
 
 
+def test_gauge_deflation_same_answer_fewer_iterations():
+    P = synth.make_problem(60, 6000, 28000, seed=14)
+    a = np.vstack([P.w, P.Te]); b = P.Xe[:3].copy()
+    out = {}
+    for defl in (0, 1):
+        ctx = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG, pcg_deflate=defl, lambda0=1e-5)
+        ctx.set_problem_sparse(P.K.T, a.T, b.T, P.obs_xy, P.obs_pt, P.obs_cam)
+        out[defl] = ctx.trial_step()
+        ctx.close()
+    print("PCG iterations plain/deflated:", out[0]["pcg_iters"], out[1]["pcg_iters"])
+    assert rel(out[1]["new_cost"], out[0]["new_cost"]) <= COST_RTOL
+    assert out[1]["pcg_iters"] < out[0]["pcg_iters"]
+    # fixed cameras must keep da = 0 with deflation on (pinv semantics of the zero rows of S)
+    piv = np.zeros(P.m); piv[:2] = 1
+    ctx = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG, pcg_deflate=1)
+    ctx.set_problem_sparse(P.K.T, a.T, b.T, P.obs_xy, P.obs_pt, P.obs_cam, pivot=piv)
+    ctx.stage1(); ctx.stage2(1e-3)
+    da = ctx.get_reduced()["da"].reshape(P.m, 6)
+    assert np.all(da[:2] == 0) and np.any(da[2:] != 0)
+    ctx.close()
+
+
 def test_device_rtable_mode_reports_mismatch():
     """VLG_BA_RTABLE_DEVICE uses CUDA's sin/cos: count rotation-table entries that differ from
     the host libm table and the resulting cost deviation (reported, loose bound)."""
