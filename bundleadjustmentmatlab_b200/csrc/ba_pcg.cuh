@@ -83,6 +83,56 @@ __device__ __forceinline__ void wait_tile(const double* src, int nob, uint64_t* 
     else __syncthreads();
 }
 
+// A thread's NW-double block of the shared-memory tile -> registers.  With NW even the block
+// is 16-byte aligned and read as double2: at a 144-byte stride a quarter-warp's LDS.128 covers
+// all 32 banks exactly once (conflict-free), and it halves the MIO instruction count.
+template <int NW>
+__device__ __forceinline__ void load_block(const double* __restrict__ tile, int idx, double* __restrict__ w)
+{
+    if constexpr (NW % 2 == 0) {
+        const double2* src = reinterpret_cast<const double2*>(tile + (size_t)idx * NW);
+#pragma unroll
+        for (int k = 0; k < NW / 2; k++) { const double2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NW; k++) w[k] = tile[(size_t)idx * NW + k];
+    }
+}
+
+// Sum of NV values over the 32 lanes by recursive halving: at each xor step a lane keeps half
+// of its values and ships the other half, so NV values cost ~NV shuffles instead of 5*NV.
+// Returns, in every lane, the total of value index `warp_reduce_owner<NPAD>(lane)`; the
+// combination order is fixed (bit-reproducible).
+template <int NPAD>
+__device__ __forceinline__ int warp_reduce_owner(int lane)
+{
+    if (NPAD == 8) return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+template <int NPAD>
+__device__ __forceinline__ double warp_reduce_many(double* v, int lane)
+{
+    static_assert(NPAD == 8 || NPAD == 16, "NPAD");
+    int width = NPAD;
+#pragma unroll
+    for (int mask = 16; width > 1; mask >>= 1, width >>= 1) {
+        const bool hi = (lane & mask) != 0;
+#pragma unroll
+        for (int k = 0; k < NPAD / 2; k++) {
+            if (k < width / 2) {
+                const double send = hi ? v[k] : v[k + width / 2];
+                const double keep = hi ? v[k + width / 2] : v[k];
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+            }
+        }
+    }
+    double s = v[0];
+    if (NPAD == 8) { s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1); }
+    else { s += __shfl_xor_sync(0xffffffffu, s, 1); }
+    return s;
+}
+
 // ---- P-order copy of W: Wp[q] = W[pt_obs[q]] ---------------------------------------------------
 template <int NA>
 __global__ void __launch_bounds__(256) k_w_to_porder(int64_t nobs, const int* __restrict__ pt_obs,
@@ -126,7 +176,8 @@ k_sweep_pt_tiled(const int* __restrict__ ptile_first, const int* __restrict__ pt
     }
     wait_tile<NW>(src, nob, bar);
     if (tid < nob) {
-        const double* w = wt + tid * NW;
+        double w[NW];
+        load_block<NW>(wt, tid, w);
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int r = 0; r < NA; r++) {
@@ -181,18 +232,20 @@ k_sweep_cam_tiled(const int* __restrict__ chunk_begin, const int* __restrict__ c
         t0 = ta.x; t1 = ta.y; t2 = tb.x;
     }
     wait_tile<NW>(src, nob, bar);
-    double acc[NA];
+    constexpr int NPAD = NA <= 8 ? 8 : 16;
+    double acc[NPAD];
 #pragma unroll
-    for (int r = 0; r < NA; r++) acc[r] = 0.0;
+    for (int r = 0; r < NPAD; r++) acc[r] = 0.0;
     if (tid < nob) {
-        const double* w = wt + tid * NW;
+        double w[NW];
+        load_block<NW>(wt, tid, w);
 #pragma unroll
         for (int r = 0; r < NA; r++) acc[r] = w[r] * t0 + w[r + NA] * t1 + w[r + 2 * NA] * t2;
     }
-#pragma unroll
-    for (int r = 0; r < NA; r++) {
-        const double v = warp_sum(acc[r]);
-        if (lane == 0) red[warp * NA + r] = v;
+    {
+        const double tot = warp_reduce_many<NPAD>(acc, lane);
+        const int own = warp_reduce_owner<NPAD>(lane);
+        if ((lane & (32 / NPAD - 1)) == 0 && own < NA) red[warp * NA + own] = tot;
     }
     __syncthreads();
     if (tid < NA) {
@@ -233,52 +286,63 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
                   const double* __restrict__ Z /* [kDefl][N] or NULL */, const double* __restrict__ SZ,
                   const DeflScalars* __restrict__ ds)
 {
-    __shared__ double sh[32];
+    // one thread per reduced unknown; a CTA owns kCams whole cameras so that the NA x NA block
+    // products (U* p, M^-1 r) only need the CTA's own slice of p and r (shared memory)
+    constexpr int ND = 1 + 2 * kDefl;             // p'w, Z'w, SZ'p
+    constexpr int kCams = 128 / NA;
+    __shared__ double shd[4 * ND];
+    __shared__ double pv[128], rv[128];
     cg::grid_group grid = cg::this_grid();
     if (sc->done) return;                         // uniform: sc is only written after the last grid sync
     const double rz = sc->rz, r0n2 = sc->r0n2;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = gridDim.x;
     const size_t N = (size_t)NA * m;
-    constexpr int ND = 1 + 2 * kDefl;             // p'w, Z'w, SZ'p
-    double pj[NA], qj[NA], rj[NA], zj[NA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lc = threadIdx.x / NA, row = threadIdx.x - lc * NA;       // local camera, row
+    const int j = blockIdx.x * kCams + lc;
+    const bool act = lc < kCams && j < m;
+    const size_t t = (size_t)NA * j + row;
     double dots[ND];
 #pragma unroll
     for (int k = 0; k < ND; k++) dots[k] = 0.0;
-    if (j < m) {
+    double pt = 0.0, qt = 0.0;
+    if (act) { pt = p[t]; pv[threadIdx.x] = pt; }
+    __syncthreads();
+    if (act) {
+        double v = 0.0;
 #pragma unroll
-        for (int k = 0; k < NA; k++) pj[k] = p[(size_t)NA * j + k];
-#pragma unroll
-        for (int row = 0; row < NA; row++) {
-            double v = 0.0;
-#pragma unroll
-            for (int c = 0; c < NA; c++) v += Ud[(size_t)NA * NA * j + row + NA * c] * pj[c];
-            double w = 0.0;
-            if (wq) w = wq[(size_t)NA * j + row];
-            else for (int c = cam_chunk_ptr[j]; c < cam_chunk_ptr[j + 1]; c++) w += qpart[(size_t)NA * c + row];
-            qj[row] = v - w;
-            dots[0] += pj[row] * qj[row];
-        }
+        for (int c = 0; c < NA; c++) v += Ud[(size_t)NA * NA * j + row + NA * c] * pv[lc * NA + c];
+        double w = 0.0;
+        if (wq) w = wq[t];
+        else for (int c = cam_chunk_ptr[j]; c < cam_chunk_ptr[j + 1]; c++) w += qpart[(size_t)NA * c + row];
+        qt = v - w;
+        dots[0] = pt * qt;
         if (Z) {
 #pragma unroll
-            for (int d = 0; d < kDefl; d++)
-#pragma unroll
-                for (int k = 0; k < NA; k++) {
-                    dots[1 + d] += Z[d * N + (size_t)NA * j + k] * qj[k];
-                    dots[1 + kDefl + d] += SZ[d * N + (size_t)NA * j + k] * pj[k];
-                }
+            for (int d = 0; d < kDefl; d++) {
+                dots[1 + d] = Z[d * N + t] * qt;
+                dots[1 + kDefl + d] = SZ[d * N + t] * pt;
+            }
         }
     }
     const int nd = Z ? ND : 1;
+    // all nd block sums with one barrier: xor tree per warp, then warps in order
     for (int k = 0; k < nd; k++) {
-        const double v = block_sum_fixed(dots[k], sh);
-        if (threadIdx.x == 0) blkpart[(size_t)k * nb + blockIdx.x] = v;
+        const double v = warp_sum(dots[k]);
+        if (lane == 0) shd[warp * ND + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nd) {
+        double v = 0.0;
+        for (int w = 0; w < 4; w++) v += shd[w * ND + threadIdx.x];
+        blkpart[(size_t)threadIdx.x * nb + blockIdx.x] = v;
     }
     grid.sync();
+    // every warp folds the per-block partials the same way (strided by lane, xor tree)
     for (int k = 0; k < nd; k++) {
         double v = 0.0;
-        for (int b = 0; b < nb; b++) v += __ldcg(blkpart + (size_t)k * nb + b);
-        dots[k] = v;
+        for (int b = lane; b < nb; b += 32) v += __ldcg(blkpart + (size_t)k * nb + b);
+        dots[k] = warp_sum(v);
     }
     // deflated operator: w <- P S p = S p - SZ Einv Z' S p ;  p'(P S p) = p'Sp - (SZ'p)' Einv (Z'Sp)
     double y[kDefl];
@@ -298,42 +362,42 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
         return;
     }
     const double alpha = rz / pq;
-    double rzn = 0.0, rr = 0.0;
-    if (j < m) {
+    double rzn = 0.0, rr = 0.0, zt = 0.0;
+    if (act) {
         if (Z) {
 #pragma unroll
-            for (int d = 0; d < kDefl; d++)
-#pragma unroll
-                for (int k = 0; k < NA; k++) qj[k] -= SZ[d * N + (size_t)NA * j + k] * y[d];
+            for (int d = 0; d < kDefl; d++) qt -= SZ[d * N + t] * y[d];
         }
-#pragma unroll
-        for (int k = 0; k < NA; k++) {
-            x[(size_t)NA * j + k] += alpha * pj[k];
-            rj[k] = r[(size_t)NA * j + k] - alpha * qj[k];
-            r[(size_t)NA * j + k] = rj[k];
-            rr += rj[k] * rj[k];
-        }
-#pragma unroll
-        for (int row = 0; row < NA; row++) {
-            double v = 0.0;
-#pragma unroll
-            for (int c = 0; c < NA; c++) v += Minv[(size_t)NA * NA * j + row + NA * c] * rj[c];
-            zj[row] = v;
-            rzn += rj[row] * v;
-        }
+        x[t] += alpha * pt;
+        const double rt = r[t] - alpha * qt;
+        r[t] = rt;
+        rv[threadIdx.x] = rt;
+        rr = rt * rt;
     }
-    rzn = block_sum_fixed(rzn, sh);
-    rr = block_sum_fixed(rr, sh);
+    __syncthreads();
+    if (act) {
+#pragma unroll
+        for (int c = 0; c < NA; c++) zt += Minv[(size_t)NA * NA * j + row + NA * c] * rv[lc * NA + c];
+        rzn = rv[threadIdx.x] * zt;
+    }
+    rzn = warp_sum(rzn);
+    rr = warp_sum(rr);
+    if (lane == 0) { shd[warp * 2] = rzn; shd[warp * 2 + 1] = rr; }   // shd's first use ended before grid.sync
+    __syncthreads();
     double* bp2 = blkpart + (size_t)ND * nb;
-    if (threadIdx.x == 0) { bp2[2 * blockIdx.x] = rzn; bp2[2 * blockIdx.x + 1] = rr; }
-    grid.sync();
-    rzn = 0.0; rr = 0.0;
-    for (int b = 0; b < nb; b++) { rzn += __ldcg(bp2 + 2 * b); rr += __ldcg(bp2 + 2 * b + 1); }
-    const double beta = rzn / rz;
-    if (j < m) {
-#pragma unroll
-        for (int k = 0; k < NA; k++) p[(size_t)NA * j + k] = zj[k] + beta * pj[k];
+    if (threadIdx.x < 2) {
+        double v = 0.0;
+        for (int w = 0; w < 4; w++) v += shd[w * 2 + threadIdx.x];
+        bp2[2 * blockIdx.x + threadIdx.x] = v;
     }
+    grid.sync();
+    {
+        double v0 = 0.0, v1 = 0.0;
+        for (int b = lane; b < nb; b += 32) { v0 += __ldcg(bp2 + 2 * b); v1 += __ldcg(bp2 + 2 * b + 1); }
+        rzn = warp_sum(v0); rr = warp_sum(v1);
+    }
+    const double beta = rzn / rz;
+    if (act) p[t] = zt + beta * pt;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->rz = rzn; sc->rn2 = rr; sc->pq = pq; sc->iters += 1;
         if (rr <= rtol * rtol * r0n2) sc->done = 1;

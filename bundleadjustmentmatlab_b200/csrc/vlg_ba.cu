@@ -467,7 +467,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         int coop = 0, nsm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-        const int g = cdiv(m, 128);
+        const int g = cdiv(m, 128 / na);            // k_pcg_update_coop: a CTA owns 128/na whole cameras
         if (coop && g <= nsm * 8) ctx->coop_grid = g;
         CHK(dalloc(ctx, &ctx->blkpart, (size_t)11 * std::max(g, 1)));
         CHK(dalloc(ctx, &ctx->Zd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->SZd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->defl_sc, 1));

@@ -216,8 +216,16 @@ def test_gauge_deflation_same_answer_fewer_iterations():
         ctx.set_problem_sparse(P.K.T, a.T, b.T, P.obs_xy, P.obs_pt, P.obs_cam)
         out[defl] = ctx.trial_step()
         ctx.close()
-    print("PCG iterations plain/deflated:", out[0]["pcg_iters"], out[1]["pcg_iters"])
-    assert rel(out[1]["new_cost"], out[0]["new_cost"]) <= COST_RTOL
+    ctx = capi.Context(num_variableK=0, solver=capi.SOLVER_CHOL, lambda0=1e-5)
+    ctx.set_problem_sparse(P.K.T, a.T, b.T, P.obs_xy, P.obs_pt, P.obs_cam)
+    exact = ctx.trial_step()
+    ctx.close()
+    print("PCG iterations plain/deflated:", out[0]["pcg_iters"], out[1]["pcg_iters"],
+          "cost deviation from the direct solve:", rel(out[0]["new_cost"], exact["new_cost"]), rel(out[1]["new_cost"], exact["new_cost"]))
+    # at lambda = 1e-5 plain PCG leaves the gauge component of da under-resolved (second-order effect
+    # on the cost); the deflated solve resolves it exactly
+    assert rel(out[1]["new_cost"], exact["new_cost"]) <= COST_RTOL
+    assert rel(out[0]["new_cost"], exact["new_cost"]) <= 1e-7
     assert out[1]["pcg_iters"] < out[0]["pcg_iters"]
     # fixed cameras must keep da = 0 with deflation on (pinv semantics of the zero rows of S)
     piv = np.zeros(P.m); piv[:2] = 1
