@@ -5,7 +5,7 @@
 // HBM-bound and each sweep is built as a pure stream:
 //   * W is kept in BOTH orders: C-order (written by stage 1) and a P-order copy Wp made once per
 //     LM trial step by k_w_to_porder, so that each sweep reads one contiguous range per CTA;
-//   * a CTA owns one tile (<= 256 observations: whole points for sweep 1, one chunk of one camera
+//   * a CTA owns one tile (<= 512 observations of whole points for sweep 1, one <= 256-observation chunk of one camera
 //     for sweep 2) and pulls it into shared memory with ONE TMA bulk copy
 //     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), several CTAs per SM keep
 //     >100 KB per SM in flight; the small gathers (p_j, t_i) overlap the bulk copy;
@@ -20,7 +20,12 @@ namespace vlgba {
 
 namespace cg = cooperative_groups;
 
-constexpr int kTileObs = 256;
+// observations per tile == threads per sweep CTA.  Measured on B200 (Venice shape): point tiles
+// of 512 (72 KB of W, 3 CTAs/SM) stream at 5.9 TB/s vs 5.3 TB/s at 256; camera chunks are better
+// at 256 (4.98 vs 4.56 TB/s: a camera's last chunk is partial, and the reduction is per chunk).
+constexpr int kPtTile = 512;
+constexpr int kCamTile = 256;
+constexpr int kCamWarps = kCamTile / 32;
 
 // ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -49,37 +54,50 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
         "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
 
-// global -> shared, contiguous, bytes % 16 == 0, both addresses 16-byte aligned
+// global -> shared, contiguous, bytes % 16 == 0, both addresses 16-byte aligned.  The W
+// stream (720 MB at Venice shape) is tagged L2 evict-first so that it does not push the small
+// gathered vectors (t: 32 MB, written by sweep 1 and gathered by sweep 2) out of the 126 MB L2.
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 
-// Pulls `count` doubles (a whole tile) into shared memory.  TMA when the tile is 16-byte
-// granular, otherwise (NA = 7 with an odd observation count/offset) a plain coalesced copy.
+// Pulls a whole tile into shared memory.  TMA when the tile is 16-byte granular (issued by
+// thread 0 straight after it initialised the mbarrier, i.e. before the CTA-wide barrier that
+// publishes the init); otherwise (NA = 7 with an odd observation count/offset) a plain
+// coalesced copy after that barrier.
 template <int NW>
-__device__ __forceinline__ void load_tile(double* dst, const double* src, int nob, uint64_t* bar)
+__device__ __forceinline__ bool tile_tma_ok(const double* src, int nob)
 {
-    const uint32_t bytes = (uint32_t)nob * NW * 8u;
-    const bool tma_ok = (bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u);
-    if (tma_ok) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, bytes);
-            tma_load_1d(dst, src, bytes, bar);
-        }
-    } else {
-        for (int t = threadIdx.x; t < nob * NW; t += blockDim.x) dst[t] = src[t];
+    return (((uint32_t)nob * NW * 8u) % 16u == 0u) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u);
+}
+
+template <int NW>
+__device__ __forceinline__ void load_tile_pre(double* dst, const double* src, int nob, uint64_t* bar)
+{
+    if (threadIdx.x == 0 && tile_tma_ok<NW>(src, nob)) {
+        const uint32_t bytes = (uint32_t)nob * NW * 8u;
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(dst, src, bytes, bar);
     }
+}
+
+template <int NW>
+__device__ __forceinline__ void load_tile_post(double* dst, const double* src, int nob)
+{
+    if (!tile_tma_ok<NW>(src, nob))
+        for (int t = threadIdx.x; t < nob * NW; t += blockDim.x) dst[t] = src[t];
 }
 
 template <int NW>
 __device__ __forceinline__ void wait_tile(const double* src, int nob, uint64_t* bar)
 {
-    const uint32_t bytes = (uint32_t)nob * NW * 8u;
-    const bool tma_ok = (bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u);
-    if (tma_ok) mbar_wait(bar, 0);
+    if (tile_tma_ok<NW>(src, nob)) mbar_wait(bar, 0);
     else __syncthreads();
 }
 
@@ -147,32 +165,43 @@ __global__ void __launch_bounds__(256) k_w_to_porder(int64_t nobs, const int* __
 }
 
 // ---- sweep 1, point-keyed: t_i = V*_i^-1 sum_j W_ij' p_j ---------------------------------------
-// tile = points [ptile_first[b], ptile_first[b+1]) with <= 256 observations in all
+// tile = points [ptile_first[b], ptile_first[b+1]) with <= kPtTile observations in all
 template <int NA>
-__global__ void __launch_bounds__(kTileObs)
-k_sweep_pt_tiled(const int* __restrict__ ptile_first, const int* __restrict__ pt_ptr, const int* __restrict__ pt_cam,
-                 const double* __restrict__ Wp, const double* __restrict__ Vinv, const double* __restrict__ p,
-                 const int* __restrict__ done, double* __restrict__ t_out)
+__global__ void __launch_bounds__(kPtTile)
+k_sweep_pt_tiled(const int4* __restrict__ ptile_meta /* (q0, nob, p0, npts) */, const int* __restrict__ pt_ptr,
+                 const int* __restrict__ pt_cam, const double* __restrict__ Wp, const double* __restrict__ Vinv,
+                 const double* __restrict__ p, const int* __restrict__ done, double* __restrict__ t_out)
 {
     constexpr int NW = 3 * NA;
     extern __shared__ __align__(128) unsigned char smraw[];
-    double* wt = reinterpret_cast<double*>(smraw);            // kTileObs x NW
-    double* sv = wt + kTileObs * NW;                          // kTileObs x 3
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sv + kTileObs * 3);
-    if (done && *done) return;
+    double* wt = reinterpret_cast<double*>(smraw);            // kPtTile x NW
+    double* sv = wt + kPtTile * NW;                          // kPtTile x 3
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sv + kPtTile * 3);
     const int tid = threadIdx.x;
-    const int p0 = ptile_first[blockIdx.x], p1 = ptile_first[blockIdx.x + 1];
-    const int q0 = pt_ptr[p0];
-    const int nob = pt_ptr[p1] - q0;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+    // one 16-byte descriptor per tile and the stop flag, fetched together: the bulk copy is
+    // issued after a single (L2) round trip instead of three dependent ones
+    const int4 meta = __ldg(ptile_meta + blockIdx.x);
+    const int stop = done ? *done : 0;
+    if (stop) return;
+    const int q0 = meta.x, nob = meta.y, p0 = meta.z, np = meta.w;
     const double* src = Wp + (size_t)q0 * NW;
-    load_tile<NW>(wt, src, nob, bar);
+    if (tid == 0) mbar_init(bar, 1);
+    load_tile_pre<NW>(wt, src, nob, bar);
+    __syncthreads();
+    load_tile_post<NW>(wt, src, nob);
     double pj[NA];
     if (tid < nob) {
         const double* pp = p + (size_t)NA * pt_cam[q0 + tid];
 #pragma unroll
         for (int r = 0; r < NA; r++) pj[r] = __ldg(pp + r);
+    }
+    // everything the per-point epilogue needs is requested now, under the shadow of the bulk copy
+    int o0 = 0, o1 = 0;
+    double Vi[9];
+    if (tid < np) {
+        o0 = pt_ptr[p0 + tid] - q0; o1 = pt_ptr[p0 + tid + 1] - q0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) Vi[k] = __ldg(Vinv + (size_t)9 * (p0 + tid) + k);
     }
     wait_tile<NW>(src, nob, bar);
     if (tid < nob) {
@@ -186,12 +215,10 @@ k_sweep_pt_tiled(const int* __restrict__ ptile_first, const int* __restrict__ pt
         sv[tid * 3] = s0; sv[tid * 3 + 1] = s1; sv[tid * 3 + 2] = s2;
     }
     __syncthreads();
-    if (tid < p1 - p0) {
+    if (tid < np) {
         const int i = p0 + tid;
-        const int o0 = pt_ptr[i] - q0, o1 = pt_ptr[i + 1] - q0;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int o = o0; o < o1; o++) { s0 += sv[o * 3]; s1 += sv[o * 3 + 1]; s2 += sv[o * 3 + 2]; }
-        const double* Vi = Vinv + (size_t)9 * i;
         // t is stored padded to 4 doubles per point: the camera sweep gathers one aligned
         // 32-byte sector per observation
         double4 tv;
@@ -206,24 +233,26 @@ k_sweep_pt_tiled(const int* __restrict__ ptile_first, const int* __restrict__ pt
 // ---- sweep 2, camera-keyed: chunk partial of sum_i W_ij t_i ------------------------------------
 // one CTA per chunk (<= 256 observations of one camera, contiguous in C-order W)
 template <int NA>
-__global__ void __launch_bounds__(kTileObs)
-k_sweep_cam_tiled(const int* __restrict__ chunk_begin, const int* __restrict__ chunk_end, const int* __restrict__ obs_pt,
+__global__ void __launch_bounds__(kPtTile)
+k_sweep_cam_tiled(const int2* __restrict__ chunk_meta /* (begin, nob) */, const int* __restrict__ obs_pt,
                   const double* __restrict__ W, const double* __restrict__ t_in, const int* __restrict__ done,
                   double* __restrict__ part /* [nchunks][NA] */)
 {
     constexpr int NW = 3 * NA;
     extern __shared__ __align__(128) unsigned char smraw[];
-    double* wt = reinterpret_cast<double*>(smraw);            // kTileObs x NW
-    double* red = wt + kTileObs * NW;                         // 8 warps x NA
-    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 8 * NA);
-    if (done && *done) return;
+    double* wt = reinterpret_cast<double*>(smraw);            // kCamTile x NW
+    double* red = wt + kCamTile * NW;                         // kCamWarps x NA
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + kCamWarps * NA);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int beg = chunk_begin[blockIdx.x];
-    const int nob = chunk_end[blockIdx.x] - beg;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+    const int2 meta = __ldg(chunk_meta + blockIdx.x);
+    const int stop = done ? *done : 0;
+    if (stop) return;
+    const int beg = meta.x, nob = meta.y;
     const double* src = W + (size_t)beg * NW;
-    load_tile<NW>(wt, src, nob, bar);
+    if (tid == 0) mbar_init(bar, 1);
+    load_tile_pre<NW>(wt, src, nob, bar);
+    __syncthreads();
+    load_tile_post<NW>(wt, src, nob);
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     if (tid < nob) {
         const int i = obs_pt[beg + tid];

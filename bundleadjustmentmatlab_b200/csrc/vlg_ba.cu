@@ -98,7 +98,8 @@ struct vlg_ba_ctx {
     int *blk_j = nullptr, *blk_k = nullptr;
     int64_t* blk_ptr = nullptr;
     int2* pairs = nullptr;
-    int* ptile_first = nullptr;      // point tiles of the PCG point sweep
+    int4* ptile_meta = nullptr;      // point tiles of the PCG point sweep: (q0, nob, p0, npts)
+    int2* chunk_meta = nullptr;      // camera chunks: (begin, nob)
     int nptiles = 0;
     bool tiled_ok = false;           // every track fits one tile
     double *Wp = nullptr, *blkpart = nullptr;
@@ -361,7 +362,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     if (o.order == VLG_BA_ORDER_REFERENCE) cs = 1 << 30;
     else {
         int64_t want = nobs / (148 * 8);
-        cs = (int)std::min<int64_t>(256, std::max<int64_t>(32, (want + 31) / 32 * 32));
+        cs = (int)std::min<int64_t>(kCamTile, std::max<int64_t>(32, (want + 31) / 32 * 32));
     }
     ctx->chunk_size = cs;
     std::vector<int> chunk_cam, chunk_begin, chunk_end, cam_chunk_ptr(m + 1, 0);
@@ -426,8 +427,8 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         ptile_first.push_back(0);
         for (int i = 0; i < n; i++) {
             const int t = pt_ptr[i + 1] - pt_ptr[i];
-            if (t > kTileObs) { ctx->tiled_ok = false; break; }
-            if (acc + t > kTileObs || cntp == kTileObs) { ptile_first.push_back(i); acc = 0; cntp = 0; }
+            if (t > kPtTile) { ctx->tiled_ok = false; break; }
+            if (acc + t > kPtTile || cntp == kPtTile) { ptile_first.push_back(i); acc = 0; cntp = 0; }
             acc += t; cntp++;
         }
         ptile_first.push_back(n);
@@ -473,8 +474,14 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         CHK(dalloc(ctx, &ctx->Zd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->SZd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->defl_sc, 1));
         if (ctx->tiled_ok) {
             CHK(dalloc(ctx, &ctx->Wp, (size_t)3 * na * nobs));
-            CHK(dalloc(ctx, &ctx->ptile_first, ptile_first.size()));
-            CHK(upload(ctx, ctx->ptile_first, ptile_first.data(), ptile_first.size()));
+            std::vector<int4> pm((size_t)ctx->nptiles);
+            for (int t = 0; t < ctx->nptiles; t++) {
+                const int p0 = ptile_first[t], p1 = ptile_first[t + 1];
+                pm[t] = make_int4(pt_ptr[p0], pt_ptr[p1] - pt_ptr[p0], p0, p1 - p0);
+            }
+            CHK(dalloc(ctx, &ctx->ptile_meta, pm.size()));
+            CHK(upload(ctx, ctx->ptile_meta, pm.data(), pm.size()));
+            CU(cudaStreamSynchronize(ctx->stream));
         }
     }
     if (ctx->use_chol) {
@@ -494,6 +501,13 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(upload(ctx, ctx->chunk_cam, chunk_cam.data(), (size_t)ctx->nchunks));
     CHK(upload(ctx, ctx->chunk_begin, chunk_begin.data(), (size_t)ctx->nchunks));
     CHK(upload(ctx, ctx->chunk_end, chunk_end.data(), (size_t)ctx->nchunks));
+    {
+        std::vector<int2> cm((size_t)ctx->nchunks);
+        for (int c = 0; c < ctx->nchunks; c++) cm[c] = make_int2(chunk_begin[c], chunk_end[c] - chunk_begin[c]);
+        CHK(dalloc(ctx, &ctx->chunk_meta, cm.size()));
+        CHK(upload(ctx, ctx->chunk_meta, cm.data(), cm.size()));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     CHK(upload(ctx, ctx->cam_chunk_ptr, cam_chunk_ptr.data(), (size_t)m + 1));
     CHK(upload(ctx, ctx->cam_fixed, fixed.data(), (size_t)m));
     CHK(upload(ctx, ctx->K4, K, (size_t)4 * m)); CHK(upload(ctx, ctx->a, a, N)); CHK(upload(ctx, ctx->b, b, (size_t)3 * n));

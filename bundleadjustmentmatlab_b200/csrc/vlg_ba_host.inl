@@ -81,9 +81,9 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         const double rtol = ctx->opt.pcg_rtol;
         int* done = pcg_done_ptr(ctx);
         constexpr int NW = 3 * NA;
-        const size_t sm_pt = sizeof(double) * (kTileObs * NW + kTileObs * 3) + 16;
-        const size_t sm_cam = sizeof(double) * (kTileObs * NW + 8 * NA) + 16;
-        const bool tiled_cam = ctx->chunk_size <= kTileObs;
+        const size_t sm_pt = sizeof(double) * (kPtTile * NW + kPtTile * 3) + 16;
+        const size_t sm_cam = sizeof(double) * (kCamTile * NW + kCamWarps * NA) + 16;
+        const bool tiled_cam = ctx->chunk_size <= kCamTile;
         const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0;
         CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pt));
         CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cam));
@@ -92,7 +92,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             if (n > 0) {
                 TimedScope ts(ctx, T_SWEEP_PT);
                 if (ctx->tiled_ok)
-                    k_sweep_pt_tiled<NA><<<ctx->nptiles, kTileObs, sm_pt, ctx->stream>>>(ctx->ptile_first, ctx->pt_ptr, ctx->pt_cam,
+                    k_sweep_pt_tiled<NA><<<ctx->nptiles, kPtTile, sm_pt, ctx->stream>>>(ctx->ptile_meta, ctx->pt_ptr, ctx->pt_cam,
                                                                                       ctx->Wp, ctx->Vinv, v, dn, ctx->tvec);
                 else
                     k_sweep_pt<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W, ctx->Vinv,
@@ -102,7 +102,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             if (ctx->nchunks > 0) {
                 TimedScope ts(ctx, T_SWEEP_CAM);
                 if (tiled_cam)
-                    k_sweep_cam_tiled<NA><<<ctx->nchunks, kTileObs, sm_cam, ctx->stream>>>(ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt,
+                    k_sweep_cam_tiled<NA><<<ctx->nchunks, kCamTile, sm_cam, ctx->stream>>>(ctx->chunk_meta, ctx->obs_pt,
                                                                                          ctx->W, ctx->tvec, dn, ctx->qpart);
                 else
                     k_sweep_cam<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
