@@ -562,3 +562,207 @@ k_pcg_defl_final(int m, const double* __restrict__ Z, const double* __restrict__
 }
 
 }  // namespace vlgba
+
+// =========================================================================================
+// Persistent ("ring") versions of the two sweeps.  tools/stream_probe.cu shows that a CTA-per-
+// tile TMA stream reaches 7.2 TB/s when the CTA does nothing else, but every sweep CTA also has
+// a prologue (descriptor fetch) and an epilogue (reduction, store) during which its shared-
+// memory tile is not being refilled (measured: 5.0-5.3 TB/s).  Here a CTA stays resident, owns
+// every gridDim.x-th tile and keeps kStages bulk copies in flight: the copy of tile k+kStages is
+// issued the moment tile k has been consumed, the small gathers of tile k+1 (and their indices
+// for k+2) are requested one tile ahead, and all tile descriptors are fetched once up front.
+// =========================================================================================
+namespace vlgba {
+
+constexpr int kRingTile = 256;      // observations per ring tile == threads per CTA
+constexpr int kRingMaxTiles = 384;  // tile descriptors cached in shared memory per CTA
+
+template <int NA, int STAGES>
+__global__ void __launch_bounds__(kRingTile)
+k_sweep_cam_ring(int ntiles, const int2* __restrict__ chunk_meta, const int* __restrict__ obs_pt,
+                 const double* __restrict__ W, const double* __restrict__ t_in, const int* __restrict__ done,
+                 double* __restrict__ part /* [nchunks][NA] */)
+{
+    constexpr int NW = 3 * NA;
+    constexpr int NPAD = NA <= 8 ? 8 : 16;
+    constexpr int NWARP = kRingTile / 32;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* wt = reinterpret_cast<double*>(smraw);                       // STAGES x kRingTile x NW
+    double* red = wt + (size_t)STAGES * kRingTile * NW;                  // 2 x NWARP x NA
+    int2* metas = reinterpret_cast<int2*>(red + 2 * NWARP * NA);         // kRingMaxTiles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(metas + kRingMaxTiles);  // STAGES
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (done && *done) return;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int mine = first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    for (int k = tid; k < mine; k += kRingTile) metas[k] = __ldg(chunk_meta + first + (size_t)k * step);
+    if (tid == 0)
+        for (int s = 0; s < STAGES; s++) mbar_init(bar + s, 1);
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < STAGES && s < mine; s++) {
+            const uint32_t bytes = (uint32_t)metas[s].y * NW * 8u;
+            mbar_expect_tx(bar + s, bytes);
+            tma_load_1d(wt + (size_t)s * kRingTile * NW, W + (size_t)metas[s].x * NW, bytes, bar + s);
+        }
+    // gather pipeline: index of tile k+2 and t of tile k+1 are requested while tile k is consumed
+    int idx1 = 0;
+    double tc0 = 0.0, tc1 = 0.0, tc2 = 0.0;
+    if (mine > 0 && tid < metas[0].y) {
+        const int i = obs_pt[metas[0].x + tid];
+        const double2 ta = __ldg(reinterpret_cast<const double2*>(t_in) + 2 * (size_t)i);
+        const double2 tb = __ldg(reinterpret_cast<const double2*>(t_in) + 2 * (size_t)i + 1);
+        tc0 = ta.x; tc1 = ta.y; tc2 = tb.x;
+    }
+    if (mine > 1 && tid < metas[1].y) idx1 = obs_pt[metas[1].x + tid];
+    for (int k = 0; k < mine; k++) {
+        const int slot = k % STAGES;
+        const int nob = metas[k].y;
+        int idx2 = 0;
+        if (k + 2 < mine && tid < metas[k + 2].y) idx2 = obs_pt[metas[k + 2].x + tid];
+        double tn0 = 0.0, tn1 = 0.0, tn2 = 0.0;
+        if (k + 1 < mine && tid < metas[k + 1].y) {
+            const double2 ta = __ldg(reinterpret_cast<const double2*>(t_in) + 2 * (size_t)idx1);
+            const double2 tb = __ldg(reinterpret_cast<const double2*>(t_in) + 2 * (size_t)idx1 + 1);
+            tn0 = ta.x; tn1 = ta.y; tn2 = tb.x;
+        }
+        mbar_wait(bar + slot, (uint32_t)((k / STAGES) & 1));
+        double acc[NPAD];
+#pragma unroll
+        for (int r = 0; r < NPAD; r++) acc[r] = 0.0;
+        if (tid < nob) {
+            double w[NW];
+            load_block<NW>(wt + (size_t)slot * kRingTile * NW, tid, w);
+#pragma unroll
+            for (int r = 0; r < NA; r++) acc[r] = w[r] * tc0 + w[r + NA] * tc1 + w[r + 2 * NA] * tc2;
+        }
+        double* rd = red + (k & 1) * NWARP * NA;
+        {
+            const double tot = warp_reduce_many<NPAD>(acc, lane);
+            const int own = warp_reduce_owner<NPAD>(lane);
+            if ((lane & (32 / NPAD - 1)) == 0 && own < NA) rd[warp * NA + own] = tot;
+        }
+        __syncthreads();       // tile consumed by every thread, partials of all warps visible
+        if (tid == 0 && k + STAGES < mine) {
+            const int2 mt = metas[k + STAGES];
+            const uint32_t bytes = (uint32_t)mt.y * NW * 8u;
+            mbar_expect_tx(bar + slot, bytes);
+            tma_load_1d(wt + (size_t)slot * kRingTile * NW, W + (size_t)mt.x * NW, bytes, bar + slot);
+        }
+        if (tid < NA) {
+            double s = 0.0;
+            const int nw = (nob + 31) >> 5;
+            for (int w = 0; w < nw; w++) s += rd[w * NA + tid];
+            part[(size_t)NA * (first + (size_t)k * step) + tid] = s;
+        }
+        tc0 = tn0; tc1 = tn1; tc2 = tn2;
+        idx1 = idx2;
+    }
+}
+
+template <int NA, int STAGES>
+__global__ void __launch_bounds__(kRingTile)
+k_sweep_pt_ring(int ntiles, const int4* __restrict__ ptile_meta /* (q0, nob, p0, npts) */, const int* __restrict__ pt_ptr,
+                const int* __restrict__ pt_cam, const double* __restrict__ Wp, const double* __restrict__ Vinv,
+                const double* __restrict__ p, const int* __restrict__ done, double* __restrict__ t_out)
+{
+    constexpr int NW = 3 * NA;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* wt = reinterpret_cast<double*>(smraw);                       // STAGES x kRingTile x NW
+    double* sv = wt + (size_t)STAGES * kRingTile * NW;                   // 2 x kRingTile x 3
+    int4* metas = reinterpret_cast<int4*>(sv + 2 * kRingTile * 3);       // kRingMaxTiles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(metas + kRingMaxTiles);  // STAGES
+    const int tid = threadIdx.x;
+    if (done && *done) return;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int mine = first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    for (int k = tid; k < mine; k += kRingTile) metas[k] = __ldg(ptile_meta + first + (size_t)k * step);
+    if (tid == 0)
+        for (int s = 0; s < STAGES; s++) mbar_init(bar + s, 1);
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < STAGES && s < mine; s++) {
+            const uint32_t bytes = (uint32_t)metas[s].y * NW * 8u;
+            mbar_expect_tx(bar + s, bytes);
+            tma_load_1d(wt + (size_t)s * kRingTile * NW, Wp + (size_t)metas[s].x * NW, bytes, bar + s);
+        }
+    // per-tile operands, requested one tile ahead: p_j of the observation's camera (index two ahead),
+    // and the point epilogue's track bounds and V*^-1
+    double pc[NA], Vc[9];
+    int oc0 = 0, oc1 = 0, cam1 = 0;
+#pragma unroll
+    for (int r = 0; r < NA; r++) pc[r] = 0.0;
+    if (mine > 0) {
+        const int4 m0 = metas[0];
+        if (tid < m0.y) {
+            const double* pp = p + (size_t)NA * pt_cam[m0.x + tid];
+#pragma unroll
+            for (int r = 0; r < NA; r++) pc[r] = __ldg(pp + r);
+        }
+        if (tid < m0.w) {
+            oc0 = pt_ptr[m0.z + tid] - m0.x; oc1 = pt_ptr[m0.z + tid + 1] - m0.x;
+#pragma unroll
+            for (int q = 0; q < 9; q++) Vc[q] = __ldg(Vinv + (size_t)9 * (m0.z + tid) + q);
+        }
+    }
+    if (mine > 1 && tid < metas[1].y) cam1 = pt_cam[metas[1].x + tid];
+    for (int k = 0; k < mine; k++) {
+        const int slot = k % STAGES;
+        const int4 mk = metas[k];
+        int cam2 = 0;
+        if (k + 2 < mine && tid < metas[k + 2].y) cam2 = pt_cam[metas[k + 2].x + tid];
+        double pn[NA], Vn[9];
+        int on0 = 0, on1 = 0;
+#pragma unroll
+        for (int r = 0; r < NA; r++) pn[r] = 0.0;
+        if (k + 1 < mine) {
+            const int4 mn = metas[k + 1];
+            if (tid < mn.y) {
+                const double* pp = p + (size_t)NA * cam1;
+#pragma unroll
+                for (int r = 0; r < NA; r++) pn[r] = __ldg(pp + r);
+            }
+            if (tid < mn.w) {
+                on0 = pt_ptr[mn.z + tid] - mn.x; on1 = pt_ptr[mn.z + tid + 1] - mn.x;
+#pragma unroll
+                for (int q = 0; q < 9; q++) Vn[q] = __ldg(Vinv + (size_t)9 * (mn.z + tid) + q);
+            }
+        }
+        mbar_wait(bar + slot, (uint32_t)((k / STAGES) & 1));
+        double* svk = sv + (k & 1) * kRingTile * 3;
+        if (tid < mk.y) {
+            double w[NW];
+            load_block<NW>(wt + (size_t)slot * kRingTile * NW, tid, w);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NA; r++) {
+                s0 += w[r] * pc[r]; s1 += w[r + NA] * pc[r]; s2 += w[r + 2 * NA] * pc[r];
+            }
+            svk[tid * 3] = s0; svk[tid * 3 + 1] = s1; svk[tid * 3 + 2] = s2;
+        }
+        __syncthreads();       // tile consumed, per-observation products visible
+        if (tid == 0 && k + STAGES < mine) {
+            const int4 mt = metas[k + STAGES];
+            const uint32_t bytes = (uint32_t)mt.y * NW * 8u;
+            mbar_expect_tx(bar + slot, bytes);
+            tma_load_1d(wt + (size_t)slot * kRingTile * NW, Wp + (size_t)mt.x * NW, bytes, bar + slot);
+        }
+        if (tid < mk.w) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int o = oc0; o < oc1; o++) { s0 += svk[o * 3]; s1 += svk[o * 3 + 1]; s2 += svk[o * 3 + 2]; }
+            double4 tv;
+            tv.x = Vc[0] * s0 + Vc[3] * s1 + Vc[6] * s2;
+            tv.y = Vc[1] * s0 + Vc[4] * s1 + Vc[7] * s2;
+            tv.z = Vc[2] * s0 + Vc[5] * s1 + Vc[8] * s2;
+            tv.w = 0.0;
+            reinterpret_cast<double4*>(t_out)[mk.z + tid] = tv;
+        }
+#pragma unroll
+        for (int r = 0; r < NA; r++) pc[r] = pn[r];
+#pragma unroll
+        for (int q = 0; q < 9; q++) Vc[q] = Vn[q];
+        oc0 = on0; oc1 = on1; cam1 = cam2;
+    }
+}
+
+}  // namespace vlgba

@@ -102,6 +102,8 @@ struct vlg_ba_ctx {
     int2* chunk_meta = nullptr;      // camera chunks: (begin, nob)
     int nptiles = 0;
     bool tiled_ok = false;           // every track fits one tile
+    int use_ring = 0;                // persistent ring sweeps (ba_pcg.cuh): bit 0 = camera sweep, bit 1 = point sweep
+    int pt_tile = 0, nsm = 148;
     double *Wp = nullptr, *blkpart = nullptr;
     double *Zd = nullptr, *SZd = nullptr;   // deflation vectors [4][N] and S*Z
     DeflScalars* defl_sc = nullptr;
@@ -418,17 +420,26 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         ctx->nblocks = 0; ctx->npairs = 0;
     }
 
-    // point tiles for the PCG point sweep: consecutive whole points, <= kTileObs observations
+    // point tiles for the PCG point sweep: consecutive whole points, <= pt_tile observations
     std::vector<int> ptile_first;
     ctx->tiled_ok = !ctx->use_chol;
+    {
+        const char* e = getenv("VLG_BA_RING");
+        // measured on B200 (Venice shape, gpurun_out/bench_venice_r01h_*): the ring helps the camera
+        // sweep (0.1485 vs 0.1526 ms) and hurts the point sweep (0.170 vs 0.148 ms: 512-observation
+        // tiles do not fit a 2-stage ring at 3 CTAs/SM), so only the camera ring is on by default
+        ctx->use_ring = (3 * na) % 2 == 0 ? (e ? atoi(e) : 1) : 0;
+        ctx->pt_tile = (ctx->use_ring & 2) ? kRingTile : kPtTile;
+        cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    }
     if (!ctx->use_chol) {
         int64_t acc = 0;
         int cntp = 0;
         ptile_first.push_back(0);
         for (int i = 0; i < n; i++) {
             const int t = pt_ptr[i + 1] - pt_ptr[i];
-            if (t > kPtTile) { ctx->tiled_ok = false; break; }
-            if (acc + t > kPtTile || cntp == kPtTile) { ptile_first.push_back(i); acc = 0; cntp = 0; }
+            if (t > ctx->pt_tile) { ctx->tiled_ok = false; break; }
+            if (acc + t > ctx->pt_tile || cntp == ctx->pt_tile) { ptile_first.push_back(i); acc = 0; cntp = 0; }
             acc += t; cntp++;
         }
         ptile_first.push_back(n);

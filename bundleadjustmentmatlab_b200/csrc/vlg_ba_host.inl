@@ -87,11 +87,24 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0;
         CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pt));
         CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cam));
+        // persistent ring variants: 2 stages, as many CTAs per SM as shared memory allows
+        constexpr int RS = 2;
+        const size_t sm_ring_cam = sizeof(double) * ((size_t)RS * kRingTile * NW + 2 * (kRingTile / 32) * NA) + sizeof(int2) * kRingMaxTiles + 8 * RS + 16;
+        const size_t sm_ring_pt = sizeof(double) * ((size_t)RS * kRingTile * NW + 2 * kRingTile * 3) + sizeof(int4) * kRingMaxTiles + 8 * RS + 16;
+        const int g_ring_cam = ctx->nsm * (int)std::max<size_t>(1, (size_t)(227 * 1024) / (sm_ring_cam + 1024));
+        const int g_ring_pt = ctx->nsm * (int)std::max<size_t>(1, (size_t)(227 * 1024) / (sm_ring_pt + 1024));
+        const bool ring_cam = (ctx->use_ring & 1) && tiled_cam && ctx->nchunks <= (int64_t)g_ring_cam * kRingMaxTiles && ctx->chunk_size <= kRingTile;
+        const bool ring_pt = (ctx->use_ring & 2) && ctx->tiled_ok && ctx->pt_tile <= kRingTile && ctx->nptiles <= (int64_t)g_ring_pt * kRingMaxTiles;
+        if (ring_cam) CU(cudaFuncSetAttribute(k_sweep_cam_ring<NA, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ring_cam));
+        if (ring_pt) CU(cudaFuncSetAttribute(k_sweep_pt_ring<NA, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ring_pt));
         // the two sweeps of W V*^-1 W' v: chunk partials land in qpart (and, all-reduced, in wq)
         auto sweeps = [&](const double* v, const int* dn) -> int {
             if (n > 0) {
                 TimedScope ts(ctx, T_SWEEP_PT);
-                if (ctx->tiled_ok)
+                if (ring_pt)
+                    k_sweep_pt_ring<NA, RS><<<std::min(g_ring_pt, ctx->nptiles), kRingTile, sm_ring_pt, ctx->stream>>>(
+                        ctx->nptiles, ctx->ptile_meta, ctx->pt_ptr, ctx->pt_cam, ctx->Wp, ctx->Vinv, v, dn, ctx->tvec);
+                else if (ctx->tiled_ok)
                     k_sweep_pt_tiled<NA><<<ctx->nptiles, kPtTile, sm_pt, ctx->stream>>>(ctx->ptile_meta, ctx->pt_ptr, ctx->pt_cam,
                                                                                       ctx->Wp, ctx->Vinv, v, dn, ctx->tvec);
                 else
@@ -101,7 +114,10 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             }
             if (ctx->nchunks > 0) {
                 TimedScope ts(ctx, T_SWEEP_CAM);
-                if (tiled_cam)
+                if (ring_cam)
+                    k_sweep_cam_ring<NA, RS><<<std::min(g_ring_cam, ctx->nchunks), kRingTile, sm_ring_cam, ctx->stream>>>(
+                        ctx->nchunks, ctx->chunk_meta, ctx->obs_pt, ctx->W, ctx->tvec, dn, ctx->qpart);
+                else if (tiled_cam)
                     k_sweep_cam_tiled<NA><<<ctx->nchunks, kCamTile, sm_cam, ctx->stream>>>(ctx->chunk_meta, ctx->obs_pt,
                                                                                          ctx->W, ctx->tvec, dn, ctx->qpart);
                 else
