@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--config", default="venice")
     ap.add_argument("--scale", type=float, default=1.0, help="scale points/observations per rank")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--solver", default="auto", choices=["auto", "chol", "pcg"])
+    ap.add_argument("--solver", default="auto", choices=["auto", "chol", "pcg", "pcgx"])
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--rtable", default="host", choices=["host", "device"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -166,6 +166,7 @@ def algorithmic_bytes(name, P, na=6):
     """ALGORITHMIC bytes per launch of each kernel group."""
     no, n, m = P.nobs, P.n, P.m
     W = 3 * na * 8
+    Np = (na * m + 31) // 32 * 32
     table = {
         # read (u,v)+point id, write W; per point b; per camera table/a/K in, partial U/eA out
         "stage1_cam": no * (16 + 4 + W) + n * 24 + m * (288 + 8 * na + 32 + 8 * (na * (na + 1) // 2 + na)),
@@ -177,6 +178,8 @@ def algorithmic_bytes(name, P, na=6):
         "stage3": no * (W + 4 + 4 + 16 + 4 + 4 + 8) + n * (72 + 24 + 24 + 24 + 24 + 8) + m * (72 + 8 * na + 32),
         "vinv": n * (72 + 72) + m * 2 * 8 * na * na,
         "w_copy": no * (2 * W + 4),
+        # explicit-S PCG: lower triangle of S (32-column strips incl. the full diagonal blocks) + partial vectors
+        "pcg_symv": 4 * Np * (Np + 32) + 8 * Np * 4,
     }
     return table.get(name)
 
@@ -196,7 +199,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     P, a0, b0 = make_shard(args, rank)
-    solver = {"auto": capi.SOLVER_AUTO, "chol": capi.SOLVER_CHOL, "pcg": capi.SOLVER_PCG}[args.solver]
+    solver = {"auto": capi.SOLVER_AUTO, "chol": capi.SOLVER_CHOL, "pcg": capi.SOLVER_PCG, "pcgx": capi.SOLVER_PCG_EXPLICIT}[args.solver]
     rtable = capi.RTABLE_HOST_LIBM if args.rtable == "host" else capi.RTABLE_DEVICE
     ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=args.pcg_rtol, rtable=rtable, device=local)
     if world > 1:
@@ -234,7 +237,7 @@ def run_ours(args):
     launches = ctx.kernel_launches - l0
     groups = {}
     for g in ("stage1_cam", "stage1_pt", "w_copy", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt", "pcg_sweep_cam",
-              "pcg_update", "stage3"):
+              "pcg_symv", "pcg_update", "stage3"):
         avg, cnt = ctx.kernel_time(g)
         groups[g] = {"avg_ms": avg, "count": cnt, "total_ms": avg * cnt}
     ctx.reset_timers(False)
@@ -322,7 +325,7 @@ def run_ours(args):
                 ab = algorithmic_bytes(g, P)
                 per_kernel[g] = {"avg_ms": round(v["avg_ms"], 5), "count": v["count"],
                                  "GBps": (ab / (v["avg_ms"] * 1e-3) / 1e9) if ab else None}
-        js = sum(groups[g]["total_ms"] for g in ("stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "pcg_sweep_pt", "pcg_sweep_cam"))
+        js = sum(groups[g]["total_ms"] for g in ("stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "pcg_sweep_pt", "pcg_sweep_cam", "pcg_symv"))
         cpu = None
         if not args.no_cpu_baseline:
             times, iters, cores = cpu_trial_steps(args, P, a0, b0, 1, 0)
@@ -334,7 +337,8 @@ def run_ours(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, P, world), "num_a": 6,
-                       "solver": "cholesky" if infos[-1]["solver_used"] == capi.SOLVER_CHOL else "pcg (block-Jacobi, implicit Schur)",
+                       "solver": {capi.SOLVER_CHOL: "cholesky", capi.SOLVER_PCG: "pcg (block-Jacobi, implicit Schur)",
+                                  capi.SOLVER_PCG_EXPLICIT: "pcg (block-Jacobi, assembled S, symmetric lower-triangle matvec)"}[infos[-1]["solver_used"]],
                        "pcg_rtol": args.pcg_rtol, "rtable": args.rtable,
                        "l2": "inputs larger than L2 (W alone is %.0f MB per rank)" % (P.nobs * 144 / 1e6)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),

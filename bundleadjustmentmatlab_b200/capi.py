@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvlgba.so")
 
-SOLVER_AUTO, SOLVER_CHOL, SOLVER_PCG = 0, 1, 2
+SOLVER_AUTO, SOLVER_CHOL, SOLVER_PCG, SOLVER_PCG_EXPLICIT = 0, 1, 2, 3
 RTABLE_HOST_LIBM, RTABLE_DEVICE = 0, 1
 ORDER_CHUNKED, ORDER_REFERENCE = 0, 1
 

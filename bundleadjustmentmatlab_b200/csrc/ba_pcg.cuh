@@ -67,6 +67,21 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+
+__device__ __forceinline__ void tma_load_1d_pol(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 // Pulls a whole tile into shared memory.  TMA when the tile is 16-byte granular (issued by
 // thread 0 straight after it initialised the mbarrier, i.e. before the CTA-wide barrier that
 // publishes the init); otherwise (NA = 7 with an odd observation count/offset) a plain
@@ -762,6 +777,178 @@ k_sweep_pt_ring(int ntiles, const int4* __restrict__ ptile_meta /* (q0, nob, p0,
 #pragma unroll
         for (int q = 0; q < 9; q++) Vc[q] = Vn[q];
         oc0 = on0; oc1 = on1; cam1 = cam2;
+    }
+}
+
+}  // namespace vlgba
+
+// =========================================================================================
+// Explicit-S matvec for mid-sized camera counts.  When the assembled reduced system is smaller
+// than the W stream (4 Np^2 bytes for the lower triangle vs 304 B/observation for the two
+// implicit sweeps; Venice shape: 0.46 GB vs 1.52 GB) PCG runs on the dense block-assembled S of
+// k_schur_blocks instead, and one iteration is a symmetric matrix-vector product that reads the
+// LOWER TRIANGLE ONLY: every element a = S[r][c] read once feeds both y_r += a x_c and
+// y_c += a x_r.
+//   * a tile is 256 rows x 32 columns of S (column-major => 32 contiguous 2-KB runs), pulled
+//     into shared memory by 32 TMA bulk copies on one mbarrier; a persistent CTA per SM walks a
+//     host-built tile list (LPT-balanced) with a 3-stage ring, i.e. up to 192 KB in flight per SM;
+//   * thread t owns row t of the tile: row sums leave as per-strip partials, the 32 column
+//     sums stay in registers over a work item (strip segment) and leave as per-segment partials;
+//   * k_symv_finish adds the partials in a fixed order (ascending strip, then ascending segment)
+//     -> bit-reproducible, no atomics.
+// =========================================================================================
+namespace vlgba {
+
+constexpr int kSymvCols = 32;
+constexpr int kSymvRows = 256;    // rows per tile == threads per CTA
+constexpr int kSymvStages = 3;
+constexpr int kSymvSegRows = 1024;   // rows per work item (strip segment): granularity of the load balance
+
+// tile descriptor: x = strip, y = first row, z = rows | first-of-item << 16 | last-of-item << 17, w = segment
+struct SymvTile { int strip, r0, rows_flags, seg; };
+
+// all 32 values of every lane summed over the warp; lane l ends up owning value l
+__device__ __forceinline__ double warp_reduce_32(double* v, int lane)
+{
+    int width = 32;
+#pragma unroll
+    for (int mask = 16; mask >= 1; mask >>= 1, width >>= 1) {
+        const bool hi = (lane & mask) != 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (k < width / 2) {
+                const double send = hi ? v[k] : v[k + width / 2];
+                const double keep = hi ? v[k + width / 2] : v[k];
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+            }
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void consumer_sync()      // named barrier 1: the 256 consumer threads only
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(kSymvRows) : "memory");
+}
+
+// warps 0..7 consume (thread t = row t of the tile), warp 8 produces: lane c issues the bulk copy of
+// column c, so a whole tile is requested by one warp instruction and the producer runs ahead of the
+// consumers by kSymvStages tiles (full/empty mbarrier pairs, no CTA-wide barrier per tile)
+__global__ void __launch_bounds__(kSymvRows + 32, 1)
+k_symv_lower(int Np, int ld, int N, const double* __restrict__ S, const double* __restrict__ x,
+             const int* __restrict__ tile_ptr /* [gridDim.x + 1] */, const int4* __restrict__ tiles,
+             const int* __restrict__ done, double* __restrict__ rowpart /* [Np/32][Np] */,
+             double* __restrict__ colpart /* [nseg][Np] */)
+{
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* st = reinterpret_cast<double*>(smraw);                                   // kSymvStages x 32 x 256
+    double* cred = st + (size_t)kSymvStages * kSymvCols * kSymvRows;                 // 8 x 32
+    double* xs = cred + (kSymvRows / 32) * kSymvCols;                                // 32
+    uint64_t* full = reinterpret_cast<uint64_t*>(xs + kSymvCols);                    // kSymvStages
+    uint64_t* empty = full + kSymvStages;                                            // kSymvStages
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (done && *done) return;
+    const int t0 = tile_ptr[blockIdx.x], nt = tile_ptr[blockIdx.x + 1] - t0;
+    if (nt <= 0) return;
+    if (tid == 0)
+        for (int s = 0; s < kSymvStages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, kSymvRows / 32); }
+    __syncthreads();
+    if (warp == kSymvRows / 32) {
+        // ---- producer warp
+        const uint64_t policy = l2_evict_first_policy();
+        for (int k = 0; k < nt; k++) {
+            const int slot = k % kSymvStages;
+            const int4 d = __ldg(tiles + t0 + k);
+            const uint32_t bytes = (uint32_t)(d.z & 0xffff) * 8u;
+            if (k >= kSymvStages) mbar_wait(empty + slot, (uint32_t)((k / kSymvStages - 1) & 1));
+            if (lane == 0) mbar_expect_tx(full + slot, bytes * kSymvCols);
+            __syncwarp();
+            tma_load_1d_pol(st + ((size_t)slot * kSymvCols + lane) * kSymvRows,
+                            S + (size_t)ld * (kSymvCols * d.x + lane) + d.y, bytes, full + slot, policy);
+        }
+        return;
+    }
+    // ---- consumer warps
+    double colacc[kSymvCols];
+#pragma unroll
+    for (int c = 0; c < kSymvCols; c++) colacc[c] = 0.0;
+    // x of this thread's row, requested one tile ahead
+    int4 dn = __ldg(tiles + t0);
+    double xr_next = 0.0;
+    { const int r = dn.y + tid; if (tid < (dn.z & 0xffff) && r < N) xr_next = __ldg(x + r); }
+    for (int k = 0; k < nt; k++) {
+        const int slot = k % kSymvStages;
+        const int4 d = dn;
+        const int rows = d.z & 0xffff, c0 = kSymvCols * d.x, r = d.y + tid;
+        double xr = xr_next;
+        if (k + 1 < nt) {
+            dn = __ldg(tiles + t0 + k + 1);
+            const int rn = dn.y + tid;
+            xr_next = (tid < (dn.z & 0xffff) && rn < N) ? __ldg(x + rn) : 0.0;
+        }
+        if (d.z & (1 << 16)) {                      // first tile of a work item: this strip's x
+            if (tid < kSymvCols) xs[tid] = (c0 + tid < N) ? __ldg(x + c0 + tid) : 0.0;
+            consumer_sync();
+        }
+        mbar_wait(full + slot, (uint32_t)((k / kSymvStages) & 1));
+        double ra = 0.0;
+        if (tid < rows) {
+            // the diagonal 32 x 32 block is stored in full: whole-row dot product there, no mirrored part
+            if (r < c0 + kSymvCols) xr = 0.0;
+            const double* a = st + (size_t)slot * kSymvCols * kSymvRows + tid;
+#pragma unroll
+            for (int c = 0; c < kSymvCols; c++) {
+                const double v = a[c * kSymvRows];
+                ra += v * xs[c];
+                colacc[c] += v * xr;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);   // this warp is done with the slot
+        if (tid < rows) rowpart[(size_t)d.x * Np + r] = ra;
+        if (d.z & (1 << 17)) {                      // last tile of the work item: column sums out
+            const double tot = warp_reduce_32(colacc, lane);
+            cred[warp * kSymvCols + lane] = tot;
+            consumer_sync();
+            if (tid < kSymvCols) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < kSymvRows / 32; w++) s += cred[w * kSymvCols + tid];
+                colpart[(size_t)d.w * Np + c0 + tid] = s;
+            }
+#pragma unroll
+            for (int c = 0; c < kSymvCols; c++) colacc[c] = 0.0;
+        }
+    }
+}
+
+// out[r] = sign * ( sum_seg colpart[seg][r] + sum_{strip <= r/32} rowpart[strip][r] ), r < N.
+// CTA = 32 rows x 32 strip groups; group g adds strips g, g+32, ... in order, groups are folded in order.
+__global__ void __launch_bounds__(1024)
+k_symv_finish(int Np, int N, double sign, const double* __restrict__ rowpart, const double* __restrict__ colpart,
+              const int* __restrict__ done, double* __restrict__ out)
+{
+    __shared__ double red[32][33];
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + lane;
+    const int jb = blockIdx.x;                       // r / 32: strips 0..jb have this row
+    double s = 0.0;
+    for (int J = g; J <= jb; J += 32) s += __ldcs(rowpart + (size_t)J * Np + r);
+    red[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && r < N) {
+        double y = 0.0;
+        const int nseg = (Np - kSymvCols * jb + kSymvSegRows - 1) / kSymvSegRows;
+        for (int sg = 0; sg < nseg; sg++) y += __ldcs(colpart + (size_t)sg * Np + r);
+#pragma unroll
+        for (int q = 0; q < 32; q++) y += red[q][lane];
+        out[r] = sign * y;
     }
 }
 

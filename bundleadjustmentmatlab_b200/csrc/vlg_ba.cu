@@ -59,9 +59,9 @@ bool nccl_load()
 
 char g_create_error[512] = "";
 
-enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_COUNT };
+enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_SYMV, T_COUNT };
 const char* kTimerNames[T_COUNT] = {"stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt",
-                                    "pcg_sweep_cam", "stage3", "pcg_update", "w_copy"};
+                                    "pcg_sweep_cam", "stage3", "pcg_update", "w_copy", "pcg_symv"};
 
 struct KTimer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -83,6 +83,11 @@ struct vlg_ba_ctx {
     bool have_problem = false;
     int nchunks = 0, chunk_size = 256;
     bool use_chol = false;
+    bool use_explicit = false;        // PCG on the assembled dense S (k_symv_lower) instead of the two W sweeps
+    int4* symv_tiles = nullptr;       // tile list of k_symv_lower, grouped per CTA
+    int* symv_tile_ptr = nullptr;
+    int symv_grid = 0, nsymv_seg = 0;
+    double *symv_rowpart = nullptr, *symv_colpart = nullptr;
     int Np = 0;               // padded order of S
     int64_t nblocks = 0, npairs = 0;
     // host copies
@@ -383,12 +388,20 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
 
     ctx->use_chol = (o.solver == VLG_BA_SOLVER_CHOL) || (o.solver == VLG_BA_SOLVER_AUTO && m <= o.chol_max_cams);
     ctx->Np = (int)((N + kNB - 1) / kNB * kNB);
+    {
+        // explicit-S PCG: one iteration streams the lower triangle (4 Np^2 bytes) instead of W twice
+        // (2 x (24 na + 8) bytes per observation); assembling S costs about a dozen sweeps
+        const double s_bytes = 8.0 * (double)ctx->Np * (double)ctx->Np;
+        const bool pays = 0.75 * s_bytes < 2.0 * (24.0 * na + 8.0) * (double)nobs && s_bytes <= 8e9 && (int64_t)m * m <= ((int64_t)1 << 28);
+        ctx->use_explicit = !ctx->use_chol && (o.solver == VLG_BA_SOLVER_PCG_EXPLICIT || (o.solver == VLG_BA_SOLVER_AUTO && pays));
+    }
+    const bool need_S = ctx->use_chol || ctx->use_explicit;
 
     // block structure of S: cameras j <= k sharing a point; pair lists in ascending point order
     std::vector<int64_t> blk_ptr;
     std::vector<int2> pairs;
     ctx->h_blk_j.clear(); ctx->h_blk_k.clear();
-    if (ctx->use_chol) {
+    if (need_S) {
         if ((int64_t)m * m > ((int64_t)1 << 28)) return fail(ctx, VLG_BA_EINVAL, "explicit Schur/Cholesky path supports m <= 16384 cameras");
         std::vector<int64_t> cnt((size_t)m * m + 1, 0);
         for (int i = 0; i < n; i++)
@@ -422,7 +435,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
 
     // point tiles for the PCG point sweep: consecutive whole points, <= pt_tile observations
     std::vector<int> ptile_first;
-    ctx->tiled_ok = !ctx->use_chol;
+    ctx->tiled_ok = !need_S;
     {
         const char* e = getenv("VLG_BA_RING");
         // measured on B200 (Venice shape, gpurun_out/bench_venice_r01h_*): the ring helps the camera
@@ -432,7 +445,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         ctx->pt_tile = (ctx->use_ring & 2) ? kRingTile : kPtTile;
         cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     }
-    if (!ctx->use_chol) {
+    if (!need_S) {
         int64_t acc = 0;
         int cntp = 0;
         ptile_first.push_back(0);
@@ -495,7 +508,45 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
             CU(cudaStreamSynchronize(ctx->stream));
         }
     }
-    if (ctx->use_chol) {
+    if (ctx->use_explicit) {
+        // work items = strip segments of <= kSymvSegRows rows, spread over one persistent CTA per SM by
+        // longest-processing-time-first; each CTA's items are flattened into 256-row tiles
+        const int Np = ctx->Np, nstrips = Np / kSymvCols;
+        struct Item { int strip, seg, r0, rows; };
+        std::vector<Item> items;
+        for (int J = 0; J < nstrips; J++)
+            for (int sg = 0, r0 = kSymvCols * J; r0 < Np; sg++, r0 += kSymvSegRows)
+                items.push_back({J, sg, r0, std::min(kSymvSegRows, Np - r0)});
+        std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.rows > b.rows; });
+        const int G = std::max(1, std::min(ctx->nsm, (int)items.size()));
+        std::vector<std::vector<Item>> mine((size_t)G);
+        std::vector<int64_t> load((size_t)G, 0);
+        for (const Item& it : items) {
+            int best = 0;
+            for (int g = 1; g < G; g++) if (load[g] < load[best]) best = g;
+            mine[best].push_back(it); load[best] += (it.rows + kSymvRows - 1) / kSymvRows * 8 + 1;
+        }
+        std::vector<int4> tiles;
+        std::vector<int> tptr((size_t)G + 1, 0);
+        for (int g = 0; g < G; g++) {
+            for (const Item& it : mine[g])
+                for (int r = 0; r < it.rows; r += kSymvRows) {
+                    const int rows = std::min(kSymvRows, it.rows - r);
+                    const int flags = (r == 0 ? 1 << 16 : 0) | (r + kSymvRows >= it.rows ? 1 << 17 : 0);
+                    tiles.push_back(make_int4(it.strip, it.r0 + r, rows | flags, it.seg));
+                }
+            tptr[g + 1] = (int)tiles.size();
+        }
+        ctx->symv_grid = G;
+        ctx->nsymv_seg = (Np + kSymvSegRows - 1) / kSymvSegRows;
+        CHK(dalloc(ctx, &ctx->symv_tiles, tiles.size())); CHK(dalloc(ctx, &ctx->symv_tile_ptr, tptr.size()));
+        CHK(upload(ctx, ctx->symv_tiles, tiles.data(), tiles.size()));
+        CHK(upload(ctx, ctx->symv_tile_ptr, tptr.data(), tptr.size()));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CHK(dalloc(ctx, &ctx->symv_rowpart, (size_t)nstrips * Np));
+        CHK(dalloc(ctx, &ctx->symv_colpart, (size_t)ctx->nsymv_seg * Np));
+    }
+    if (need_S) {
         CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));
         CHK(dalloc(ctx, &ctx->blk_j, (size_t)ctx->nblocks)); CHK(dalloc(ctx, &ctx->blk_k, (size_t)ctx->nblocks));
         CHK(dalloc(ctx, &ctx->blk_ptr, (size_t)ctx->nblocks + 1)); CHK(dalloc(ctx, &ctx->pairs, (size_t)ctx->npairs));

@@ -84,7 +84,21 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         const size_t sm_pt = sizeof(double) * (kPtTile * NW + kPtTile * 3) + 16;
         const size_t sm_cam = sizeof(double) * (kCamTile * NW + kCamWarps * NA) + 16;
         const bool tiled_cam = ctx->chunk_size <= kCamTile;
-        const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0;
+        const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0 || ctx->use_explicit;
+        constexpr size_t kSymvSmem = sizeof(double) * ((size_t)kSymvStages * kSymvCols * kSymvRows + (kSymvRows / 32) * kSymvCols + kSymvCols) + 16 * kSymvStages + 16;
+        if (ctx->use_explicit) {
+            CU(cudaFuncSetAttribute(k_symv_lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSymvSmem));
+            // this rank's share of sum_i Y_ij W_ik' (S without U*; U* p is added by the update kernel)
+            TimedScope ts(ctx, T_SCHUR_BLK);
+            CU(cudaMemsetAsync(ctx->S, 0, sizeof(double) * (size_t)ctx->Np * ctx->Np, ctx->stream));
+            if (ctx->nblocks > 0) {
+                k_schur_blocks<NA><<<cdiv(ctx->nblocks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+                    (int)ctx->nblocks, ctx->Np, 0, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt,
+                    ctx->W, ctx->Vinv, ctx->Ud, ctx->S);
+                ctx->launches++;
+            }
+            CU(cudaGetLastError());
+        }
         CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pt));
         CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cam));
         // persistent ring variants: 2 stages, as many CTAs per SM as shared memory allows
@@ -99,6 +113,17 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         if (ring_pt) CU(cudaFuncSetAttribute(k_sweep_pt_ring<NA, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ring_pt));
         // the two sweeps of W V*^-1 W' v: chunk partials land in qpart (and, all-reduced, in wq)
         auto sweeps = [&](const double* v, const int* dn) -> int {
+            if (ctx->use_explicit) {
+                // wq = (sum Y W') v = -(S - U*) v from the lower triangle of the assembled S
+                TimedScope ts(ctx, T_SYMV);
+                k_symv_lower<<<ctx->symv_grid, kSymvRows + 32, kSymvSmem, ctx->stream>>>(ctx->Np, ctx->Np, N, ctx->S, v, ctx->symv_tile_ptr,
+                                                                                   ctx->symv_tiles, dn, ctx->symv_rowpart, ctx->symv_colpart);
+                k_symv_finish<<<ctx->Np / 32, 1024, 0, ctx->stream>>>(ctx->Np, N, -1.0, ctx->symv_rowpart, ctx->symv_colpart, dn, ctx->wq);
+                ctx->launches += 2;
+                CU(cudaGetLastError());
+                CHK(allreduce(ctx, ctx->wq, (size_t)N));
+                return VLG_BA_OK;
+            }
             if (n > 0) {
                 TimedScope ts(ctx, T_SWEEP_PT);
                 if (ring_pt)
@@ -193,7 +218,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             ctx->launches++;
             CU(cudaGetLastError());
         }
-        ctx->last_solver = VLG_BA_SOLVER_PCG;
+        ctx->last_solver = ctx->use_explicit ? VLG_BA_SOLVER_PCG_EXPLICIT : VLG_BA_SOLVER_PCG;
         ctx->last_pcg_iters = ctx->h_pcg->iters;
         ctx->last_pcg_relres = ctx->h_pcg->r0n2 > 0.0 ? sqrt(ctx->h_pcg->rn2 / ctx->h_pcg->r0n2) : 0.0;
     }

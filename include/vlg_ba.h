@@ -40,7 +40,11 @@ extern "C" {
 #define VLG_BA_ENCCL    -5   /* NCCL missing or failed */
 #define VLG_BA_ENUM     -6   /* numerical breakdown (non-finite cost, PCG breakdown) */
 
-enum { VLG_BA_SOLVER_AUTO = 0, VLG_BA_SOLVER_CHOL = 1, VLG_BA_SOLVER_PCG = 2 };
+/* CHOL: dense blocked Cholesky of the assembled S.  PCG: block-Jacobi PCG on the implicit Schur complement
+ * (two sweeps over W per iteration).  PCG_EXPLICIT: the same PCG on the assembled dense S, one symmetric
+ * lower-triangle matvec per iteration -- cheaper than the sweeps when 4 (6m)^2 bytes << 304 bytes x nobs.
+ * AUTO: CHOL when m <= chol_max_cams, else PCG_EXPLICIT when 6 (6m)^2 < 304 nobs and S fits in 8 GB, else PCG. */
+enum { VLG_BA_SOLVER_AUTO = 0, VLG_BA_SOLVER_CHOL = 1, VLG_BA_SOLVER_PCG = 2, VLG_BA_SOLVER_PCG_EXPLICIT = 3 };
 enum { VLG_BA_RTABLE_HOST_LIBM = 0, VLG_BA_RTABLE_DEVICE = 1 };
 enum { VLG_BA_ORDER_CHUNKED = 0, VLG_BA_ORDER_REFERENCE = 1 };
 
@@ -80,7 +84,7 @@ typedef struct vlg_ba_trial_info {
     double lambda_next;
     double nu_next;
     int    accepted;
-    int    solver_used;   /* VLG_BA_SOLVER_CHOL or VLG_BA_SOLVER_PCG */
+    int    solver_used;   /* VLG_BA_SOLVER_CHOL, VLG_BA_SOLVER_PCG or VLG_BA_SOLVER_PCG_EXPLICIT */
     int    pcg_iters;
     double pcg_relres;
     float  ms_stage1;     /* residual + Jacobian + U,V,W,eA,eB       (mex1) */

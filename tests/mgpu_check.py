@@ -26,7 +26,7 @@ def main():
         return bytes(uid.cpu().numpy().tobytes())
 
     results = {}
-    for solver in (capi.SOLVER_PCG, capi.SOLVER_CHOL):
+    for solver in (capi.SOLVER_PCG, capi.SOLVER_CHOL, capi.SOLVER_PCG_EXPLICIT):
         ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12, device=local)
         ctx.set_comm(rank, world, fresh_uid())
         xy, pt, cam, bl, _ = shard.shard_points(P.obs_xy, P.obs_pt, P.obs_cam, b, rank, world)
@@ -36,7 +36,7 @@ def main():
         ctx.close()
     if rank == 0:
         ref = {}
-        for solver in (capi.SOLVER_PCG, capi.SOLVER_CHOL):
+        for solver in (capi.SOLVER_PCG, capi.SOLVER_CHOL, capi.SOLVER_PCG_EXPLICIT):
             ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12, device=local)
             ctx.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
             ref[solver] = [ctx.trial_step() for _ in range(3)]

@@ -127,7 +127,7 @@ def test_stage2_stage3_vs_golden(name):
 
 
 @pytest.mark.parametrize("name", golden_names())
-@pytest.mark.parametrize("solver", [capi.SOLVER_CHOL, capi.SOLVER_PCG])
+@pytest.mark.parametrize("solver", [capi.SOLVER_CHOL, capi.SOLVER_PCG, capi.SOLVER_PCG_EXPLICIT])
 def test_teacher_forced_cost_trajectory(name, solver):
     """Every iteration of the reference's trajectory, restarted from the reference's exact
     (a, b, lambda): old cost, new cost, accept decision."""
@@ -173,7 +173,7 @@ def test_medium_problem_vs_sparse_oracle():
     obs = lm.ObsList(P.m, P.n, P.obs_xy, P.obs_pt, P.obs_cam)
     o = lm.parse_options(P.m, P.n, np.ones((2, 1, 1)), ["fix_calibration", "visibility", np.zeros(0)])
     t = lm.lm_trial(P.K, a, b, obs, 1e-3, o, backend="sparse")
-    for solver in (capi.SOLVER_CHOL, capi.SOLVER_PCG):
+    for solver in (capi.SOLVER_CHOL, capi.SOLVER_PCG, capi.SOLVER_PCG_EXPLICIT):
         ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12)
         ctx.set_problem_sparse(P.K.T, a.T, b.T, P.obs_xy, P.obs_pt, P.obs_cam)
         J = ctx.get_jacobians()
@@ -300,15 +300,17 @@ def test_large_problem_invariants():
     P = synth.make_config("trafalgar", seed=0)
     a = np.vstack([P.w, P.Te]); b = P.Xe[:3].copy()
     news = {}
-    for solver in (capi.SOLVER_CHOL, capi.SOLVER_PCG):
+    for solver in (capi.SOLVER_CHOL, capi.SOLVER_PCG, capi.SOLVER_PCG_EXPLICIT):
         ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-10)
         ctx.set_problem_sparse(P.K.T, a.T, b.T, P.obs_xy, P.obs_pt, P.obs_cam)
         i1 = ctx.trial_step()
         assert i1["accepted"] and i1["new_cost"] < i1["old_cost"]
+        assert i1["solver_used"] == solver
         news[solver] = i1["new_cost"]
-        if solver == capi.SOLVER_PCG:
+        if solver != capi.SOLVER_CHOL:
             ctx.set_state(a=a.T, b=b.T, lam=1e-3, nu=2.0)
             i2 = ctx.trial_step()
             assert i2["new_cost"] == i1["new_cost"] and i2["old_cost"] == i1["old_cost"]
         ctx.close()
     assert rel(news[capi.SOLVER_PCG], news[capi.SOLVER_CHOL]) <= COST_RTOL
+    assert rel(news[capi.SOLVER_PCG_EXPLICIT], news[capi.SOLVER_CHOL]) <= COST_RTOL
