@@ -226,7 +226,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         lm_step()
     barrier()
-    ctx.reset_timers(True)
+    # timed region: K steps, CUDA events on the library's stream, no per-kernel instrumentation
+    ctx.reset_timers(False)
     l0 = ctx.kernel_launches
     with ClockSampler(local) as clk:
         ctx.timer_start()
@@ -235,6 +236,14 @@ def run_ours(args):
         ms = ctx.timer_stop()
         barrier()
     launches = ctx.kernel_launches - l0
+    # the same K steps again with a CUDA-event pair around every kernel group (feeds `roofline` and
+    # `kernels`; the event records cost a few us per launch, so this pass is not the one `value` comes from)
+    ctx.reset_timers(True)
+    ctx.timer_start()
+    for _ in range(args.steps):
+        lm_step()
+    ms_instr = ctx.timer_stop()
+    barrier()
     groups = {}
     for g in ("stage1_cam", "stage1_pt", "w_copy", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt", "pcg_sweep_cam",
               "pcg_symv", "pcg_update", "stage3"):
@@ -318,7 +327,7 @@ def run_ours(args):
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": groups[dom]["avg_ms"],
                     "launches": groups[dom]["count"], "peak_source": peak_kind,
-                    "share_of_step": groups[dom]["total_ms"] / (ms * 1.0)}
+                    "share_of_step": groups[dom]["total_ms"] / (ms_instr * 1.0)}
         per_kernel = {}
         for g, v in groups.items():
             if v["count"]:
@@ -344,6 +353,7 @@ def run_ours(args):
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
             "lm_iters_per_sec": args.steps / (ms_max * 1e-3),
+            "ms_per_step_instrumented": ms_instr / args.steps,
             "jacobian_schur_obs_per_sec": (nobs_total * args.steps / (js * 1e-3)) if js > 0 else None,
             "pcg_iters_mean": float(np.mean([i["pcg_iters"] for i in infos])),
             "accepted_steps": int(sum(i["accepted"] for i in infos)),
