@@ -476,150 +476,6 @@ __global__ void k_ebar_from_Y(int m, const int* __restrict__ cam_ptr, const int*
 }
 
 // ---------------------------------------------------------------------------------------
-// dense blocked Cholesky of S (lower triangle, column-major, leading dimension ld, order
-// Np = multiple of 32), right-looking, 32-wide panels, with elimination of non-positive
-// pivots (pinv semantics for the exactly-zero rows/columns of S: bundle_euclid.m:193).
-// ---------------------------------------------------------------------------------------
-constexpr int kNB = 32;
-
-__global__ void __launch_bounds__(kNB * kNB) k_chol_potrf(double* __restrict__ S, int ld, int kb)
-{
-    __shared__ double A[kNB][kNB + 1];
-    const int tx = threadIdx.x, ty = threadIdx.y;   // tx = column, ty = row
-    double* D = S + (size_t)kb * kNB + (size_t)ld * kb * kNB;
-    A[ty][tx] = D[ty + (size_t)ld * tx];
-    __syncthreads();
-    for (int j = 0; j < kNB; j++) {
-        if (tx == j && ty == j) {
-            const double d = A[j][j];
-            A[j][j] = d > 0.0 ? sqrt(d) : 0.0;
-        }
-        __syncthreads();
-        if (tx == j && ty > j) {
-            const double d = A[j][j];
-            A[ty][j] = d != 0.0 ? A[ty][j] / d : 0.0;
-        }
-        __syncthreads();
-        if (tx > j && ty >= tx) A[ty][tx] -= A[ty][j] * A[tx][j];
-        __syncthreads();
-    }
-    if (ty >= tx) D[ty + (size_t)ld * tx] = A[ty][tx];
-}
-
-// panel: X = A_ib,kb * L_kk^-T, one thread per row
-__global__ void __launch_bounds__(kNB) k_chol_trsm(double* __restrict__ S, int ld, int kb)
-{
-    __shared__ double L[kNB][kNB + 1];
-    const int ib = kb + 1 + blockIdx.x;
-    const int t = threadIdx.x;
-    const double* D = S + (size_t)kb * kNB + (size_t)ld * kb * kNB;
-    for (int c = 0; c < kNB; c++) L[t][c] = D[t + (size_t)ld * c];
-    __syncthreads();
-    double* P = S + (size_t)ib * kNB + (size_t)ld * kb * kNB;
-    double x[kNB];
-#pragma unroll
-    for (int c = 0; c < kNB; c++) x[c] = P[t + (size_t)ld * c];
-#pragma unroll
-    for (int c = 0; c < kNB; c++) {
-        double s = x[c];
-#pragma unroll
-        for (int q = 0; q < c; q++) s -= x[q] * L[c][q];
-        const double d = L[c][c];
-        x[c] = d != 0.0 ? s / d : 0.0;
-    }
-#pragma unroll
-    for (int c = 0; c < kNB; c++) P[t + (size_t)ld * c] = x[c];
-}
-
-// trailing update: C_ib,jb -= X_ib X_jb' for ib >= jb > kb (lower triangle only)
-__global__ void __launch_bounds__(256) k_chol_syrk(double* __restrict__ S, int ld, int kb)
-{
-    const int jb = kb + 1 + blockIdx.x, ib = kb + 1 + blockIdx.y;
-    if (ib < jb) return;
-    __shared__ double Xi[kNB][kNB + 1], Xj[kNB][kNB + 1];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 2 x 2 outputs each
-    const double* Pi = S + (size_t)ib * kNB + (size_t)ld * kb * kNB;
-    const double* Pj = S + (size_t)jb * kNB + (size_t)ld * kb * kNB;
-    for (int t = threadIdx.x; t < kNB * kNB; t += 256) {
-        const int r = t & 31, c = t >> 5;
-        Xi[r][c] = Pi[r + (size_t)ld * c];
-        Xj[r][c] = Pj[r + (size_t)ld * c];
-    }
-    __syncthreads();
-    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-#pragma unroll
-    for (int q = 0; q < kNB; q++) {
-        const double a0 = Xi[ty][q], a1 = Xi[ty + 16][q], b0 = Xj[tx][q], b1 = Xj[tx + 16][q];
-        c00 += a0 * b0; c01 += a0 * b1; c10 += a1 * b0; c11 += a1 * b1;
-    }
-    double* Cb = S + (size_t)ib * kNB + (size_t)ld * jb * kNB;
-    Cb[ty + (size_t)ld * tx] -= c00;
-    Cb[ty + (size_t)ld * (tx + 16)] -= c01;
-    Cb[ty + 16 + (size_t)ld * tx] -= c10;
-    Cb[ty + 16 + (size_t)ld * (tx + 16)] -= c11;
-}
-
-// x = S^+ rhs from the factor: forward then backward substitution, one CTA, x in shared
-// memory; eliminated pivots (L_cc = 0) give x_c = 0 (pinv of the zero rows of S).
-__global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ L, int ld, int Np, int N,
-                                                     const double* __restrict__ rhs, double* __restrict__ x_out)
-{
-    extern __shared__ double x[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int t = tid; t < Np; t += 1024) x[t] = t < N ? rhs[t] : 0.0;
-    __syncthreads();
-    const int nb = Np / kNB;
-    for (int kb = 0; kb < nb; kb++) {           // L y = rhs
-        if (warp == 0) {
-            const double* D = L + (size_t)kb * kNB + (size_t)ld * kb * kNB;
-            double y = x[kb * kNB + lane];
-            for (int c = 0; c < kNB; c++) {
-                const double d = D[c + (size_t)ld * c];
-                double yc = __shfl_sync(0xffffffffu, y, c);
-                yc = d != 0.0 ? yc / d : 0.0;
-                if (lane == c) y = yc;
-                if (lane > c) y -= D[lane + (size_t)ld * c] * yc;
-            }
-            x[kb * kNB + lane] = y;
-        }
-        __syncthreads();
-        for (int r = (kb + 1) * kNB + tid; r < Np; r += 1024) {
-            double s = x[r];
-            const double* Lr = L + r + (size_t)ld * kb * kNB;
-#pragma unroll 8
-            for (int c = 0; c < kNB; c++) s -= Lr[(size_t)ld * c] * x[kb * kNB + c];
-            x[r] = s;
-        }
-        __syncthreads();
-    }
-    for (int kb = nb - 1; kb >= 0; kb--) {      // L' x = y
-        {   // warp w handles column c = w: s_c = sum_{r below block} L[r][c] x[r]
-            const int c = kb * kNB + warp;
-            double s = 0.0;
-            for (int r = (kb + 1) * kNB + lane; r < Np; r += 32) s += L[r + (size_t)ld * c] * x[r];
-            s = warp_sum(s);
-            __syncthreads();
-            if (lane == 0) x[c] -= s;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const double* D = L + (size_t)kb * kNB + (size_t)ld * kb * kNB;
-            double y = x[kb * kNB + lane];
-            for (int c = kNB - 1; c >= 0; c--) {
-                const double d = D[c + (size_t)ld * c];
-                double yc = __shfl_sync(0xffffffffu, y, c);
-                yc = d != 0.0 ? yc / d : 0.0;
-                if (lane == c) y = yc;
-                if (lane < c) y -= D[c + (size_t)ld * lane] * yc;
-            }
-            x[kb * kNB + lane] = y;
-        }
-        __syncthreads();
-    }
-    for (int t = tid; t < N; t += 1024) x_out[t] = x[t];
-}
-
-// ---------------------------------------------------------------------------------------
 // implicit Schur matvec q = S p = U* p - W V*^-1 W' p (never forming S), two sweeps.
 // ---------------------------------------------------------------------------------------
 // sweep 1, point-keyed: t_i = V*_i^-1 sum_j W_ij' p_j  (one thread per point, ascending j)

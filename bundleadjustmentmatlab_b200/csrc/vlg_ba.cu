@@ -6,6 +6,7 @@
 // that the single-GPU library has no NCCL dependency.
 #include "../../include/vlg_ba.h"
 #include "ba_kernels.cuh"
+#include "ba_chol.cuh"
 #include "ba_pcg.cuh"
 
 #include <cuda_runtime.h>
@@ -120,6 +121,9 @@ struct vlg_ba_ctx {
     double *W = nullptr, *Upart = nullptr, *V = nullptr, *eB = nullptr, *cost_pt = nullptr, *red_part = nullptr;
     // device: stage 2
     double *Ud = nullptr, *Vinv = nullptr, *Spart = nullptr, *S = nullptr;
+    double *chol_R = nullptr, *chol_Ld = nullptr, *chol_Dinv = nullptr;
+    unsigned int* chol_bar = nullptr;   // k_chol_coop: right-hand-side row tiles, factored diagonal tiles
+    int chol_grid = 0;
     double *red2 = nullptr, *Sjj = nullptr, *ebar = nullptr;   // red2 = per-camera sums [m][NU], all-reduced
     double *Minv = nullptr, *da = nullptr;
     double *pr = nullptr, *pz = nullptr, *pp = nullptr, *pq = nullptr, *wq = nullptr, *tvec = nullptr, *qpart = nullptr;
@@ -545,6 +549,19 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         CU(cudaStreamSynchronize(ctx->stream));
         CHK(dalloc(ctx, &ctx->symv_rowpart, (size_t)nstrips * Np));
         CHK(dalloc(ctx, &ctx->symv_colpart, (size_t)ctx->nsymv_seg * Np));
+    }
+    if (ctx->use_chol) {
+        const int nb = ctx->Np / kNB;
+        CHK(dalloc(ctx, &ctx->chol_R, (size_t)nb * kNB * kNB)); CHK(dalloc(ctx, &ctx->chol_Ld, (size_t)nb * kNB * kNB));
+        CHK(dalloc(ctx, &ctx->chol_Dinv, (size_t)ctx->Np)); CHK(dalloc(ctx, &ctx->chol_bar, 1));
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (!coop) return fail(ctx, VLG_BA_ECUDA, "device lacks cooperative launch (needed by k_chol_coop)");
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_coop, kCholWarps * 32, 0));
+        if (per_sm < 1) return fail(ctx, VLG_BA_ECUDA, "k_chol_coop does not fit an SM");
+        // enough CTAs for the first trailing update (one 32 x 32 tile per warp), never more than one per SM
+        const int64_t tiles = (int64_t)nb * (nb + 1) / 2;
+        ctx->chol_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->nsm, (tiles + kCholWarps - 1) / kCholWarps));
     }
     if (need_S) {
         CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));

@@ -59,19 +59,12 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         CHK(allreduce(ctx, ctx->S, (size_t)Np * Np));
         {
             TimedScope ts(ctx, T_CHOL);
-            for (int kb = 0; kb < nb; kb++) {
-                k_chol_potrf<<<1, dim3(kNB, kNB), 0, ctx->stream>>>(ctx->S, Np, kb);
-                ctx->launches++;
-                const int rem = nb - kb - 1;
-                if (rem > 0) {
-                    k_chol_trsm<<<rem, kNB, 0, ctx->stream>>>(ctx->S, Np, kb);
-                    k_chol_syrk<<<dim3(rem, rem), 256, 0, ctx->stream>>>(ctx->S, Np, kb);
-                    ctx->launches += 2;
-                }
-            }
-            const size_t smem = sizeof(double) * (size_t)Np;
-            CU(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-            k_chol_solve<<<1, 1024, smem, ctx->stream>>>(ctx->S, Np, Np, N, ctx->ebar, ctx->da);
+            CholArgs ca;
+            ca.S = ctx->S; ca.ld = Np; ca.nb = nb; ca.N = N; ca.rhs = ctx->ebar; ca.R = ctx->chol_R; ca.Ld = ctx->chol_Ld; ca.x = ctx->da;
+            ca.Dinv = ctx->chol_Dinv; ca.barrier = ctx->chol_bar;
+            CU(cudaMemsetAsync(ctx->chol_bar, 0, sizeof(unsigned int), ctx->stream));
+            void* args[] = {&ca};
+            CU(cudaLaunchCooperativeKernel((void*)k_chol_coop, dim3(ctx->chol_grid), dim3(kCholWarps * 32), args, 0, ctx->stream));
             ctx->launches++;
         }
         CU(cudaGetLastError());
