@@ -37,6 +37,7 @@ struct CholArgs {
     double* Ld;      // nb factored diagonal tiles, 32 x 32 (ld 32), upper part zero
     double* Dinv;    // Np reciprocals of the factor's diagonal (0 = eliminated pivot)
     unsigned int* barrier;   // grid barrier counter, zero at launch
+    long long* prof;         // optional (tools/chol_probe.cu): clock64 totals per phase seen by CTA 0 thread 0, or NULL
     double* x;       // N: solution
 };
 
@@ -87,30 +88,69 @@ __device__ __forceinline__ void tile_update_dmma(double* __restrict__ C, int ldc
             for (int e = 0; e < 2; e++) C[(8 * mb + g) + (size_t)ldc * (8 * nbk + 2 * q + e)] = c[mb][nbk][e];
 }
 
+// 1/d and 1/sqrt(d) for d > 0 from the hardware's double-precision seeds (MUFU.RCP64H / RSQ64H,
+// ~20 bits) and two Newton steps: branch-free, 4-5 dependent FP64 operations.  d <= 0 gives 0
+// (eliminated pivot).  FP64 operations have ~30-cycle latency on this part, so the number of
+// DEPENDENT operations per pivot is what the factorisation's critical path is made of.
+__device__ __forceinline__ double fast_rcp_pos(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return d > 0.0 ? r : 0.0;
+}
+
+__device__ __forceinline__ double fast_rsqrt_pos(double d)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double hd = 0.5 * d;
+    r = r * fma(-hd * r, r, 1.5);
+    r = r * fma(-hd * r, r, 1.5);
+    return d > 0.0 ? r : 0.0;
+}
+
 // Cholesky of a 32 x 32 block by one warp: lane r holds row r (a[c], c <= r used).  Pivots <= 0
 // eliminate their row and column.  On return a[c] = L[r][c] for c <= r and 0 above; the return value
-// is 1 / L[r][r] (0 for an eliminated pivot).  The pivot chain is the critical path of the whole
-// factorisation, so it uses one rsqrt per pivot (L_jj = d * rsqrt(d), column scaled by the same
-// reciprocal) instead of a square root and 31 divisions.
-__device__ __forceinline__ double potrf_warp(double (&a)[kNB], int lane)
+// is 1 / L[r][r] (0 for an eliminated pivot).
+// The chain of 32 dependent pivots is the critical path of the whole factorisation.  It runs in
+// LDL' form -- per pivot: reciprocal of the diagonal entry (own scalar of lane j), one shuffle,
+// t = u / d, own diagonal entry -= t * u -- with the columns left unscaled and broadcast through
+// shared memory (col: 2 x 32 doubles) off the chain; the 32 reciprocal square roots that turn
+// L D L' into L L' are taken at the end, all at once.
+__device__ __forceinline__ double potrf_warp(double (&a)[kNB], int lane, double* __restrict__ col)
 {
-    double my_inv = 0.0;
+    double dg = 0.0, dpiv = 0.0;
+#pragma unroll
+    for (int c = 0; c < kNB; c++)
+        if (lane == c) dg = a[c];
 #pragma unroll
     for (int j = 0; j < kNB; j++) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
-        const double rinv = d > 0.0 ? rsqrt(d) : 0.0;
-        if (lane == j) { a[j] = d * rinv; my_inv = rinv; }
-        else if (lane > j) a[j] = a[j] * rinv;
-        else a[j] = 0.0;
+        double* cb = col + (j & 1) * kNB;
+        cb[lane] = lane > j ? a[j] : 0.0;                       // column j, unscaled (known before 1/d_j is)
+        const double rcp = __shfl_sync(0xffffffffu, fast_rcp_pos(dg), j);
+        if (lane == j) dpiv = dg;
+        const double t = lane > j ? a[j] * rcp : 0.0;           // u_rj / d_j
+        dg = lane > j ? fma(-t, a[j], dg) : 1.0;                // own diagonal entry; finished lanes keep a benign value
+        if (lane < j) a[j] = 0.0;
 #pragma unroll
-        for (int c = 0; c < kNB; c++) {
-            if (c > j) {                 // constant after unrolling (a[] must stay in registers)
-                const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-                if (lane >= c) a[c] -= a[j] * lcj;
-            }
-        }
+        for (int c = 0; c < kNB; c++)
+            if (c > j) a[c] = fma(-t, cb[c], a[c]);             // lanes <= j have t = 0; entries above the diagonal are junk, never read
     }
-    return my_inv;
+    // L = U diag(1/sqrt(d)): lane c publishes its 1/sqrt(d_c)
+    const double rs = fast_rsqrt_pos(dpiv);
+    __syncwarp();
+    col[lane] = rs;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < kNB; c++) {
+        const double v = a[c] * col[c];
+        a[c] = lane > c ? v : (lane == c ? dpiv * rs : 0.0);
+    }
+    return rs;
 }
 
 // x (row of 32, one per lane) <- x * L^-T with L in shared memory (ld kLsLd) and the reciprocals
@@ -174,12 +214,23 @@ __device__ __forceinline__ void row_tile_store(const CholArgs& p, int i, int kn,
     for (int c = 0; c < kNB; c++) T[lane + (size_t)ldt * c] = x[c];
 }
 
+#define CHOL_PROF(slot)                                                          \
+    do {                                                                         \
+        if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) {                     \
+            const long long now_ = clock64();                                    \
+            p.prof[slot] += now_ - prof_t;                                       \
+            prof_t = now_;                                                       \
+        }                                                                        \
+    } while (0)
+
 __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
 {
+    long long prof_t = p.prof ? clock64() : 0;
     __shared__ double Xs[kNB * kLsLd];     // X[kb+1][kb] (row-major with pad): Xs[c * kLsLd + k]
     __shared__ double Ls[kNB * kLsLd];     // diagonal tile being formed / its factor: Ls[r * kLsLd + c]
     __shared__ double dinv[kNB];           // reciprocal diagonal of the factor
     __shared__ double xsol[kNB];
+    __shared__ __align__(16) double pcol[2 * kNB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x, nb = p.nb;
     const int gw = cta * kCholWarps + warp, nwarps = G * kCholWarps;
@@ -192,11 +243,20 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
         p.R[t] = (row == 0 && u < p.N) ? p.rhs[u] : 0.0;
     }
     grid_barrier(p.barrier, bar_target, G);
+    CHOL_PROF(0);
 
     // ---- factorisation: step kb = -1 is the prologue (no previous panel), steps 0..nb-2 carry a trailing update
     for (int kb = -1; kb < nb - 1; kb++) {
         const int kn = kb + 1;                       // panel finished by this step
-        // (1) X[kn][kb] into shared memory
+        // (1) X[kn][kb] into shared memory; this warp's 4 columns of the next diagonal tile are requested
+        //     at the same time (they do not depend on the panel)
+        double dv[kNB / kCholWarps];
+        {
+            const double* A = p.S + (size_t)kNB * kn + (size_t)p.ld * kNB * kn;
+#pragma unroll
+            for (int cc = 0; cc < kNB / kCholWarps; cc++)
+                dv[cc] = __ldcg(A + lane + (size_t)p.ld * (warp * (kNB / kCholWarps) + cc));
+        }
         if (kb >= 0) {
             const double* X = p.S + (size_t)kNB * kn + (size_t)p.ld * kNB * kb;
             for (int t = tid; t < kNB * kNB; t += blockDim.x) {
@@ -205,23 +265,23 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
             }
         }
         __syncthreads();
+        CHOL_PROF(1);
         // (2) the next diagonal tile, brought up to date: every CTA, 4 columns per warp
-        {
-            const double* A = p.S + (size_t)kNB * kn + (size_t)p.ld * kNB * kn;
-#pragma unroll
-            for (int cc = 0; cc < kNB / kCholWarps; cc++) {
-                const int c = warp * (kNB / kCholWarps) + cc;
-                double v = __ldcg(A + lane + (size_t)p.ld * c);
-                if (kb >= 0) {
+        if (kb >= 0) {
 #pragma unroll 8
-                    for (int k = 0; k < kNB; k++) v -= Xs[lane * kLsLd + k] * Xs[c * kLsLd + k];
-                }
-                Ls[lane * kLsLd + c] = v;
+            for (int k = 0; k < kNB; k++) {
+                const double xr = Xs[lane * kLsLd + k];
+#pragma unroll
+                for (int cc = 0; cc < kNB / kCholWarps; cc++) dv[cc] -= xr * Xs[(warp * (kNB / kCholWarps) + cc) * kLsLd + k];
             }
         }
+#pragma unroll
+        for (int cc = 0; cc < kNB / kCholWarps; cc++) Ls[lane * kLsLd + warp * (kNB / kCholWarps) + cc] = dv[cc];
         __syncthreads();
-        // (3) warp 0 factors it while the row-tile owners (warps 1..7: the q-th row tile of this CTA
-        //     belongs to warp 1 + q % 7) bring their first tile of panel kn up to date
+        CHOL_PROF(2);
+        // (3) warp 0 factors it.  Meanwhile warps 1..7 bring their row tile of panel kn up to date (the
+        //     q-th row tile of this CTA belongs to warp 1 + q % 7) and run the trailing update with
+        //     panel kb: tiles (i, j), kn < j < nb, j <= i <= nb, dealt round-robin to the non-factoring warps
         int i_mine = -1;
         if (warp > 0) {
             const int i = kn + 1 + cta + G * (warp - 1);
@@ -231,7 +291,7 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
         if (warp == 0) {
 #pragma unroll
             for (int c = 0; c < kNB; c++) x[c] = Ls[lane * kLsLd + c];
-            const double inv = potrf_warp(x, lane);
+            const double inv = potrf_warp(x, lane, pcol);
 #pragma unroll
             for (int c = 0; c < kNB; c++) Ls[lane * kLsLd + c] = x[c];
             dinv[lane] = inv;
@@ -240,10 +300,25 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
                 for (int c = 0; c < kNB; c++) p.Ld[(size_t)kNB * kNB * kn + lane + kNB * c] = x[c];
                 p.Dinv[kNB * kn + lane] = inv;
             }
-        } else if (i_mine >= 0) {
-            row_tile_update(p, i_mine, kn, kb, Xs, lane, x);
+        } else {
+            if (i_mine >= 0) row_tile_update(p, i_mine, kn, kb, Xs, lane, x);
+            if (kb >= 0) {
+                int j = kn + 1, cnt = nb - j + 1;
+                for (int t = cta * (kCholWarps - 1) + warp - 1; j < nb; t += G * (kCholWarps - 1)) {
+                    while (j < nb && t >= cnt) { t -= cnt; j++; cnt--; }
+                    if (j >= nb) break;
+                    const int i = j + t;
+                    int ldc, ldi, ldj;
+                    double* C = chol_tile(p, i, j, ldc);
+                    const double* Xi = chol_tile(p, i, kb, ldi);
+                    const double* Xj = chol_tile(p, j, kb, ldj);
+                    tile_update_dmma(C, ldc, Xi, ldi, Xj, ldj, lane);
+                }
+            }
         }
+        CHOL_PROF(3);
         __syncthreads();
+        CHOL_PROF(4);
         // (4) solve against the new factor; further row tiles of this warp follow one by one
         if (i_mine >= 0) {
             trsm_row(x, Ls, dinv);
@@ -254,33 +329,49 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
                 row_tile_store(p, i, kn, lane, x);
             }
         }
-        // (5) trailing update with panel kb: tiles (i, j), kn < j < nb, j <= i <= nb
-        if (kb >= 0) {
-            int j = kn + 1, cnt = nb - j + 1;
-            for (int t = gw; j < nb; t += nwarps) {
-                while (j < nb && t >= cnt) { t -= cnt; j++; cnt--; }
-                if (j >= nb) break;
-                const int i = j + t;
-                int ldc, ldi, ldj;
-                double* C = chol_tile(p, i, j, ldc);
-                const double* Xi = chol_tile(p, i, kb, ldi);
-                const double* Xj = chol_tile(p, j, kb, ldj);
-                tile_update_dmma(C, ldc, Xi, ldi, Xj, ldj, lane);
-            }
-        }
+        CHOL_PROF(5);
         grid_barrier(p.barrier, bar_target, G);
+        CHOL_PROF(6);
     }
 
-    // ---- backward solve L' x = y, y in row 0 of the extra row tile
+    // ---- backward solve L' x = y, y in row 0 of the extra row tile.  Everything that does not depend on
+    //      x_kb (the factor tiles, the y entries to be updated) is requested before the triangular solve.
+    double ldpre[kNB * kNB / (kCholWarps * 32)];
+    double dipre = 0.0;
+    {
+        const int kb = nb - 1;
+#pragma unroll
+        for (int u = 0; u < kNB * kNB / (kCholWarps * 32); u++) ldpre[u] = __ldcg(p.Ld + (size_t)kNB * kNB * kb + tid + u * kCholWarps * 32);
+        if (tid < kNB) dipre = __ldcg(p.Dinv + kNB * kb + tid);
+    }
     for (int kb = nb - 1; kb >= 0; kb--) {
-        for (int t = tid; t < kNB * kNB; t += blockDim.x) {
-            const int r = t % kNB, c = t / kNB;
-            Ls[r * kLsLd + c] = __ldcg(p.Ld + (size_t)kNB * kNB * kb + t);
+#pragma unroll
+        for (int u = 0; u < kNB * kNB / (kCholWarps * 32); u++) {
+            const int t = tid + u * kCholWarps * 32, r = t % kNB, c = t / kNB;
+            Ls[r * kLsLd + c] = ldpre[u];
         }
-        if (tid < kNB) dinv[tid] = __ldcg(p.Dinv + kNB * kb + tid);
+        if (tid < kNB) dinv[tid] = dipre;
+        // this warp's first tile of row kb and its y
+        const int j0 = gw;
+        double2 lt[kNB / 2];
+        double yj0 = 0.0;
+        if (j0 < kb) {
+            const double* Lt = p.S + (size_t)kNB * kb + (size_t)p.ld * (kNB * j0 + lane);
+#pragma unroll
+            for (int r = 0; r < kNB / 2; r++) lt[r] = __ldcg(reinterpret_cast<const double2*>(Lt) + r);
+            yj0 = __ldcg(p.R + (size_t)kNB * kNB * j0 + kNB * lane);
+        }
+        double yk = 0.0;
+        if (warp == 0) yk = __ldcg(p.R + (size_t)kNB * kNB * kb + kNB * lane);      // lane = column c
+        if (kb > 0) {
+#pragma unroll
+            for (int u = 0; u < kNB * kNB / (kCholWarps * 32); u++) ldpre[u] = __ldcg(p.Ld + (size_t)kNB * kNB * (kb - 1) + tid + u * kCholWarps * 32);
+            if (tid < kNB) dipre = __ldcg(p.Dinv + kNB * (kb - 1) + tid);
+        }
         __syncthreads();
+        CHOL_PROF(7);
         if (warp == 0) {
-            double y = __ldcg(p.R + (size_t)kNB * kNB * kb + kNB * lane);      // lane = column c
+            double y = yk;
 #pragma unroll
             for (int r = kNB - 1; r >= 0; r--) {
                 const double xr = __shfl_sync(0xffffffffu, y, r) * dinv[r];
@@ -291,8 +382,15 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
             if (cta == 0 && kNB * kb + lane < p.N) p.x[kNB * kb + lane] = y;
         }
         __syncthreads();
+        CHOL_PROF(8);
         // y_j -= L[kb][j]' x_kb for j < kb: lane = column, its 32 rows are contiguous
-        for (int j = gw; j < kb; j += nwarps) {
+        if (j0 < kb) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < kNB / 2; r++) s += lt[r].x * xsol[2 * r] + lt[r].y * xsol[2 * r + 1];
+            p.R[(size_t)kNB * kNB * j0 + kNB * lane] = yj0 - s;
+        }
+        for (int j = j0 + nwarps; j < kb; j += nwarps) {
             const double* Lt = p.S + (size_t)kNB * kb + (size_t)p.ld * (kNB * j + lane);
             double s = 0.0;
 #pragma unroll
@@ -303,7 +401,9 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) k_chol_coop(CholArgs p)
             double* yj = p.R + (size_t)kNB * kNB * j + kNB * lane;
             *yj = __ldcg(yj) - s;
         }
+        CHOL_PROF(9);
         if (kb > 0) grid_barrier(p.barrier, bar_target, G);
+        CHOL_PROF(10);
     }
 }
 

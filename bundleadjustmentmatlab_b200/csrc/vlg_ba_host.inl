@@ -61,7 +61,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             TimedScope ts(ctx, T_CHOL);
             CholArgs ca;
             ca.S = ctx->S; ca.ld = Np; ca.nb = nb; ca.N = N; ca.rhs = ctx->ebar; ca.R = ctx->chol_R; ca.Ld = ctx->chol_Ld; ca.x = ctx->da;
-            ca.Dinv = ctx->chol_Dinv; ca.barrier = ctx->chol_bar;
+            ca.Dinv = ctx->chol_Dinv; ca.barrier = ctx->chol_bar; ca.prof = nullptr;
             CU(cudaMemsetAsync(ctx->chol_bar, 0, sizeof(unsigned int), ctx->stream));
             void* args[] = {&ca};
             CU(cudaLaunchCooperativeKernel((void*)k_chol_coop, dim3(ctx->chol_grid), dim3(kCholWarps * 32), args, 0, ctx->stream));

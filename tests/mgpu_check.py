@@ -25,31 +25,45 @@ def main():
         dist.broadcast(uid, 0)
         return bytes(uid.cpu().numpy().tobytes())
 
-    results = {}
-    for solver in (capi.SOLVER_PCG, capi.SOLVER_CHOL, capi.SOLVER_PCG_EXPLICIT):
+    solvers = (capi.SOLVER_PCG, capi.SOLVER_CHOL, capi.SOLVER_PCG_EXPLICIT)
+    nsteps = 3
+    # single-GPU trajectory on every rank's own device (identical inputs, deterministic kernels =>
+    # identical on all ranks): the state before each trial step and what the step did
+    ref = {}
+    for solver in solvers:
+        ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12, device=local)
+        ctx.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
+        steps = []
+        for _ in range(nsteps):
+            st = ctx.get_state()
+            steps.append((st, ctx.trial_step()))
+        ref[solver] = steps
+        ctx.close()
+    # G ranks, teacher-forced from the single-GPU states: the free-running trajectory is chaotic at
+    # ~1e-6 after the first accepted step (SURVEY.md finding 2: any change of summation order, here the
+    # per-shard sums + all-reduce, is amplified by the finite-difference Jacobians), so the 1e-9 bar is
+    # a per-step statement
+    worst = 0.0
+    lo_hi = shard.point_ranges(np.asarray(P.obs_pt), b.shape[0], world)
+    lo, hi = int(lo_hi[rank]), int(lo_hi[rank + 1])
+    for solver in solvers:
         ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12, device=local)
         ctx.set_comm(rank, world, fresh_uid())
         xy, pt, cam, bl, _ = shard.shard_points(P.obs_xy, P.obs_pt, P.obs_cam, b, rank, world)
         ctx.set_problem_sparse(P.K.T, a, bl, xy, pt, cam)
-        infos = [ctx.trial_step() for _ in range(3)]
-        results[solver] = infos
+        for st, info_ref in ref[solver]:
+            ctx.set_state(a=st["a"], b=np.ascontiguousarray(st["b"][lo:hi]), lam=st["lam"], nu=st["nu"])
+            info = ctx.trial_step()
+            for key in ("old_cost", "new_cost"):
+                worst = max(worst, abs(info[key] - info_ref[key]) / info_ref[key])
+            assert info["accepted"] == info_ref["accepted"], (solver, info, info_ref)
+            assert info["solver_used"] == solver
         ctx.close()
+    w = torch.tensor([worst], dtype=torch.float64, device="cuda")
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
     if rank == 0:
-        ref = {}
-        for solver in (capi.SOLVER_PCG, capi.SOLVER_CHOL, capi.SOLVER_PCG_EXPLICIT):
-            ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12, device=local)
-            ctx.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
-            ref[solver] = [ctx.trial_step() for _ in range(3)]
-            ctx.close()
-        worst = 0.0
-        for solver in ref:
-            for k in range(3):
-                for key in ("old_cost", "new_cost"):
-                    d = abs(results[solver][k][key] - ref[solver][k][key]) / ref[solver][k][key]
-                    worst = max(worst, d)
-                assert results[solver][k]["accepted"] == ref[solver][k]["accepted"]
-        print(f"MGPU_OK world={world} worst relative cost deviation vs 1 GPU: {worst:.3e}")
-        assert worst <= 1e-9
+        print(f"MGPU_OK world={world} worst relative per-step cost deviation vs 1 GPU (teacher-forced): {float(w.item()):.3e}")
+    assert float(w.item()) <= 1e-9
     dist.barrier()
     dist.destroy_process_group()
 
