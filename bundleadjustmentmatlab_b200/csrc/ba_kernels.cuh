@@ -293,6 +293,35 @@ __global__ void k_vinv_damp(int n, double lambda, const double* __restrict__ V, 
     for (int k = 0; k < 9; k++) Vinv[(size_t)9 * i + k] = Vi[k];
 }
 
+// An observation's NW-double block in global memory <-> registers; 16-byte accesses when NW is even
+// (every block then starts on a 16-byte boundary): half the load/store instructions, i.e. half the
+// LSU wavefronts of a gather whose lanes all hit different lines.
+template <int NW>
+__device__ __forceinline__ void load_block_g(const double* __restrict__ base, size_t idx, double* __restrict__ w)
+{
+    if constexpr (NW % 2 == 0) {
+        const double2* src = reinterpret_cast<const double2*>(base + idx * NW);
+#pragma unroll
+        for (int k = 0; k < NW / 2; k++) { const double2 v = __ldg(src + k); w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NW; k++) w[k] = __ldg(base + idx * NW + k);
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void store_block_g(double* __restrict__ base, size_t idx, const double* __restrict__ w)
+{
+    if constexpr (NW % 2 == 0) {
+        double2* dst = reinterpret_cast<double2*>(base + idx * NW);
+#pragma unroll
+        for (int k = 0; k < NW / 2; k++) dst[k] = make_double2(w[2 * k], w[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NW; k++) base[idx * NW + k] = w[k];
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // camera-keyed Schur pieces: e_j = eA_j - sum_i Y_ij eB_i (mex_bundle_2_Se_.c:132-155) and
 // the diagonal blocks S_jj = U*_j - sum_i Y_ij W_ij' (mex_bundle_2_Se_.c:80-118 with k = j),
@@ -303,7 +332,8 @@ template <int NA>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_cam_schur_diag(int nchunks, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_end,
                  const int* __restrict__ obs_pt, const double* __restrict__ W, const double* __restrict__ Vinv,
-                 const double* __restrict__ eB, double* __restrict__ part /* [nchunks][NU] */)
+                 const double* __restrict__ eB, double* __restrict__ part /* [nchunks][NU] */,
+                 double* __restrict__ Yout = nullptr /* [nobs][3 NA], C-order: kept for the assembly of S */)
 {
     constexpr int NU = nu_of(NA);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -328,6 +358,7 @@ k_cam_schur_diag(int nchunks, const int* __restrict__ chunk_begin, const int* __
 #pragma unroll
             for (int r = 0; r < NA; r++)
                 Y[r + NA * cc] = Wo[r] * Vi[3 * cc] + Wo[r + NA] * Vi[1 + 3 * cc] + Wo[r + 2 * NA] * Vi[2 + 3 * cc];
+        if (Yout) store_block_g<3 * NA>(Yout, o, Y);
 #pragma unroll
         for (int col = 0; col < NA; col++)
 #pragma unroll
@@ -452,6 +483,122 @@ k_schur_blocks(int nblocks, int N, int add_U, const int* __restrict__ blk_j, con
             if (j == k && add_U) v += Ud[(size_t)NA * NA * j + t];
             S[(size_t)(NA * j + row) + (size_t)N * (NA * k + col)] = v;
             if (j != k) S[(size_t)(NA * k + col) + (size_t)N * (NA * j + row)] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Assembly of S at scale (explicit-S PCG, Venice shape: 0.93 M non-zero blocks, 21 M pairs).  The
+// pair counts are extremely skewed -- 2 % of the blocks (cameras that share a track window) hold
+// 92 % of the pairs, the rest hold 1-3 pairs each -- and the work per pair is a gather of two
+// 144-byte blocks, i.e. bound by LSU wavefronts (one per distinct line per instruction), not by
+// DRAM or FP64.  Hence: Y = W V*^-1 is stored once per observation by k_cam_schur_diag (a pair
+// then gathers Y_ij and W_ik with 9 + 9 16-byte loads instead of 18 + 18 + 9 8-byte ones), heavy
+// blocks get a warp each (lanes over pairs, one tree reduction per block), light blocks a thread
+// each (pairs in ascending point order, no reduction at all).
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__device__ __forceinline__ void schur_pair(const double* __restrict__ Y, const double* __restrict__ W, int2 pr,
+                                           double* __restrict__ acc)
+{
+    double Yj[3 * NA], Wk[3 * NA];
+    load_block_g<3 * NA>(Y, (size_t)pr.x, Yj);
+    load_block_g<3 * NA>(W, (size_t)pr.y, Wk);
+#pragma unroll
+    for (int col = 0; col < NA; col++)
+#pragma unroll
+        for (int row = 0; row < NA; row++)
+            acc[row + NA * col] += Yj[row] * Wk[col] + Yj[row + NA] * Wk[col + NA] + Yj[row + 2 * NA] * Wk[col + 2 * NA];
+}
+
+// v[row + NA col] -> S block (j,k) and its mirror (k,j); 16-byte stores when NA is even
+template <int NA>
+__device__ __forceinline__ void schur_store_block(double* __restrict__ S, int ld, int j, int k, const double* __restrict__ v)
+{
+    if constexpr (NA % 2 == 0) {
+#pragma unroll
+        for (int col = 0; col < NA; col++) {
+            double2* d = reinterpret_cast<double2*>(S + (size_t)(NA * j) + (size_t)ld * (NA * k + col));
+#pragma unroll
+            for (int h = 0; h < NA / 2; h++) d[h] = make_double2(v[2 * h + NA * col], v[2 * h + 1 + NA * col]);
+        }
+        if (j != k) {
+#pragma unroll
+            for (int row = 0; row < NA; row++) {
+                double2* d = reinterpret_cast<double2*>(S + (size_t)(NA * k) + (size_t)ld * (NA * j + row));
+#pragma unroll
+                for (int h = 0; h < NA / 2; h++) d[h] = make_double2(v[row + NA * (2 * h)], v[row + NA * (2 * h + 1)]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int col = 0; col < NA; col++)
+#pragma unroll
+            for (int row = 0; row < NA; row++) {
+                S[(size_t)(NA * j + row) + (size_t)ld * (NA * k + col)] = v[row + NA * col];
+                if (j != k) S[(size_t)(NA * k + col) + (size_t)ld * (NA * j + row)] = v[row + NA * col];
+            }
+    }
+}
+
+// light blocks: one thread per block, pairs in ascending point order (the reference's order of
+// summation, mex_bundle_2_Se_.c:103-118)
+template <int NA>
+__global__ void __launch_bounds__(128)
+k_schur_blocks_light(int nlist, const int* __restrict__ list, int ld, int add_U, const int* __restrict__ blk_j,
+                     const int* __restrict__ blk_k, const int64_t* __restrict__ blk_ptr, const int2* __restrict__ pairs,
+                     const double* __restrict__ Y, const double* __restrict__ W, const double* __restrict__ Ud,
+                     double* __restrict__ S)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlist) return;
+    const int b = list[t];
+    const int j = blk_j[b], k = blk_k[b];
+    double acc[NA * NA];
+#pragma unroll
+    for (int u = 0; u < NA * NA; u++) acc[u] = 0.0;
+    for (int64_t q = blk_ptr[b]; q < blk_ptr[b + 1]; q++) schur_pair<NA>(Y, W, pairs[q], acc);
+#pragma unroll
+    for (int u = 0; u < NA * NA; u++) {
+        double v = -acc[u];
+        if (j == k && add_U) v += Ud[(size_t)NA * NA * j + u];
+        acc[u] = v;
+    }
+    schur_store_block<NA>(S, ld, j, k, acc);
+}
+
+// heavy blocks: one warp per block, lanes stride over the pairs, values folded by recursive halving
+template <int NA>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_schur_blocks_heavy(int nlist, const int* __restrict__ list, int ld, int add_U, const int* __restrict__ blk_j,
+                     const int* __restrict__ blk_k, const int64_t* __restrict__ blk_ptr, const int2* __restrict__ pairs,
+                     const double* __restrict__ Y, const double* __restrict__ W, const double* __restrict__ Ud,
+                     double* __restrict__ S)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= nlist) return;
+    const int b = list[t];
+    const int j = blk_j[b], k = blk_k[b];
+    double acc[NA * NA];
+#pragma unroll
+    for (int u = 0; u < NA * NA; u++) acc[u] = 0.0;
+    for (int64_t q = blk_ptr[b] + lane; q < blk_ptr[b + 1]; q += 32) schur_pair<NA>(Y, W, pairs[q], acc);
+    double mine[(NA * NA + 31) / 32];
+#pragma unroll
+    for (int u = 0; u < NA * NA; u++) {
+        const double v = warp_sum(acc[u]);
+        if (lane == (u & 31)) mine[u >> 5] = v;
+    }
+#pragma unroll
+    for (int w = 0; w < (NA * NA + 31) / 32; w++) {
+        const int u = lane + 32 * w;
+        if (u < NA * NA) {
+            const int row = u % NA, col = u / NA;
+            double v = -mine[w];
+            if (j == k && add_U) v += Ud[(size_t)NA * NA * j + u];
+            S[(size_t)(NA * j + row) + (size_t)ld * (NA * k + col)] = v;
+            if (j != k) S[(size_t)(NA * k + col) + (size_t)ld * (NA * j + row)] = v;
         }
     }
 }

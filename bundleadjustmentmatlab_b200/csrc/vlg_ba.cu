@@ -104,6 +104,9 @@ struct vlg_ba_ctx {
     int *blk_j = nullptr, *blk_k = nullptr;
     int64_t* blk_ptr = nullptr;
     int2* pairs = nullptr;
+    int *blk_heavy = nullptr, *blk_light = nullptr;   // S-assembly work lists: blocks with many / few pairs
+    int nheavy = 0, nlight = 0;
+    double* Ybuf = nullptr;                           // Y = W V*^-1 per observation (C-order), explicit-S paths
     int4* ptile_meta = nullptr;      // point tiles of the PCG point sweep: (q0, nob, p0, npts)
     int2* chunk_meta = nullptr;      // camera chunks: (begin, nob)
     int nptiles = 0;
@@ -214,6 +217,8 @@ int download(vlg_ba_ctx* ctx, T* dst, const T* src, size_t count)
     if (count && dst) CU(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     return VLG_BA_OK;
 }
+
+constexpr int kSchurHeavy = 16;   // blocks with more pairs than this get a warp, the others a thread
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -571,6 +576,15 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         CHK(upload(ctx, ctx->blk_k, ctx->h_blk_k.data(), (size_t)ctx->nblocks));
         CHK(upload(ctx, ctx->blk_ptr, blk_ptr.data(), (size_t)ctx->nblocks + 1));
         CHK(upload(ctx, ctx->pairs, pairs.data(), (size_t)ctx->npairs));
+        {
+            std::vector<int> heavy, light;
+            for (int64_t bb = 0; bb < ctx->nblocks; bb++) (blk_ptr[bb + 1] - blk_ptr[bb] > kSchurHeavy ? heavy : light).push_back((int)bb);
+            ctx->nheavy = (int)heavy.size(); ctx->nlight = (int)light.size();
+            CHK(dalloc(ctx, &ctx->blk_heavy, heavy.size())); CHK(dalloc(ctx, &ctx->blk_light, light.size()));
+            CHK(upload(ctx, ctx->blk_heavy, heavy.data(), heavy.size())); CHK(upload(ctx, ctx->blk_light, light.data(), light.size()));
+            CU(cudaStreamSynchronize(ctx->stream));
+            CHK(dalloc(ctx, &ctx->Ybuf, (size_t)3 * na * nobs));
+        }
     }
     CHK(upload(ctx, (double*)ctx->obs_xy, obs_xy, 2 * (size_t)nobs));
     CHK(upload(ctx, (double*)ctx->pt_xy, pt_xy.data(), 2 * (size_t)nobs));

@@ -12,6 +12,24 @@ __global__ void k_gather_xy(int64_t nobs, const int* __restrict__ pt_obs, const 
 
 int* pcg_done_ptr(vlg_ba_ctx* ctx) { return (int*)((char*)ctx->pcg_sc + offsetof(PcgScalars, done)); }
 
+// S (or this rank's share of it) from the Y kept by k_cam_schur_diag: heavy blocks a warp each, light blocks a thread each
+template <int NA>
+int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S)
+{
+    if (ctx->nheavy > 0) {
+        k_schur_blocks_heavy<NA><<<cdiv(ctx->nheavy, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+            ctx->nheavy, ctx->blk_heavy, ctx->Np, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
+        ctx->launches++;
+    }
+    if (ctx->nlight > 0) {
+        k_schur_blocks_light<NA><<<cdiv(ctx->nlight, 128), 128, 0, ctx->stream>>>(
+            ctx->nlight, ctx->blk_light, ctx->Np, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return VLG_BA_OK;
+}
+
 // damping + V*^-1 + camera-keyed Schur sums + (Cholesky: S, factor, solve | PCG)  ->  da
 template <int NA>
 int run_stage2(vlg_ba_ctx* ctx, double lambda)
@@ -31,7 +49,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         TimedScope ts(ctx, T_SCHUR);
         if (ctx->nchunks > 0) {
             k_cam_schur_diag<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
-                ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->eB, ctx->Spart);
+                ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->eB, ctx->Spart, ctx->Ybuf);
             ctx->launches++;
         }
         k_cam_sum_partials<<<cdiv((int64_t)m * NU, 128), 128, 0, ctx->stream>>>(m, NU, ctx->cam_chunk_ptr, ctx->Spart, nullptr, ctx->red2);
@@ -49,12 +67,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         {
             TimedScope ts(ctx, T_SCHUR_BLK);
             CU(cudaMemsetAsync(ctx->S, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
-            if (ctx->nblocks > 0) {
-                k_schur_blocks<NA><<<cdiv(ctx->nblocks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
-                    (int)ctx->nblocks, Np, ctx->rank == 0 ? 1 : 0, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt,
-                    ctx->W, ctx->Vinv, ctx->Ud, ctx->S);
-                ctx->launches++;
-            }
+            CHK(assemble_S<NA>(ctx, ctx->rank == 0 ? 1 : 0, ctx->S));
         }
         CHK(allreduce(ctx, ctx->S, (size_t)Np * Np));
         {
@@ -84,13 +97,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             // this rank's share of sum_i Y_ij W_ik' (S without U*; U* p is added by the update kernel)
             TimedScope ts(ctx, T_SCHUR_BLK);
             CU(cudaMemsetAsync(ctx->S, 0, sizeof(double) * (size_t)ctx->Np * ctx->Np, ctx->stream));
-            if (ctx->nblocks > 0) {
-                k_schur_blocks<NA><<<cdiv(ctx->nblocks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
-                    (int)ctx->nblocks, ctx->Np, 0, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt,
-                    ctx->W, ctx->Vinv, ctx->Ud, ctx->S);
-                ctx->launches++;
-            }
-            CU(cudaGetLastError());
+            CHK(assemble_S<NA>(ctx, 0, ctx->S));
         }
         CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pt));
         CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cam));
@@ -596,11 +603,9 @@ int vlg_ba_get_reduced(vlg_ba_ctx* ctx, double* Vinv, double* S, double* e_, dou
         double* tmp = nullptr;
         CU(cudaMalloc(&tmp, sizeof(double) * (size_t)Np * Np));
         CU(cudaMemsetAsync(tmp, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
-        if (ctx->nblocks > 0) {
-            const int g = cdiv(ctx->nblocks, kWarpsPerBlock), th = kWarpsPerBlock * 32;
-            if (ctx->na == 6) k_schur_blocks<6><<<g, th, 0, ctx->stream>>>((int)ctx->nblocks, Np, 1, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->Ud, tmp);
-            else if (ctx->na == 7) k_schur_blocks<7><<<g, th, 0, ctx->stream>>>((int)ctx->nblocks, Np, 1, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->Ud, tmp);
-            else k_schur_blocks<10><<<g, th, 0, ctx->stream>>>((int)ctx->nblocks, Np, 1, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->Ud, tmp);
+        {
+            const int r = DISPATCH_NA(ctx, assemble_S)(ctx, 1, tmp);
+            if (r != VLG_BA_OK) { cudaFree(tmp); return r; }
         }
         cudaError_t e = cudaMemcpy2DAsync(S, sizeof(double) * N, tmp, sizeof(double) * (size_t)Np, sizeof(double) * N, N,
                                           cudaMemcpyDeviceToHost, ctx->stream);
