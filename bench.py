@@ -246,7 +246,7 @@ def run_ours(args):
     barrier()
     groups = {}
     for g in ("stage1_cam", "stage1_pt", "w_copy", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt", "pcg_sweep_cam",
-              "pcg_symv", "pcg_update", "stage3"):
+              "pcg_symv", "pcg_update", "precond", "stage3"):
         avg, cnt = ctx.kernel_time(g)
         groups[g] = {"avg_ms": avg, "count": cnt, "total_ms": avg * cnt}
     ctx.reset_timers(False)

@@ -696,33 +696,6 @@ __device__ __forceinline__ double block_sum_1024(double v, double* sh)
     return r;   // every thread
 }
 
-// r = e_, x = 0, z = M^-1 r, p = z, rz = r'z, r0n2 = r'r
-template <int NA>
-__global__ void __launch_bounds__(1024) k_pcg_init(int m, const double* __restrict__ ebar, const double* __restrict__ Minv,
-                                                   double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-                                                   double* __restrict__ p, PcgScalars* __restrict__ sc, double rtol)
-{
-    __shared__ double sh[32];
-    const int N = NA * m;
-    double rz = 0.0, rr = 0.0;
-    for (int t = threadIdx.x; t < N; t += 1024) {
-        const int j = t / NA, row = t % NA;
-        double zz = 0.0;
-#pragma unroll
-        for (int c = 0; c < NA; c++) zz += Minv[(size_t)NA * NA * j + row + NA * c] * ebar[(size_t)NA * j + c];
-        const double rv = ebar[t];
-        x[t] = 0.0; r[t] = rv; z[t] = zz; p[t] = zz;
-        rz += rv * zz; rr += rv * rv;
-    }
-    rz = block_sum_1024(rz, sh);
-    rr = block_sum_1024(rr, sh);
-    if (threadIdx.x == 0) {
-        sc->rz = rz; sc->r0n2 = rr; sc->rn2 = rr; sc->pq = 0.0; sc->iters = 0;
-        sc->done = (rr == 0.0) ? 1 : 0;
-        (void)rtol;
-    }
-}
-
 // q = U* p - wq;  alpha = rz / p'q;  x += alpha p;  r -= alpha q;  z = M^-1 r;
 // beta = r'z / rz;  p = z + beta p;  stop flag when |r| <= rtol |r0|
 template <int NA>

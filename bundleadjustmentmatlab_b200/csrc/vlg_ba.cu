@@ -60,9 +60,9 @@ bool nccl_load()
 
 char g_create_error[512] = "";
 
-enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_SYMV, T_COUNT };
+enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_SYMV, T_PRECOND, T_COUNT };
 const char* kTimerNames[T_COUNT] = {"stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt",
-                                    "pcg_sweep_cam", "stage3", "pcg_update", "w_copy", "pcg_symv"};
+                                    "pcg_sweep_cam", "stage3", "pcg_update", "w_copy", "pcg_symv", "precond"};
 
 struct KTimer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -89,6 +89,7 @@ struct vlg_ba_ctx {
     int* symv_tile_ptr = nullptr;
     int symv_grid = 0, nsymv_seg = 0;
     double *symv_rowpart = nullptr, *symv_colpart = nullptr;
+    double *Cblk = nullptr, *McL = nullptr;   // cluster-Jacobi preconditioner: gathered diagonal blocks of S, their inverses [coop_grid][128 x 128]
     int Np = 0;               // padded order of S
     int64_t nblocks = 0, npairs = 0;
     // host copies
@@ -504,6 +505,9 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         const int g = cdiv(m, 128 / na);            // k_pcg_update_coop: a CTA owns 128/na whole cameras
         if (coop && g <= nsm * 8) ctx->coop_grid = g;
         CHK(dalloc(ctx, &ctx->blkpart, (size_t)11 * std::max(g, 1)));
+        if (ctx->use_explicit && ctx->coop_grid > 0 && ctx->opt.pcg_cluster) {
+            CHK(dalloc(ctx, &ctx->Cblk, (size_t)g * 128 * 128)); CHK(dalloc(ctx, &ctx->McL, (size_t)g * 128 * 128));
+        }
         CHK(dalloc(ctx, &ctx->Zd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->SZd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->defl_sc, 1));
         if (ctx->tiled_ok) {
             CHK(dalloc(ctx, &ctx->Wp, (size_t)3 * na * nobs));

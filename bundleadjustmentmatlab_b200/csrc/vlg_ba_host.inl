@@ -99,6 +99,19 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CU(cudaMemsetAsync(ctx->S, 0, sizeof(double) * (size_t)ctx->Np * ctx->Np, ctx->stream));
             CHK(assemble_S<NA>(ctx, 0, ctx->S));
         }
+        const double* McL = nullptr;
+        if (ctx->use_explicit && ctx->McL) {
+            // cluster-Jacobi: diagonal blocks of S over the update kernel's CTAs, summed over ranks, inverted
+            TimedScope ts(ctx, T_PRECOND);
+            k_cluster_gather<NA><<<ctx->coop_grid, 128, 0, ctx->stream>>>(m, ctx->Np, ctx->S, ctx->Cblk);
+            ctx->launches++;
+            CHK(allreduce(ctx, ctx->Cblk, (size_t)ctx->coop_grid * 128 * 128));
+            CU(cudaFuncSetAttribute(k_cluster_inverse<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cluster<NA>::kSmem));
+            k_cluster_inverse<NA><<<ctx->coop_grid, 128, Cluster<NA>::kSmem, ctx->stream>>>(m, 1, ctx->Cblk, ctx->Ud, ctx->McL);
+            ctx->launches++;
+            CU(cudaGetLastError());
+            McL = ctx->McL;
+        }
         CU(cudaFuncSetAttribute(k_sweep_pt_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pt));
         CU(cudaFuncSetAttribute(k_sweep_cam_tiled<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cam));
         // persistent ring variants: 2 stages, as many CTAs per SM as shared memory allows
@@ -170,9 +183,9 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                 ctx->launches++;
             }
             k_pcg_init_defl<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->Zd, ctx->SZd, ctx->defl_sc, ctx->da, ctx->pr,
-                                                           ctx->pz, ctx->pp, ctx->pcg_sc);
+                                                           ctx->pz, ctx->pp, ctx->pcg_sc, McL);
         } else {
-            k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol);
+            k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol, McL);
         }
         ctx->launches++;
         int launched = 0;
@@ -195,7 +208,8 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                         const double* zz = defl ? ctx->Zd : nullptr;
                         const double* sz = defl ? ctx->SZd : nullptr;
                         const DeflScalars* dsc = ctx->defl_sc;
-                        void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt, &zz, &sz, &dsc};
+                        const double* mcl = McL;
+                        void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt, &zz, &sz, &dsc, &mcl};
                         CU(cudaLaunchCooperativeKernel((void*)k_pcg_update_coop<NA>, dim3(ctx->coop_grid), dim3(128), args, 0, ctx->stream));
                     } else {
                         k_pcg_update<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Ud, ctx->Minv, ctx->wq, ctx->da, ctx->pr, ctx->pz, ctx->pp,
@@ -383,6 +397,7 @@ void vlg_ba_opts_default(vlg_ba_opts* o)
     o->solver = VLG_BA_SOLVER_AUTO; o->chol_max_cams = 300; o->pcg_rtol = 1e-8; o->pcg_max_iter = 1000;
     o->rtable = VLG_BA_RTABLE_HOST_LIBM; o->order = VLG_BA_ORDER_CHUNKED; o->device = -1; o->verbose = 0;
     o->pcg_deflate = 1;
+    o->pcg_cluster = 1;
 }
 
 const char* vlg_ba_version(void) { return "vlgba 0.1 (sm_100a, fp64)"; }

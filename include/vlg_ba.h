@@ -70,6 +70,8 @@ typedef struct vlg_ba_opts {
     int    device;            /* CUDA device ordinal; -1 = current device */
     int    verbose;           /* 'verbose': print "iter k: error= a -> b" (bundle_euclid.m:221-224) */
     int    pcg_deflate;       /* 1 (default): deflate the 4 gauge directions (world translation, scale) in PCG */
+    int    pcg_cluster;       /* 1 (default): PCG_EXPLICIT preconditions with the inverses of 128/num_a-camera diagonal blocks of S
+                                 (cluster-Jacobi) instead of per-camera blocks */
 } vlg_ba_opts;
 
 typedef struct vlg_ba_ctx vlg_ba_ctx;
