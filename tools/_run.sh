@@ -1,7 +1,5 @@
 set -x
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
-python bench.py --config venice --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_venice_r01n.json 2> gpurun_out/bench_n.err
-python -c "
-import json;d=json.load(open('gpurun_out/bench_venice_r01n.json'));print(d['ms_per_step'],d['lm_iters_per_sec'],d['e2e']['ms_per_step'],d['cost_first_last'],d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_n.err
-python bench.py --config trafalgar --solver pcgx --steps 10 --warmup 3 --no-cpu-baseline --no-e2e | python -c "
-import json,sys;d=json.loads(sys.stdin.read());print(d['ms_per_step'],d['lm_iters_per_sec'],d['cost_first_last'],d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+timeout 900 python bench.py > gpurun_out/bench_default_r01o.json 2> gpurun_out/bench_o.err; tail -c 600 gpurun_out/bench_default_r01o.json; tail -3 gpurun_out/bench_o.err
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_r01o.json 2> gpurun_out/bench_ref_o.err; cat gpurun_out/bench_reference_r01o.json; tail -3 gpurun_out/bench_ref_o.err
+timeout 1200 python bench.py --config final --steps 3 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_final_r01o.json 2> gpurun_out/bench_final_o.err; tail -c 1500 gpurun_out/bench_final_r01o.json; tail -3 gpurun_out/bench_final_o.err
