@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: all-reduce the PCG vector with NCCL instead of peer-memory mailboxes")
     return ap.parse_args()
 
 
@@ -209,6 +210,13 @@ def run_ours(args):
         dist.broadcast(uid, 0)
         ctx.set_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
     ctx.set_problem_sparse(P.K.T, a0, b0, P.obs_xy, P.obs_pt, P.obs_cam)
+    p2p = world > 1 and not args.no_p2p
+    if p2p:
+        # the per-iteration PCG vector goes through NVLink peer-memory mailboxes (CUDA IPC), not NCCL
+        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.p2p_import(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
 
     def barrier():
         if world > 1:
@@ -349,6 +357,7 @@ def run_ours(args):
                        "solver": {capi.SOLVER_CHOL: "cholesky", capi.SOLVER_PCG: "pcg (block-Jacobi, implicit Schur)",
                                   capi.SOLVER_PCG_EXPLICIT: "pcg (block-Jacobi, assembled S, symmetric lower-triangle matvec)"}[infos[-1]["solver_used"]],
                        "pcg_rtol": args.pcg_rtol, "rtable": args.rtable,
+                       "pcg_vector_allreduce": ("nvlink peer-memory mailboxes (k_p2p_allreduce)" if p2p else "nccl") if world > 1 else None,
                        "l2": "inputs larger than L2 (W alone is %.0f MB per rank)" % (P.nobs * 144 / 1e6)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,

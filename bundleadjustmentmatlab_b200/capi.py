@@ -53,7 +53,7 @@ _lib = None
 # every symbol include/vlg_ba.h declares
 SYMBOLS = [
     "vlg_ba_opts_default", "vlg_ba_version", "vlg_ba_create", "vlg_ba_destroy", "vlg_ba_last_error",
-    "vlg_ba_nccl_unique_id", "vlg_ba_set_comm", "vlg_ba_set_problem_dense", "vlg_ba_set_problem_sparse",
+    "vlg_ba_nccl_unique_id", "vlg_ba_set_comm", "vlg_ba_p2p_export", "vlg_ba_p2p_import", "vlg_ba_set_problem_dense", "vlg_ba_set_problem_sparse",
     "vlg_ba_set_num_vis", "vlg_ba_nobs", "vlg_ba_get_obs", "vlg_ba_set_state", "vlg_ba_get_state",
     "vlg_ba_stage1", "vlg_ba_get_blocks", "vlg_ba_get_jacobians", "vlg_ba_stage2", "vlg_ba_get_reduced",
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
@@ -147,6 +147,16 @@ class Context:
 
     def set_comm(self, rank: int, nranks: int, unique_id: bytes):
         self._ck(self._L.vlg_ba_set_comm(self._h, C.c_int(rank), C.c_int(nranks), C.c_char_p(unique_id)))
+
+    def p2p_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's PCG mailbox (after set_comm and set_problem_*)."""
+        buf = C.create_string_buffer(64)
+        self._ck(self._L.vlg_ba_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_import(self, handles: bytes):
+        """`handles`: the ranks' 64-byte handles concatenated in rank order."""
+        self._ck(self._L.vlg_ba_p2p_import(self._h, C.c_char_p(handles)))
 
     # ---- problem
     def set_problem_sparse(self, K, a, b, obs_xy, obs_pt, obs_cam, pivot=None):

@@ -1096,9 +1096,15 @@ k_symv_lower(int Np, int ld, int N, const double* __restrict__ S, const double* 
 
 // out[r] = sign * ( sum_seg colpart[seg][r] + sum_{strip <= r/32} rowpart[strip][r] ), r < N.
 // CTA = 32 rows x 32 strip groups; group g adds strips g, g+32, ... in order, groups are folded in order.
+struct P2PMail;
+__device__ __forceinline__ double p2p_allreduce_elem(const P2PMail& mb, unsigned int epoch, int t, double x);
+
+// With `mb` (multi-GPU) the row's value is exchanged with the peers right here: it is stored into every
+// rank's mailbox and the sum over ranks comes back, see the P2PMail section at the end of this file.
 __global__ void __launch_bounds__(1024)
 k_symv_finish(int Np, int N, double sign, const double* __restrict__ rowpart, const double* __restrict__ colpart,
-              const int* __restrict__ done, double* __restrict__ out)
+              const int* __restrict__ done, double* __restrict__ out, const P2PMail* __restrict__ mb = nullptr,
+              unsigned int epoch = 0)
 {
     __shared__ double red[32][33];
     if (done && *done) return;
@@ -1115,8 +1121,68 @@ k_symv_finish(int Np, int N, double sign, const double* __restrict__ rowpart, co
         for (int sg = 0; sg < nseg; sg++) y += __ldcs(colpart + (size_t)sg * Np + r);
 #pragma unroll
         for (int q = 0; q < 32; q++) y += red[q][lane];
-        out[r] = sign * y;
+        y *= sign;
+        if (mb) y = p2p_allreduce_elem(*mb, epoch, r, y);
+        out[r] = y;
     }
+}
+
+}  // namespace vlgba
+
+// =========================================================================================
+// All-reduce of the per-iteration PCG vector over NVLink peer memory (multi-GPU, one process per
+// GPU).  The vector is small (6m doubles: 85 kB at Venice shape) and sits on the critical path of
+// every iteration, so it is latency that counts, not bandwidth.  Each rank owns a MAILBOX
+// (cudaMalloc'ed, opened by every peer through CUDA IPC); an element travels as one 16-byte store
+// {lo, epoch, hi, epoch} into slot [parity][my rank][t] of EVERY rank's mailbox -- the flag rides
+// with the data (each 8-byte half carries its own copy, so the protocol does not depend on 16-byte
+// store atomicity), hence no fence and no separate flag round trip -- and the receiving thread polls
+// its own element of every rank's slot and adds them in rank order: every rank gets bit-identical
+// sums.  No barrier of any kind; a thread always publishes before it polls, so there is no
+// deadlock.  Slots are double-buffered by epoch parity: a peer can only send epoch e+2 after it
+// consumed my epoch e+1, which I send after my epoch-e kernel has finished.
+// The exchange is a device function so that it runs INSIDE the kernel that produces the vector
+// (k_symv_finish: transfer of one row block overlaps the partial sums of the others).
+// =========================================================================================
+namespace vlgba {
+
+constexpr int kP2pMaxRanks = 16;
+constexpr int kP2pThreads = 256;
+
+struct P2PMail {
+    uint4* data[kP2pMaxRanks];           // data[r]: rank r's mailbox, [2][nranks][nslot] packets
+    int nranks, rank, nslot;
+};
+
+__device__ __forceinline__ double p2p_allreduce_elem(const P2PMail& mb, unsigned int epoch, int t, double x)
+{
+    const int par = (int)(epoch & 1u);
+    const size_t mine = ((size_t)par * mb.nranks + mb.rank) * mb.nslot + t;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    const uint4 pkt = make_uint4((unsigned int)bits, epoch, (unsigned int)(bits >> 32), epoch);
+    for (int r = 0; r < mb.nranks; r++) {
+        uint4* dst = mb.data[r] + mine;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pkt.x), "r"(pkt.y), "r"(pkt.z), "r"(pkt.w) : "memory");
+    }
+    double s = 0.0;
+    for (int r = 0; r < mb.nranks; r++) {
+        const uint4* src = mb.data[mb.rank] + ((size_t)par * mb.nranks + r) * mb.nslot + t;
+        uint4 v;
+        do {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+        } while (v.y != epoch || v.w != epoch);
+        s += __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
+    }
+    return s;
+}
+
+// stand-alone form (implicit-Schur path: after k_cam_sum_partials)
+__global__ void __launch_bounds__(kP2pThreads)
+k_p2p_allreduce(P2PMail mb, int n, unsigned int epoch, const int* __restrict__ done, double* __restrict__ v /* in: partial, out: sum */)
+{
+    if (done && *done) return;            // identical on every rank (the stop flag comes from all-reduced values)
+    const int t = blockIdx.x * kP2pThreads + threadIdx.x;
+    if (t < n) v[t] = p2p_allreduce_elem(mb, epoch, t, v[t]);
 }
 
 }  // namespace vlgba

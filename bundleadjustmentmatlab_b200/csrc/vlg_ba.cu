@@ -150,6 +150,14 @@ struct vlg_ba_ctx {
     // multi-GPU
     nccl_comm comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory all-reduce of the PCG vector (vlg_ba_p2p_export / _import)
+    void* p2p_base = nullptr;             // this rank's mailbox: data then flags
+    size_t p2p_bytes = 0;
+    std::vector<void*> p2p_peer_base;     // opened peer mailboxes (own entry = p2p_base)
+    P2PMail p2p;
+    P2PMail* p2p_dev = nullptr;           // device copy (argument of k_symv_finish)
+    bool p2p_ready = false;
+    unsigned int p2p_epoch = 0;
     // accounting
     int64_t launches = 0;
     bool timers_on = false;
@@ -202,6 +210,7 @@ void free_problem(vlg_ba_ctx* ctx)
     for (void* p : ctx->allocs) cudaFree(p);
     ctx->allocs.clear();
     ctx->have_problem = false;
+    ctx->p2p_ready = false;           // the mailbox is sized by the problem: export/import again
     ctx->s1_valid = ctx->s2_valid = ctx->s3_valid = false;
 }
 

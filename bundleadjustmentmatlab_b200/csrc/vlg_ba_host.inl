@@ -12,6 +12,18 @@ __global__ void k_gather_xy(int64_t nobs, const int* __restrict__ pt_obs, const 
 
 int* pcg_done_ptr(vlg_ba_ctx* ctx) { return (int*)((char*)ctx->pcg_sc + offsetof(PcgScalars, done)); }
 
+// all-reduce of the per-iteration PCG vector: peer-memory mailboxes when imported, NCCL otherwise
+int allreduce_pcg_vector(vlg_ba_ctx* ctx, double* v, int n, const int* done)
+{
+    if (ctx->nranks <= 1) return VLG_BA_OK;
+    if (!ctx->p2p_ready) return allreduce(ctx, v, (size_t)n);
+    ctx->p2p_epoch++;
+    k_p2p_allreduce<<<cdiv(n, kP2pThreads), kP2pThreads, 0, ctx->stream>>>(ctx->p2p, n, ctx->p2p_epoch, done, v);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return VLG_BA_OK;
+}
+
 // S (or this rank's share of it) from the Y kept by k_cam_schur_diag: heavy blocks a warp each, light blocks a thread each
 template <int NA>
 int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S)
@@ -131,10 +143,13 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                 TimedScope ts(ctx, T_SYMV);
                 k_symv_lower<<<ctx->symv_grid, kSymvRows + 32, kSymvSmem, ctx->stream>>>(ctx->Np, ctx->Np, N, ctx->S, v, ctx->symv_tile_ptr,
                                                                                    ctx->symv_tiles, dn, ctx->symv_rowpart, ctx->symv_colpart);
-                k_symv_finish<<<ctx->Np / 32, 1024, 0, ctx->stream>>>(ctx->Np, N, -1.0, ctx->symv_rowpart, ctx->symv_colpart, dn, ctx->wq);
+                const bool fused = ctx->nranks > 1 && ctx->p2p_ready;     // the exchange with the peers happens inside the finish kernel
+                if (fused) ctx->p2p_epoch++;
+                k_symv_finish<<<ctx->Np / 32, 1024, 0, ctx->stream>>>(ctx->Np, N, -1.0, ctx->symv_rowpart, ctx->symv_colpart, dn, ctx->wq,
+                                                                      fused ? ctx->p2p_dev : nullptr, ctx->p2p_epoch);
                 ctx->launches += 2;
                 CU(cudaGetLastError());
-                CHK(allreduce(ctx, ctx->wq, (size_t)N));
+                if (!fused) CHK(allreduce_pcg_vector(ctx, ctx->wq, N, dn));
                 return VLG_BA_OK;
             }
             if (n > 0) {
@@ -166,7 +181,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             if (need_wq) {
                 k_cam_sum_partials<<<cdiv((int64_t)m * NA, 128), 128, 0, ctx->stream>>>(m, NA, ctx->cam_chunk_ptr, ctx->qpart, dn, ctx->wq);
                 ctx->launches++;
-                CHK(allreduce(ctx, ctx->wq, (size_t)N));
+                CHK(allreduce_pcg_vector(ctx, ctx->wq, N, dn));
             }
             CU(cudaGetLastError());
             return VLG_BA_OK;
@@ -435,11 +450,14 @@ int vlg_ba_create(const vlg_ba_opts* opts, vlg_ba_ctx** out)
     return VLG_BA_OK;
 }
 
+static void p2p_close(vlg_ba_ctx* ctx);
+
 void vlg_ba_destroy(vlg_ba_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    p2p_close(ctx);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     free_problem(ctx);
     for (int t = 0; t < T_COUNT; t++)
@@ -474,6 +492,64 @@ int vlg_ba_set_comm(vlg_ba_ctx* ctx, int rank, int nranks, const void* unique_id
     int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
     if (r != 0) return fail(ctx, VLG_BA_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     ctx->rank = rank; ctx->nranks = nranks;
+    return VLG_BA_OK;
+}
+
+static void p2p_close(vlg_ba_ctx* ctx)
+{
+    for (size_t r = 0; r < ctx->p2p_peer_base.size(); r++)
+        if (ctx->p2p_peer_base[r] && ctx->p2p_peer_base[r] != ctx->p2p_base) cudaIpcCloseMemHandle(ctx->p2p_peer_base[r]);
+    ctx->p2p_peer_base.clear();
+    if (ctx->p2p_base) cudaFree(ctx->p2p_base);
+    if (ctx->p2p_dev) cudaFree(ctx->p2p_dev);
+    ctx->p2p_base = nullptr; ctx->p2p_dev = nullptr; ctx->p2p_ready = false; ctx->p2p_epoch = 0;
+}
+
+int vlg_ba_p2p_export(vlg_ba_ctx* ctx, void* ipc_handle_64)
+{
+    if (!ctx || !ipc_handle_64) return VLG_BA_EINVAL;
+    if (!ctx->have_problem || ctx->nranks <= 1) return fail(ctx, VLG_BA_ESTATE, "p2p_export needs set_comm (nranks > 1) and a problem");
+    if (ctx->nranks > kP2pMaxRanks) return fail(ctx, VLG_BA_EINVAL, "p2p supports up to %d ranks", kP2pMaxRanks);
+    CU(cudaSetDevice(ctx->device));
+    p2p_close(ctx);
+    const int N = ctx->na * ctx->m;
+    P2PMail& mb = ctx->p2p;
+    memset(&mb, 0, sizeof(mb));
+    mb.nranks = ctx->nranks; mb.rank = ctx->rank;
+    mb.nslot = std::max(ctx->Np, cdiv(N, kP2pThreads) * kP2pThreads);
+    ctx->p2p_bytes = sizeof(uint4) * 2 * (size_t)mb.nranks * mb.nslot;
+    CU(cudaMalloc(&ctx->p2p_base, ctx->p2p_bytes));
+    CU(cudaMemset(ctx->p2p_base, 0, ctx->p2p_bytes));      // flag 0 = nothing sent yet (epochs start at 1)
+    CU(cudaMalloc(&ctx->p2p_dev, sizeof(P2PMail)));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->p2p_base));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(ipc_handle_64, &h, 64);
+    return VLG_BA_OK;
+}
+
+int vlg_ba_p2p_import(vlg_ba_ctx* ctx, const void* ipc_handles)
+{
+    if (!ctx || !ipc_handles) return VLG_BA_EINVAL;
+    if (!ctx->p2p_base) return fail(ctx, VLG_BA_ESTATE, "p2p_import needs p2p_export first");
+    CU(cudaSetDevice(ctx->device));
+    P2PMail& mb = ctx->p2p;
+    ctx->p2p_peer_base.assign((size_t)mb.nranks, nullptr);
+    for (int r = 0; r < mb.nranks; r++) {
+        void* base = ctx->p2p_base;
+        if (r != mb.rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)ipc_handles + 64 * (size_t)r, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(ctx, VLG_BA_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        ctx->p2p_peer_base[(size_t)r] = base;
+        mb.data[r] = (uint4*)base;
+    }
+    CU(cudaMemcpy(ctx->p2p_dev, &mb, sizeof(P2PMail), cudaMemcpyHostToDevice));
+    ctx->p2p_epoch = 0;
+    ctx->p2p_ready = true;
     return VLG_BA_OK;
 }
 

@@ -108,6 +108,13 @@ const char *vlg_ba_last_error(const vlg_ba_ctx *ctx);      /* ctx may be NULL: e
  * the caller.  After this call the per-camera sums and scalars are all-reduced over ranks. */
 int  vlg_ba_nccl_unique_id(void *unique_id_128);
 int  vlg_ba_set_comm(vlg_ba_ctx *ctx, int rank, int nranks, const void *unique_id_128);
+/* Optional, after set_problem_* on every rank: all-reduce the per-iteration PCG vector through NVLink
+ * peer memory instead of ncclAllReduce (one kernel: stores into every peer's mailbox, release/acquire
+ * flags, sum in rank order).  Each rank exports the 64-byte CUDA IPC handle of its mailbox, the host
+ * gathers them (rank order) and every rank imports the nranks x 64 bytes.  Ranks must be processes on
+ * one node with peer access. */
+int  vlg_ba_p2p_export(vlg_ba_ctx *ctx, void *ipc_handle_64);
+int  vlg_ba_p2p_import(vlg_ba_ctx *ctx, const void *ipc_handles /* nranks x 64 bytes */);
 
 /* Problem definition.  Replaces the argument packing of bundle_euclid.m:81-102 and the
  * positional inputs of mex_bundle_1_XABeUVWeAeB.c:76-83.  `pivot` (m doubles or NULL) is

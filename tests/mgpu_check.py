@@ -46,11 +46,20 @@ def main():
     worst = 0.0
     lo_hi = shard.point_ranges(np.asarray(P.obs_pt), b.shape[0], world)
     lo, hi = int(lo_hi[rank]), int(lo_hi[rank + 1])
-    for solver in solvers:
+    def exchange_mailboxes(ctx):
+        # every rank's 64-byte CUDA IPC handle, gathered in rank order
+        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.p2p_import(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+
+    for solver, p2p in [(s, q) for s in solvers for q in (False, True) if not (q and s == capi.SOLVER_CHOL)]:
         ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12, device=local)
         ctx.set_comm(rank, world, fresh_uid())
         xy, pt, cam, bl, _ = shard.shard_points(P.obs_xy, P.obs_pt, P.obs_cam, b, rank, world)
         ctx.set_problem_sparse(P.K.T, a, bl, xy, pt, cam)
+        if p2p:     # PCG vector through NVLink peer-memory mailboxes instead of ncclAllReduce
+            exchange_mailboxes(ctx)
         for st, info_ref in ref[solver]:
             ctx.set_state(a=st["a"], b=np.ascontiguousarray(st["b"][lo:hi]), lam=st["lam"], nu=st["nu"])
             info = ctx.trial_step()
@@ -58,6 +67,7 @@ def main():
                 worst = max(worst, abs(info[key] - info_ref[key]) / info_ref[key])
             assert info["accepted"] == info_ref["accepted"], (solver, info, info_ref)
             assert info["solver_used"] == solver
+        dist.barrier()
         ctx.close()
     w = torch.tensor([worst], dtype=torch.float64, device="cuda")
     dist.all_reduce(w, op=dist.ReduceOp.MAX)

@@ -1,5 +1,8 @@
 set -x
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
-timeout 900 python bench.py > gpurun_out/bench_default_r01o.json 2> gpurun_out/bench_o.err; tail -c 600 gpurun_out/bench_default_r01o.json; tail -3 gpurun_out/bench_o.err
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_r01o.json 2> gpurun_out/bench_ref_o.err; cat gpurun_out/bench_reference_r01o.json; tail -3 gpurun_out/bench_ref_o.err
-timeout 1200 python bench.py --config final --steps 3 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_final_r01o.json 2> gpurun_out/bench_final_o.err; tail -c 1500 gpurun_out/bench_final_r01o.json; tail -3 gpurun_out/bench_final_o.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/mgpu_check.py > gpurun_out/mgpu.log 2>&1
+grep -E "MGPU|Error|error|assert" gpurun_out/mgpu.log | head
+for mode in "" "--no-p2p"; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e $mode > gpurun_out/bench_2gpu_p2p$mode.json 2> gpurun_out/bench_2gpu.err
+python -c "
+import json,sys;d=json.load(open('gpurun_out/bench_2gpu_p2p$mode.json'));print(d['ms_per_step'],d['lm_iters_per_sec'],d['config'].get('pcg_vector_allreduce'),d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_2gpu.err
+done
