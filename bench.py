@@ -378,6 +378,9 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse()
     if args.impl == "reference":
         run_reference(args)
