@@ -342,3 +342,29 @@ def test_large_problem_invariants():
         ctx.close()
     assert rel(news[capi.SOLVER_PCG], news[capi.SOLVER_CHOL]) <= COST_RTOL
     assert rel(news[capi.SOLVER_PCG_EXPLICIT], news[capi.SOLVER_CHOL]) <= COST_RTOL
+
+
+def test_venice_shape_invariants():
+    """Venice-shaped problem (BASELINE.json config 4, the bench workload: 1 778 cameras, 994 k points,
+    5.0 M observations) -- size-independent properties at full size: AUTO picks the assembled-S PCG, the
+    first LM step is accepted and lowers the cost, the assembled and the implicit Schur operators give
+    the same step (teacher-forced, 1e-9), and a repeated step is bit-identical (deterministic kernels)."""
+    P = synth.make_config("venice", seed=0)
+    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T); b = np.ascontiguousarray(P.Xe[:3].T)
+    news = {}
+    for solver in (capi.SOLVER_AUTO, capi.SOLVER_PCG):
+        ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-10)
+        ctx.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
+        i1 = ctx.trial_step()
+        assert i1["accepted"] and i1["new_cost"] < i1["old_cost"]
+        if solver == capi.SOLVER_AUTO:
+            assert i1["solver_used"] == capi.SOLVER_PCG_EXPLICIT
+            ctx.set_state(a=a, b=b, lam=1e-3, nu=2.0)
+            i2 = ctx.trial_step()
+            assert i2["new_cost"] == i1["new_cost"] and i2["old_cost"] == i1["old_cost"] and i2["pcg_iters"] == i1["pcg_iters"]
+        news[solver] = (i1["old_cost"], i1["new_cost"], i1["pcg_iters"])
+        ctx.close()
+    print("venice: (old, new, PCG iterations) assembled / implicit:", news[capi.SOLVER_AUTO], news[capi.SOLVER_PCG])
+    assert news[capi.SOLVER_AUTO][0] == news[capi.SOLVER_PCG][0]
+    assert rel(news[capi.SOLVER_AUTO][1], news[capi.SOLVER_PCG][1]) <= COST_RTOL
+
