@@ -228,6 +228,77 @@ __global__ void k_stage1_pt(int n, const int* __restrict__ pt_ptr, const int* __
 // deterministic sum of a long vector: fixed-shape two-level tree (grid of kRedBlocks CTAs,
 // then one CTA).  out[slot] = sum(in[0..n)).
 // ---------------------------------------------------------------------------------------
+// The same point pass with one LANE per observation: a CTA owns a tile of whole points (<= kS1Tile
+// observations, the tile list of the PCG point sweep), every thread does the 4 reprojections of one
+// observation and leaves the 10 products (B'B, B'e, e'e) in shared memory, then one thread per point
+// adds its track in ascending camera order -- the reference's order, bit-identical to k_stage1_pt --
+// without the divergence of a thread-per-point loop over tracks of 2..64 observations (0.49 -> see
+// DESIGN.md).
+constexpr int kS1Tile = 512;
+
+template <int NA>
+__global__ void __launch_bounds__(kS1Tile)
+k_stage1_pt_tiled(const int4* __restrict__ ptile_meta /* (q0, nob, p0, npts) */, const int* __restrict__ pt_ptr,
+                  const int* __restrict__ pt_cam, const int* __restrict__ pt_pt, const double2* __restrict__ pt_xy,
+                  const double* __restrict__ K4, const double* __restrict__ a, const double* __restrict__ b,
+                  const double* __restrict__ rtab, int fix_structure, double* __restrict__ V,
+                  double* __restrict__ eB, double* __restrict__ cost_pt)
+{
+    __shared__ double pr[10][kS1Tile];
+    const int4 meta = __ldg(ptile_meta + blockIdx.x);
+    const int q0 = meta.x, nob = meta.y, p0 = meta.z, np = meta.w, tid = threadIdx.x;
+    if (tid < nob) {
+        const int q = q0 + tid;
+        const int j = pt_cam[q], i = pt_pt[q];
+        const double2 xy = pt_xy[q];
+        const double b0 = __ldg(b + (size_t)3 * i), b1 = __ldg(b + (size_t)3 * i + 1), b2 = __ldg(b + (size_t)3 * i + 2);
+        const double* R = rtab + (size_t)36 * j;
+        const double* aj = a + (size_t)NA * j;
+        double Rl[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rl[k] = __ldg(R + k);
+        double al[NA];
+#pragma unroll
+        for (int k = 3; k < NA; k++) al[k] = __ldg(aj + k);
+        double fx, fy, cx, cy;
+        double Kl[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
+        effective_K<NA>(Kl, al, fx, fy, cx, cy);
+        double B[6], e[2];
+        obs_point_jacobian(Rl, al[3], al[4], al[5], fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, B, e);
+        pr[0][tid] = dot2(B[0], B[1], B[0], B[1]);
+        pr[1][tid] = dot2(B[2], B[3], B[0], B[1]);
+        pr[2][tid] = dot2(B[4], B[5], B[0], B[1]);
+        pr[3][tid] = dot2(B[2], B[3], B[2], B[3]);
+        pr[4][tid] = dot2(B[4], B[5], B[2], B[3]);
+        pr[5][tid] = dot2(B[4], B[5], B[4], B[5]);
+        pr[6][tid] = dot2(B[0], B[1], e[0], e[1]);
+        pr[7][tid] = dot2(B[2], B[3], e[0], e[1]);
+        pr[8][tid] = dot2(B[4], B[5], e[0], e[1]);
+        pr[9][tid] = e[0] * e[0] + e[1] * e[1];
+    }
+    __syncthreads();
+    if (tid < np) {
+        const int i = p0 + tid;
+        const int o0 = pt_ptr[i] - q0, o1 = pt_ptr[i + 1] - q0;
+        double v00 = 0, v10 = 0, v20 = 0, v11 = 0, v21 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
+        for (int o = o0; o < o1; o++) {
+            v00 = VLG_P(v00, pr[0][o]); v10 = VLG_P(v10, pr[1][o]); v20 = VLG_P(v20, pr[2][o]);
+            v11 = VLG_P(v11, pr[3][o]); v21 = VLG_P(v21, pr[4][o]); v22 = VLG_P(v22, pr[5][o]);
+            g0 = VLG_P(g0, pr[6][o]); g1 = VLG_P(g1, pr[7][o]); g2 = VLG_P(g2, pr[8][o]);
+            cost += pr[9][o];
+        }
+        if (fix_structure) { v00 = v10 = v20 = v11 = v21 = v22 = 0.0; g0 = g1 = g2 = 0.0; }   // bundle_euclid.m:140-144
+        double* Vi = V + (size_t)9 * i;
+        Vi[0] = v00; Vi[1] = v10; Vi[2] = v20;
+        Vi[3] = v10; Vi[4] = v11; Vi[5] = v21;
+        Vi[6] = v20; Vi[7] = v21; Vi[8] = v22;
+        eB[(size_t)3 * i] = g0; eB[(size_t)3 * i + 1] = g1; eB[(size_t)3 * i + 2] = g2;
+        cost_pt[i] = cost;
+    }
+}
+
 constexpr int kRedBlocks = 296;
 constexpr int kRedThreads = 256;
 
@@ -346,9 +417,7 @@ k_cam_schur_diag(int nchunks, const int* __restrict__ chunk_begin, const int* __
     for (int o = beg + lane; o < end; o += 32) {
         const int i = obs_pt[o];
         double Wo[3 * NA], Vi[9], g[3], Y[3 * NA];
-        const double* Wg = W + (size_t)3 * NA * o;
-#pragma unroll
-        for (int k = 0; k < 3 * NA; k++) Wo[k] = Wg[k];
+        load_block_g<3 * NA>(W, (size_t)o, Wo);
 #pragma unroll
         for (int k = 0; k < 9; k++) Vi[k] = __ldg(Vinv + (size_t)9 * i + k);
 #pragma unroll
@@ -539,6 +608,22 @@ __device__ __forceinline__ void schur_store_block(double* __restrict__ S, int ld
                 if (j != k) S[(size_t)(NA * k + col) + (size_t)ld * (NA * j + row)] = v[row + NA * col];
             }
     }
+}
+
+// diagonal blocks of S from the per-camera sums of k_cam_schur_diag (packed upper triangle of
+// sum_i Y_ij W_ij', this rank's share): S_jj = (add_U ? U*_j : 0) - sums_j, exactly symmetric
+template <int NA>
+__global__ void k_schur_diag_fill(int m, int ld, int add_U, const double* __restrict__ sums /* [m][NU] */,
+                                  const double* __restrict__ Ud, double* __restrict__ S)
+{
+    constexpr int NU = nu_of(NA);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * NA * NA) return;
+    const int j = t / (NA * NA), u = t - j * NA * NA, row = u % NA, col = u / NA;
+    const int r = row < col ? row : col, c = row < col ? col : row;
+    double v = -sums[(size_t)NU * j + c * (c + 1) / 2 + r];
+    if (add_U) v += Ud[(size_t)NA * NA * j + u];
+    S[(size_t)(NA * j + row) + (size_t)ld * (NA * j + col)] = v;
 }
 
 // light blocks: one thread per block, pairs in ascending point order (the reference's order of
@@ -771,14 +856,18 @@ __global__ void k_backsub(int n, const int* __restrict__ pt_ptr, const int* __re
     const double g0 = w0, g1 = w1, g2 = w2;
     const int nrow = all_rows ? NA : 6;
     for (int q = pt_ptr[i]; q < pt_ptr[i + 1]; q++) {
-        const double* Wo = W + (size_t)3 * NA * pt_obs[q];
+        double Wo[3 * NA];
+        load_block_g<3 * NA>(W, (size_t)pt_obs[q], Wo);     // 16-byte gathers: half the LSU wavefronts of 8-byte ones
         const double* dj = da + (size_t)NA * pt_cam[q];
         double s0 = VLG_M(Wo[0], dj[0]), s1 = VLG_M(Wo[NA], dj[0]), s2 = VLG_M(Wo[2 * NA], dj[0]);
-        for (int r = 1; r < nrow; r++) {
-            const double d = dj[r];
-            s0 = VLG_P(s0, VLG_M(Wo[r], d));
-            s1 = VLG_P(s1, VLG_M(Wo[r + NA], d));
-            s2 = VLG_P(s2, VLG_M(Wo[r + 2 * NA], d));
+#pragma unroll
+        for (int r = 1; r < NA; r++) {
+            if (r < nrow) {                 // static register indices; nrow = 6 or NA
+                const double d = dj[r];
+                s0 = VLG_P(s0, VLG_M(Wo[r], d));
+                s1 = VLG_P(s1, VLG_M(Wo[r + NA], d));
+                s2 = VLG_P(s2, VLG_M(Wo[r + 2 * NA], d));
+            }
         }
         w0 = VLG_S(w0, s0); w1 = VLG_S(w1, s1); w2 = VLG_S(w2, s2);
     }

@@ -330,77 +330,61 @@ k_cluster_gather(int m, int ld, const double* __restrict__ S, double* __restrict
         Cblk[((size_t)cl * 128 + c) * 128 + t] = (t < nc && c < nc) ? S[(base + t) + (size_t)ld * (base + c)] : 0.0;
 }
 
+// In-place Gauss-Jordan inversion of the cluster block in shared memory (SPD => no pivot search): per
+// pivot every thread updates its half row with INDEPENDENT FMAs against the broadcast pivot row, so the
+// ~30-cycle FP64 latency is hidden (the first version -- Cholesky, triangular inverse, L^-T L^-1 -- was
+// three phases of dependent dot-product chains: 0.66 ms; this one: see DESIGN.md).  Two threads per
+// row.  A non-positive pivot eliminates its row and column (zero row/column of the inverse).
 template <int NA>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_cluster_inverse(int m, int add_U, const double* __restrict__ Cblk, const double* __restrict__ Ud, double* __restrict__ McL)
 {
     using C = Cluster<NA>;
     extern __shared__ double A[];                  // NC x LD, row-major
-    __shared__ double dinv[128], lcol[128];
-    const int cl = blockIdx.x, t = threadIdx.x;
+    __shared__ double rowk[128], colk[128];
+    const int cl = blockIdx.x, tid = threadIdx.x;
+    const int t = tid & 127, half = tid >> 7;      // row, column half
     const int nc = min(C::kCams, m - cl * C::kCams) * NA;
+    static_assert(C::NC % 2 == 0, "cluster size");
+    const int c0 = half * (C::NC / 2), c1 = c0 + C::NC / 2;
     if (t < C::NC) {
         const int jt = t / NA, rt = t - jt * NA;
-        for (int c = 0; c < C::NC; c++) {
+        for (int c = c0; c < c1; c++) {
             double v = (t < nc && c < nc) ? Cblk[((size_t)cl * 128 + c) * 128 + t] : 0.0;
             if (add_U && t < nc && c / NA == jt) v += Ud[(size_t)NA * NA * (cl * C::kCams + jt) + rt + NA * (c - jt * NA)];
             A[t * C::LD + c] = v;
         }
     }
     __syncthreads();
-    // Cholesky, right-looking, thread t owns row t
-    for (int j = 0; j < nc; j++) {
-        const double d = A[j * C::LD + j];
-        const double rinv = d > 0.0 ? rsqrt(d) : 0.0;
-        double l = 0.0;
-        if (t > j && t < nc) { l = A[t * C::LD + j] * rinv; }
-        __syncthreads();                           // everyone has read the pivot
-        if (t > j && t < nc) A[t * C::LD + j] = l;
-        if (t == j) { A[j * C::LD + j] = d * rinv; dinv[j] = rinv; }
+    for (int k = 0; k < nc; k++) {
+        const double d = A[k * C::LD + k];
+        const double p = d > 0.0 ? 1.0 / d : 0.0;
+        // pivot row scaled by 1/d, pivot column as it is now
+        if (tid < C::NC) rowk[tid] = A[k * C::LD + tid] * p;
+        else if (tid >= 128 && tid - 128 < C::NC) colk[tid - 128] = A[(tid - 128) * C::LD + k];
         __syncthreads();
-        if (t > j && t < nc) {
-            for (int c = j + 1; c <= t; c++) A[t * C::LD + c] -= l * A[c * C::LD + j];
-        }
-    }
-    __syncthreads();
-    // in-place inverse of the lower-triangular factor, last column first
-    for (int j = nc - 1; j >= 0; j--) {
-        if (t > j && t < nc) lcol[t] = A[t * C::LD + j];
-        __syncthreads();
-        if (t > j && t < nc) {
-            // FP64 operations have ~30-cycle latency here: 4 independent chains
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int c = j + 1;
-            for (; c + 3 <= t; c += 4) {
-                s0 += A[t * C::LD + c] * lcol[c]; s1 += A[t * C::LD + c + 1] * lcol[c + 1];
-                s2 += A[t * C::LD + c + 2] * lcol[c + 2]; s3 += A[t * C::LD + c + 3] * lcol[c + 3];
+        if (t < nc) {
+            // fixed trip count + unrolling: the loads and FMAs of a row are independent, keep 8 in flight
+            const double f = t == k ? 0.0 : colk[t];
+            double* row = A + t * C::LD + c0;
+            const double* rk = rowk + c0;
+            if (t == k) {
+#pragma unroll 8
+                for (int cc = 0; cc < C::NC / 2; cc++) row[cc] = rk[cc];
+            } else {
+#pragma unroll 8
+                for (int cc = 0; cc < C::NC / 2; cc++) row[cc] = row[cc] - f * rk[cc];
             }
-            for (; c <= t; c++) s0 += A[t * C::LD + c] * lcol[c];
-            A[t * C::LD + j] = -((s0 + s1) + (s2 + s3)) * dinv[j];
+            if (k >= c0 && k < c1) A[t * C::LD + k] = t == k ? p : -f * p;     // the pivot column itself
         }
-        if (t == j) A[j * C::LD + j] = dinv[j];
         __syncthreads();
     }
-    // M^-1 = Linv' Linv (thread a: row a, lower part, mirrored); rows/columns past nc are zero
+    // symmetric copy out (lower triangle mirrored); rows/columns past nc are zero
     double* out = McL + (size_t)cl * 128 * 128;
-    for (int b = 0; b < 128; b++) {
+    for (int c = half; c < 128; c += 2) {
         double v = 0.0;
-        if (t < nc && b <= t) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int r = t;
-            for (; r + 3 < nc; r += 4) {
-                s0 += A[r * C::LD + t] * A[r * C::LD + b];
-                s1 += A[(r + 1) * C::LD + t] * A[(r + 1) * C::LD + b];
-                s2 += A[(r + 2) * C::LD + t] * A[(r + 2) * C::LD + b];
-                s3 += A[(r + 3) * C::LD + t] * A[(r + 3) * C::LD + b];
-            }
-            for (; r < nc; r++) s0 += A[r * C::LD + t] * A[r * C::LD + b];
-            v = (s0 + s1) + (s2 + s3);
-        }
-        if (b <= t) {
-            out[t + 128 * b] = v;
-            out[b + 128 * t] = v;
-        }
+        if (t < nc && c < nc) v = t >= c ? A[t * C::LD + c] : A[c * C::LD + t];
+        out[t + 128 * c] = v;
     }
 }
 

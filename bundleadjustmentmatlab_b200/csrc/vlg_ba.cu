@@ -108,7 +108,11 @@ struct vlg_ba_ctx {
     int *blk_heavy = nullptr, *blk_light = nullptr;   // S-assembly work lists: blocks with many / few pairs
     int nheavy = 0, nlight = 0;
     double* Ybuf = nullptr;                           // Y = W V*^-1 per observation (C-order), explicit-S paths
+    double* red2_local = nullptr;                     // this rank's per-camera Schur sums before the all-reduce
     int4* ptile_meta = nullptr;      // point tiles of the PCG point sweep: (q0, nob, p0, npts)
+    int4* s1tile_meta = nullptr;     // point tiles of the stage-1 point pass (<= kS1Tile observations)
+    int ns1tiles = 0;
+    int* pt_pt = nullptr;            // P-order: point of each observation
     int2* chunk_meta = nullptr;      // camera chunks: (begin, nob)
     int nptiles = 0;
     bool tiled_ok = false;           // every track fits one tile
@@ -478,6 +482,26 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         if (n == 0) ctx->tiled_ok = false;
     }
     ctx->nptiles = ctx->tiled_ok ? (int)ptile_first.size() - 1 : 0;
+    // tiles of the stage-1 point pass (any solver): whole points, <= kS1Tile observations; a track longer
+    // than a tile sends the pass back to the thread-per-point kernel
+    std::vector<int4> s1tiles;
+    {
+        bool ok = n > 0;
+        int p_first = 0;
+        int64_t acc = 0;
+        for (int i = 0; i < n && ok; i++) {
+            const int t = pt_ptr[i + 1] - pt_ptr[i];
+            if (t > kS1Tile) { ok = false; break; }
+            if (acc + t > kS1Tile || i - p_first == kS1Tile) {
+                s1tiles.push_back(make_int4(pt_ptr[p_first], pt_ptr[i] - pt_ptr[p_first], p_first, i - p_first));
+                p_first = i; acc = 0;
+            }
+            acc += t;
+        }
+        if (ok) s1tiles.push_back(make_int4(pt_ptr[p_first], pt_ptr[n] - pt_ptr[p_first], p_first, n - p_first));
+        else s1tiles.clear();
+    }
+    ctx->ns1tiles = (int)s1tiles.size();
 
     const int NU = nu_of(na);
     // ---- device allocations
@@ -591,12 +615,16 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         CHK(upload(ctx, ctx->pairs, pairs.data(), (size_t)ctx->npairs));
         {
             std::vector<int> heavy, light;
-            for (int64_t bb = 0; bb < ctx->nblocks; bb++) (blk_ptr[bb + 1] - blk_ptr[bb] > kSchurHeavy ? heavy : light).push_back((int)bb);
+            // diagonal blocks are not on these lists: k_cam_schur_diag already sums them (k_schur_diag_fill)
+            for (int64_t bb = 0; bb < ctx->nblocks; bb++)
+                if (ctx->h_blk_j[(size_t)bb] != ctx->h_blk_k[(size_t)bb])
+                    (blk_ptr[bb + 1] - blk_ptr[bb] > kSchurHeavy ? heavy : light).push_back((int)bb);
             ctx->nheavy = (int)heavy.size(); ctx->nlight = (int)light.size();
             CHK(dalloc(ctx, &ctx->blk_heavy, heavy.size())); CHK(dalloc(ctx, &ctx->blk_light, light.size()));
             CHK(upload(ctx, ctx->blk_heavy, heavy.data(), heavy.size())); CHK(upload(ctx, ctx->blk_light, light.data(), light.size()));
             CU(cudaStreamSynchronize(ctx->stream));
             CHK(dalloc(ctx, &ctx->Ybuf, (size_t)3 * na * nobs));
+            CHK(dalloc(ctx, &ctx->red2_local, (size_t)nu_of(na) * m));
         }
     }
     CHK(upload(ctx, (double*)ctx->obs_xy, obs_xy, 2 * (size_t)nobs));
@@ -604,6 +632,15 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(upload(ctx, ctx->obs_pt, obs_pt, (size_t)nobs)); CHK(upload(ctx, ctx->obs_cam, obs_cam, (size_t)nobs));
     CHK(upload(ctx, ctx->cam_ptr, cam_ptr.data(), (size_t)m + 1)); CHK(upload(ctx, ctx->pt_ptr, pt_ptr.data(), (size_t)n + 1));
     CHK(upload(ctx, ctx->pt_obs, pt_obs.data(), (size_t)nobs)); CHK(upload(ctx, ctx->pt_cam, pt_cam.data(), (size_t)nobs));
+    if (ctx->ns1tiles > 0) {
+        std::vector<int> pt_pt((size_t)nobs);
+        for (int i = 0; i < n; i++)
+            for (int q = pt_ptr[i]; q < pt_ptr[i + 1]; q++) pt_pt[(size_t)q] = i;
+        CHK(dalloc(ctx, &ctx->pt_pt, (size_t)nobs)); CHK(dalloc(ctx, &ctx->s1tile_meta, s1tiles.size()));
+        CHK(upload(ctx, ctx->pt_pt, pt_pt.data(), (size_t)nobs));
+        CHK(upload(ctx, ctx->s1tile_meta, s1tiles.data(), s1tiles.size()));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     CHK(upload(ctx, ctx->chunk_cam, chunk_cam.data(), (size_t)ctx->nchunks));
     CHK(upload(ctx, ctx->chunk_begin, chunk_begin.data(), (size_t)ctx->nchunks));
     CHK(upload(ctx, ctx->chunk_end, chunk_end.data(), (size_t)ctx->nchunks));
@@ -671,9 +708,14 @@ int run_stage1(vlg_ba_ctx* ctx, double* diag_X, double* diag_A, double* diag_B, 
     ctx->launches++;
     if (ctx->n > 0) {
         TimedScope ts(ctx, T_STAGE1_PT);
-        k_stage1_pt<NA><<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->pt_ptr, ctx->pt_cam, ctx->pt_xy, ctx->K4, ctx->a,
-                                                                    ctx->b, ctx->rtab, ctx->opt.fix_structure, ctx->V, ctx->eB,
-                                                                    ctx->cost_pt);
+        if (ctx->ns1tiles > 0)
+            k_stage1_pt_tiled<NA><<<ctx->ns1tiles, kS1Tile, 0, ctx->stream>>>(ctx->s1tile_meta, ctx->pt_ptr, ctx->pt_cam, ctx->pt_pt, ctx->pt_xy,
+                                                                           ctx->K4, ctx->a, ctx->b, ctx->rtab, ctx->opt.fix_structure,
+                                                                           ctx->V, ctx->eB, ctx->cost_pt);
+        else
+            k_stage1_pt<NA><<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->pt_ptr, ctx->pt_cam, ctx->pt_xy, ctx->K4, ctx->a,
+                                                                        ctx->b, ctx->rtab, ctx->opt.fix_structure, ctx->V, ctx->eB,
+                                                                        ctx->cost_pt);
         ctx->launches++;
     }
     if (ctx->tiled_ok && ctx->nobs > 0 && !diag) {

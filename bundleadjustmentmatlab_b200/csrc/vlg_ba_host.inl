@@ -28,6 +28,8 @@ int allreduce_pcg_vector(vlg_ba_ctx* ctx, double* v, int n, const int* done)
 template <int NA>
 int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S)
 {
+    k_schur_diag_fill<NA><<<cdiv((int64_t)ctx->m * NA * NA, 256), 256, 0, ctx->stream>>>(ctx->m, ctx->Np, add_U, ctx->red2_local, ctx->Ud, S);
+    ctx->launches++;
     if (ctx->nheavy > 0) {
         k_schur_blocks_heavy<NA><<<cdiv(ctx->nheavy, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
             ctx->nheavy, ctx->blk_heavy, ctx->Np, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
@@ -67,6 +69,8 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         k_cam_sum_partials<<<cdiv((int64_t)m * NU, 128), 128, 0, ctx->stream>>>(m, NU, ctx->cam_chunk_ptr, ctx->Spart, nullptr, ctx->red2);
         ctx->launches++;
     }
+    if (ctx->red2_local)      // this rank's own sums feed the diagonal blocks of its share of S
+        CU(cudaMemcpyAsync(ctx->red2_local, ctx->red2, sizeof(double) * (size_t)NU * m, cudaMemcpyDeviceToDevice, ctx->stream));
     CHK(allreduce(ctx, ctx->red2, (size_t)NU * m));
     k_cam_schur_finalize<NA><<<cdiv(m, 64), 64, 0, ctx->stream>>>(m, ctx->red2, ctx->Ud, ctx->eA, ctx->Sjj, ctx->ebar,
                                                                   ctx->use_chol ? nullptr : ctx->Minv);
@@ -119,7 +123,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             ctx->launches++;
             CHK(allreduce(ctx, ctx->Cblk, (size_t)ctx->coop_grid * 128 * 128));
             CU(cudaFuncSetAttribute(k_cluster_inverse<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cluster<NA>::kSmem));
-            k_cluster_inverse<NA><<<ctx->coop_grid, 128, Cluster<NA>::kSmem, ctx->stream>>>(m, 1, ctx->Cblk, ctx->Ud, ctx->McL);
+            k_cluster_inverse<NA><<<ctx->coop_grid, 256, Cluster<NA>::kSmem, ctx->stream>>>(m, 1, ctx->Cblk, ctx->Ud, ctx->McL);
             ctx->launches++;
             CU(cudaGetLastError());
             McL = ctx->McL;

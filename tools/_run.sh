@@ -1,6 +1,5 @@
 set -x
-timeout 900 python -m pytest tests -q -m gpu -x -k "venice or cluster" -s 2>&1 | tail -8
-python bench.py --config venice --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/plain_q.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_venice_r01q.csv python bench.py --config venice --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list_q.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_symv_lower|k_schur_blocks_heavy|k_schur_blocks_light|k_cluster_inverse|k_cam_schur_diag|k_stage1_pt|k_backsub|k_new_cost' -c 9 -o gpurun_out/prof_venice_r01q python bench.py --config venice --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_q.log 2>&1
-python bench.py --config trafalgar --solver chol --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_chol_coop' -c 1 -o gpurun_out/prof_trafalgar_chol_r01q python bench.py --config trafalgar --solver chol --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_chol_q.log 2>&1
-tail -2 gpurun_out/ncu_full_q.log gpurun_out/ncu_full_chol_q.log
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
+python bench.py --config venice --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_venice_r01r.json 2> gpurun_out/bench_r.err
+python -c "
+import json;d=json.load(open('gpurun_out/bench_venice_r01r.json'));print(d['ms_per_step'],d['lm_iters_per_sec'],d['e2e']['ms_per_step'],d['cost_first_last'],d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_r.err
