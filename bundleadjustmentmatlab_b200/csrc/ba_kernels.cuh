@@ -882,6 +882,57 @@ __global__ void k_backsub(int n, const int* __restrict__ pt_ptr, const int* __re
     denom_pt[i] = d0 * (lambda * d0 + g0) + d1 * (lambda * d1 + g1) + d2 * (lambda * d2 + g2);
 }
 
+// back-substitution with one LANE per observation (tiles of whole points, as k_stage1_pt_tiled): every
+// thread forms W_ij' da_j for one observation, one thread per point then subtracts its track in
+// ascending camera order -- the same operations in the same order as k_backsub, without the
+// divergence of tracks of 2..64 observations.
+template <int NA>
+__global__ void __launch_bounds__(kS1Tile)
+k_backsub_tiled(const int4* __restrict__ ptile_meta, const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
+                const int* __restrict__ pt_cam, const double* __restrict__ W, const double* __restrict__ Vinv,
+                const double* __restrict__ eB, const double* __restrict__ da, const double* __restrict__ b, double lambda,
+                int all_rows, double* __restrict__ db, double* __restrict__ b_new, double* __restrict__ denom_pt)
+{
+    __shared__ double pr[3][kS1Tile];
+    const int4 meta = __ldg(ptile_meta + blockIdx.x);
+    const int q0 = meta.x, nob = meta.y, p0 = meta.z, np = meta.w, tid = threadIdx.x;
+    const int nrow = all_rows ? NA : 6;
+    if (tid < nob) {
+        const int q = q0 + tid;
+        double Wo[3 * NA];
+        load_block_g<3 * NA>(W, (size_t)pt_obs[q], Wo);
+        const double* dj = da + (size_t)NA * pt_cam[q];
+        double s0 = VLG_M(Wo[0], dj[0]), s1 = VLG_M(Wo[NA], dj[0]), s2 = VLG_M(Wo[2 * NA], dj[0]);
+#pragma unroll
+        for (int r = 1; r < NA; r++) {
+            if (r < nrow) {
+                const double d = dj[r];
+                s0 = VLG_P(s0, VLG_M(Wo[r], d));
+                s1 = VLG_P(s1, VLG_M(Wo[r + NA], d));
+                s2 = VLG_P(s2, VLG_M(Wo[r + 2 * NA], d));
+            }
+        }
+        pr[0][tid] = s0; pr[1][tid] = s1; pr[2][tid] = s2;
+    }
+    __syncthreads();
+    if (tid < np) {
+        const int i = p0 + tid;
+        double w0 = eB[(size_t)3 * i], w1 = eB[(size_t)3 * i + 1], w2 = eB[(size_t)3 * i + 2];
+        const double g0 = w0, g1 = w1, g2 = w2;
+        const int o0 = pt_ptr[i] - q0, o1 = pt_ptr[i + 1] - q0;
+        for (int o = o0; o < o1; o++) { w0 = VLG_S(w0, pr[0][o]); w1 = VLG_S(w1, pr[1][o]); w2 = VLG_S(w2, pr[2][o]); }
+        const double* Vi = Vinv + (size_t)9 * i;
+        const double d0 = VLG_P(VLG_P(VLG_M(Vi[0], w0), VLG_M(Vi[3], w1)), VLG_M(Vi[6], w2));
+        const double d1 = VLG_P(VLG_P(VLG_M(Vi[1], w0), VLG_M(Vi[4], w1)), VLG_M(Vi[7], w2));
+        const double d2 = VLG_P(VLG_P(VLG_M(Vi[2], w0), VLG_M(Vi[5], w1)), VLG_M(Vi[8], w2));
+        db[(size_t)3 * i] = d0; db[(size_t)3 * i + 1] = d1; db[(size_t)3 * i + 2] = d2;
+        b_new[(size_t)3 * i] = VLG_P(b[(size_t)3 * i], d0);
+        b_new[(size_t)3 * i + 1] = VLG_P(b[(size_t)3 * i + 1], d1);
+        b_new[(size_t)3 * i + 2] = VLG_P(b[(size_t)3 * i + 2], d2);
+        denom_pt[i] = d0 * (lambda * d0 + g0) + d1 * (lambda * d1 + g1) + d2 * (lambda * d2 + g2);
+    }
+}
+
 // new residual at (a_new, b_new): per-observation squared error (mex_bundle_3_db_new.c:149-166
 // + bundle_euclid.m:205,210).  C-order: the camera is (nearly) warp-uniform.
 template <int NA>

@@ -357,8 +357,7 @@ k_cluster_inverse(int m, int add_U, const double* __restrict__ Cblk, const doubl
     }
     __syncthreads();
     for (int k = 0; k < nc; k++) {
-        const double d = A[k * C::LD + k];
-        const double p = d > 0.0 ? 1.0 / d : 0.0;
+        const double p = fast_rcp_pos(A[k * C::LD + k]);      // 0 for a non-positive pivot
         // pivot row scaled by 1/d, pivot column as it is now
         if (tid < C::NC) rowk[tid] = A[k * C::LD + tid] * p;
         else if (tid >= 128 && tid - 128 < C::NC) colk[tid - 128] = A[(tid - 128) * C::LD + k];
@@ -366,8 +365,8 @@ k_cluster_inverse(int m, int add_U, const double* __restrict__ Cblk, const doubl
         if (t < nc) {
             // fixed trip count + unrolling: the loads and FMAs of a row are independent, keep 8 in flight
             const double f = t == k ? 0.0 : colk[t];
-            double* row = A + t * C::LD + c0;
-            const double* rk = rowk + c0;
+            double* __restrict__ row = A + t * C::LD + c0;        // restrict: lets the unrolled loads run ahead of the stores
+            const double* __restrict__ rk = rowk + c0;
             if (t == k) {
 #pragma unroll 8
                 for (int cc = 0; cc < C::NC / 2; cc++) row[cc] = rk[cc];
@@ -400,7 +399,14 @@ __device__ __forceinline__ double apply_precond_global(int m, int t, const doubl
         const int nc = min(C::kCams, m - cl * C::kCams) * NA;
         const double* M = McL + (size_t)cl * 128 * 128 + lt;
         const double* rc = r + (size_t)cl * C::NC;
-        for (int c = 0; c < nc; c++) zz += M[128 * c] * rc[c];
+        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+        int c = 0;
+        for (; c + 3 < nc; c += 4) {
+            z0 += M[128 * c] * rc[c]; z1 += M[128 * (c + 1)] * rc[c + 1];
+            z2 += M[128 * (c + 2)] * rc[c + 2]; z3 += M[128 * (c + 3)] * rc[c + 3];
+        }
+        for (; c < nc; c++) z0 += M[128 * c] * rc[c];
+        zz = (z0 + z1) + (z2 + z3);
     } else {
         const int j = t / NA, row = t - j * NA;
 #pragma unroll

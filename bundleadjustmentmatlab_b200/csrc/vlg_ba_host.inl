@@ -278,9 +278,14 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
     {
         TimedScope ts(ctx, T_STAGE3);
         if (n > 0) {
-            k_backsub<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W, ctx->Vinv, ctx->eB,
-                                                                ctx->da, ctx->b, lambda, ctx->opt.backsub_all_rows, ctx->db,
-                                                                ctx->b_new, ctx->denom_pt);
+            if (ctx->ns1tiles > 0)
+                k_backsub_tiled<NA><<<ctx->ns1tiles, kS1Tile, 0, ctx->stream>>>(ctx->s1tile_meta, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W,
+                                                                             ctx->Vinv, ctx->eB, ctx->da, ctx->b, lambda,
+                                                                             ctx->opt.backsub_all_rows, ctx->db, ctx->b_new, ctx->denom_pt);
+            else
+                k_backsub<NA><<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W, ctx->Vinv, ctx->eB,
+                                                                    ctx->da, ctx->b, lambda, ctx->opt.backsub_all_rows, ctx->db,
+                                                                    ctx->b_new, ctx->denom_pt);
             ctx->launches++;
         }
         if (ctx->nobs > 0) {
