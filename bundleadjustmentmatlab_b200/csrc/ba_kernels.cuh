@@ -580,21 +580,39 @@ __device__ __forceinline__ void schur_pair(const double* __restrict__ Y, const d
             acc[row + NA * col] += Yj[row] * Wk[col] + Yj[row + NA] * Wk[col + NA] + Yj[row + 2 * NA] * Wk[col + 2 * NA];
 }
 
+// Where block (j,k) lives: in the dense S (leading dimension ld), or -- cluster mode, ccams > 0 -- in the
+// 128 x 128 diagonal block of the cluster of `ccams` consecutive cameras that holds both j and k
+// (the cluster-Jacobi preconditioner of the implicit-Schur PCG assembles only those blocks).
+struct SchurDest { double* base; size_t ld; int jr, kr; };
+
+template <int NA>
+__device__ __forceinline__ SchurDest schur_dest(double* __restrict__ S, int ld, int ccams, int j, int k)
+{
+    SchurDest d;
+    if (ccams > 0) {
+        const int cl = j / ccams;
+        d.base = S + (size_t)cl * 128 * 128; d.ld = 128; d.jr = NA * (j - cl * ccams); d.kr = NA * (k - cl * ccams);
+    } else {
+        d.base = S; d.ld = (size_t)ld; d.jr = NA * j; d.kr = NA * k;
+    }
+    return d;
+}
+
 // v[row + NA col] -> S block (j,k) and its mirror (k,j); 16-byte stores when NA is even
 template <int NA>
-__device__ __forceinline__ void schur_store_block(double* __restrict__ S, int ld, int j, int k, const double* __restrict__ v)
+__device__ __forceinline__ void schur_store_block(const SchurDest& t, bool offdiag, const double* __restrict__ v)
 {
     if constexpr (NA % 2 == 0) {
 #pragma unroll
         for (int col = 0; col < NA; col++) {
-            double2* d = reinterpret_cast<double2*>(S + (size_t)(NA * j) + (size_t)ld * (NA * k + col));
+            double2* d = reinterpret_cast<double2*>(t.base + (size_t)t.jr + t.ld * (t.kr + col));
 #pragma unroll
             for (int h = 0; h < NA / 2; h++) d[h] = make_double2(v[2 * h + NA * col], v[2 * h + 1 + NA * col]);
         }
-        if (j != k) {
+        if (offdiag) {
 #pragma unroll
             for (int row = 0; row < NA; row++) {
-                double2* d = reinterpret_cast<double2*>(S + (size_t)(NA * k) + (size_t)ld * (NA * j + row));
+                double2* d = reinterpret_cast<double2*>(t.base + (size_t)t.kr + t.ld * (t.jr + row));
 #pragma unroll
                 for (int h = 0; h < NA / 2; h++) d[h] = make_double2(v[row + NA * (2 * h)], v[row + NA * (2 * h + 1)]);
             }
@@ -604,8 +622,8 @@ __device__ __forceinline__ void schur_store_block(double* __restrict__ S, int ld
         for (int col = 0; col < NA; col++)
 #pragma unroll
             for (int row = 0; row < NA; row++) {
-                S[(size_t)(NA * j + row) + (size_t)ld * (NA * k + col)] = v[row + NA * col];
-                if (j != k) S[(size_t)(NA * k + col) + (size_t)ld * (NA * j + row)] = v[row + NA * col];
+                t.base[(size_t)(t.jr + row) + t.ld * (t.kr + col)] = v[row + NA * col];
+                if (offdiag) t.base[(size_t)(t.kr + col) + t.ld * (t.jr + row)] = v[row + NA * col];
             }
     }
 }
@@ -613,7 +631,7 @@ __device__ __forceinline__ void schur_store_block(double* __restrict__ S, int ld
 // diagonal blocks of S from the per-camera sums of k_cam_schur_diag (packed upper triangle of
 // sum_i Y_ij W_ij', this rank's share): S_jj = (add_U ? U*_j : 0) - sums_j, exactly symmetric
 template <int NA>
-__global__ void k_schur_diag_fill(int m, int ld, int add_U, const double* __restrict__ sums /* [m][NU] */,
+__global__ void k_schur_diag_fill(int m, int ld, int ccams, int add_U, const double* __restrict__ sums /* [m][NU] */,
                                   const double* __restrict__ Ud, double* __restrict__ S)
 {
     constexpr int NU = nu_of(NA);
@@ -623,14 +641,15 @@ __global__ void k_schur_diag_fill(int m, int ld, int add_U, const double* __rest
     const int r = row < col ? row : col, c = row < col ? col : row;
     double v = -sums[(size_t)NU * j + c * (c + 1) / 2 + r];
     if (add_U) v += Ud[(size_t)NA * NA * j + u];
-    S[(size_t)(NA * j + row) + (size_t)ld * (NA * j + col)] = v;
+    const SchurDest d = schur_dest<NA>(S, ld, ccams, j, j);
+    d.base[(size_t)(d.jr + row) + d.ld * (d.kr + col)] = v;
 }
 
 // light blocks: one thread per block, pairs in ascending point order (the reference's order of
 // summation, mex_bundle_2_Se_.c:103-118)
 template <int NA>
 __global__ void __launch_bounds__(128)
-k_schur_blocks_light(int nlist, const int* __restrict__ list, int ld, int add_U, const int* __restrict__ blk_j,
+k_schur_blocks_light(int nlist, const int* __restrict__ list, int ld, int ccams, int add_U, const int* __restrict__ blk_j,
                      const int* __restrict__ blk_k, const int64_t* __restrict__ blk_ptr, const int2* __restrict__ pairs,
                      const double* __restrict__ Y, const double* __restrict__ W, const double* __restrict__ Ud,
                      double* __restrict__ S)
@@ -649,13 +668,13 @@ k_schur_blocks_light(int nlist, const int* __restrict__ list, int ld, int add_U,
         if (j == k && add_U) v += Ud[(size_t)NA * NA * j + u];
         acc[u] = v;
     }
-    schur_store_block<NA>(S, ld, j, k, acc);
+    schur_store_block<NA>(schur_dest<NA>(S, ld, ccams, j, k), j != k, acc);
 }
 
 // heavy blocks: one warp per block, lanes stride over the pairs, values folded by recursive halving
 template <int NA>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_schur_blocks_heavy(int nlist, const int* __restrict__ list, int ld, int add_U, const int* __restrict__ blk_j,
+k_schur_blocks_heavy(int nlist, const int* __restrict__ list, int ld, int ccams, int add_U, const int* __restrict__ blk_j,
                      const int* __restrict__ blk_k, const int64_t* __restrict__ blk_ptr, const int2* __restrict__ pairs,
                      const double* __restrict__ Y, const double* __restrict__ W, const double* __restrict__ Ud,
                      double* __restrict__ S)
@@ -682,8 +701,9 @@ k_schur_blocks_heavy(int nlist, const int* __restrict__ list, int ld, int add_U,
             const int row = u % NA, col = u / NA;
             double v = -mine[w];
             if (j == k && add_U) v += Ud[(size_t)NA * NA * j + u];
-            S[(size_t)(NA * j + row) + (size_t)ld * (NA * k + col)] = v;
-            if (j != k) S[(size_t)(NA * k + col) + (size_t)ld * (NA * j + row)] = v;
+            const SchurDest d = schur_dest<NA>(S, ld, ccams, j, k);
+            d.base[(size_t)(d.jr + row) + d.ld * (d.kr + col)] = v;
+            if (j != k) d.base[(size_t)(d.kr + col) + d.ld * (d.jr + row)] = v;
         }
     }
 }

@@ -358,6 +358,12 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         }
     }
     free_problem(ctx);
+    // optional buffers: which of them exist depends on the solver path of THIS problem
+    ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr;
+    ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr; ctx->pt_pt = nullptr;
+    ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
+    ctx->symv_tiles = nullptr; ctx->symv_tile_ptr = nullptr; ctx->symv_rowpart = nullptr; ctx->symv_colpart = nullptr;
+    ctx->chol_R = nullptr; ctx->chol_Ld = nullptr; ctx->chol_Dinv = nullptr; ctx->chol_bar = nullptr;
     CU(cudaSetDevice(ctx->device));
     ctx->m = m; ctx->n = n; ctx->na = na; ctx->nobs = nobs;
     ctx->num_vis = (double)nobs;
@@ -419,6 +425,15 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         ctx->use_explicit = !ctx->use_chol && (o.solver == VLG_BA_SOLVER_PCG_EXPLICIT || (o.solver == VLG_BA_SOLVER_AUTO && pays));
     }
     const bool need_S = ctx->use_chol || ctx->use_explicit;
+    // cluster-Jacobi preconditioner (PCG paths): needs the cooperative update kernel, one CTA per cluster
+    bool cluster_pc = false;
+    {
+        int coop = 0, nsm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+        cluster_pc = !ctx->use_chol && o.pcg_cluster && coop && cdiv(m, 128 / na) <= nsm * 8;
+    }
+    const bool cluster_blocks = cluster_pc && !ctx->use_explicit;     // implicit path: assemble the within-cluster blocks only
 
     // block structure of S: cameras j <= k sharing a point; pair lists in ascending point order
     std::vector<int64_t> blk_ptr;
@@ -450,6 +465,38 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
                     const int64_t s = slot[(size_t)pt_cam[qa] * m + pt_cam[qb]];
                     pairs[(size_t)fill[s]++] = make_int2(pt_obs[qa], pt_obs[qb]);
                 }
+        ctx->nblocks = (int64_t)ctx->h_blk_j.size();
+        ctx->npairs = (int64_t)pairs.size();
+    } else if (cluster_blocks) {
+        // implicit-Schur PCG with the cluster-Jacobi preconditioner: only the blocks (j,k) whose cameras sit in
+        // the same cluster of kc consecutive cameras are ever assembled; same pair-list layout, compact keys
+        const int kc = 128 / na, gcl = (m + kc - 1) / kc;
+        auto key = [&](int j, int k) { return ((size_t)(j / kc) * kc + (size_t)(j % kc)) * kc + (size_t)(k % kc); };
+        std::vector<int64_t> cnt((size_t)gcl * kc * kc + 1, 0);
+        for (int i = 0; i < n; i++)
+            for (int qa = pt_ptr[i]; qa < pt_ptr[i + 1]; qa++)
+                for (int qb = qa + 1; qb < pt_ptr[i + 1]; qb++)
+                    if (pt_cam[qa] / kc == pt_cam[qb] / kc) cnt[key(pt_cam[qa], pt_cam[qb]) + 1]++;
+        std::vector<int64_t> slot((size_t)gcl * kc * kc, -1);
+        blk_ptr.push_back(0);
+        for (int j = 0; j < m; j++)
+            for (int k = j + 1; k < std::min(m, (j / kc + 1) * kc); k++) {
+                const int64_t c = cnt[key(j, k) + 1];
+                if (c > 0) {
+                    slot[key(j, k)] = (int64_t)ctx->h_blk_j.size();
+                    ctx->h_blk_j.push_back(j); ctx->h_blk_k.push_back(k);
+                    blk_ptr.push_back(blk_ptr.back() + c);
+                }
+            }
+        pairs.resize((size_t)blk_ptr.back());
+        std::vector<int64_t> fill(blk_ptr.begin(), blk_ptr.end() - 1);
+        for (int i = 0; i < n; i++)
+            for (int qa = pt_ptr[i]; qa < pt_ptr[i + 1]; qa++)
+                for (int qb = qa + 1; qb < pt_ptr[i + 1]; qb++)
+                    if (pt_cam[qa] / kc == pt_cam[qb] / kc) {
+                        const int64_t s = slot[key(pt_cam[qa], pt_cam[qb])];
+                        pairs[(size_t)fill[s]++] = make_int2(pt_obs[qa], pt_obs[qb]);
+                    }
         ctx->nblocks = (int64_t)ctx->h_blk_j.size();
         ctx->npairs = (int64_t)pairs.size();
     } else {
@@ -538,7 +585,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         const int g = cdiv(m, 128 / na);            // k_pcg_update_coop: a CTA owns 128/na whole cameras
         if (coop && g <= nsm * 8) ctx->coop_grid = g;
         CHK(dalloc(ctx, &ctx->blkpart, (size_t)11 * std::max(g, 1)));
-        if (ctx->use_explicit && ctx->coop_grid > 0 && ctx->opt.pcg_cluster) {
+        if (cluster_pc && ctx->coop_grid > 0) {
             CHK(dalloc(ctx, &ctx->Cblk, (size_t)g * 128 * 128)); CHK(dalloc(ctx, &ctx->McL, (size_t)g * 128 * 128));
         }
         CHK(dalloc(ctx, &ctx->Zd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->SZd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->defl_sc, 1));
@@ -605,8 +652,8 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         const int64_t tiles = (int64_t)nb * (nb + 1) / 2;
         ctx->chol_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->nsm, (tiles + kCholWarps - 1) / kCholWarps));
     }
-    if (need_S) {
-        CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));
+    if (need_S) CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));
+    if (need_S || cluster_blocks) {
         CHK(dalloc(ctx, &ctx->blk_j, (size_t)ctx->nblocks)); CHK(dalloc(ctx, &ctx->blk_k, (size_t)ctx->nblocks));
         CHK(dalloc(ctx, &ctx->blk_ptr, (size_t)ctx->nblocks + 1)); CHK(dalloc(ctx, &ctx->pairs, (size_t)ctx->npairs));
         CHK(upload(ctx, ctx->blk_j, ctx->h_blk_j.data(), (size_t)ctx->nblocks));

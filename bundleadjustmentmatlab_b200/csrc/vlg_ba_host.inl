@@ -26,18 +26,18 @@ int allreduce_pcg_vector(vlg_ba_ctx* ctx, double* v, int n, const int* done)
 
 // S (or this rank's share of it) from the Y kept by k_cam_schur_diag: heavy blocks a warp each, light blocks a thread each
 template <int NA>
-int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S)
+int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S, int ccams = 0)
 {
-    k_schur_diag_fill<NA><<<cdiv((int64_t)ctx->m * NA * NA, 256), 256, 0, ctx->stream>>>(ctx->m, ctx->Np, add_U, ctx->red2_local, ctx->Ud, S);
+    k_schur_diag_fill<NA><<<cdiv((int64_t)ctx->m * NA * NA, 256), 256, 0, ctx->stream>>>(ctx->m, ctx->Np, ccams, add_U, ctx->red2_local, ctx->Ud, S);
     ctx->launches++;
     if (ctx->nheavy > 0) {
         k_schur_blocks_heavy<NA><<<cdiv(ctx->nheavy, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
-            ctx->nheavy, ctx->blk_heavy, ctx->Np, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
+            ctx->nheavy, ctx->blk_heavy, ctx->Np, ccams, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
         ctx->launches++;
     }
     if (ctx->nlight > 0) {
         k_schur_blocks_light<NA><<<cdiv(ctx->nlight, 128), 128, 0, ctx->stream>>>(
-            ctx->nlight, ctx->blk_light, ctx->Np, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
+            ctx->nlight, ctx->blk_light, ctx->Np, ccams, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -116,11 +116,17 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CHK(assemble_S<NA>(ctx, 0, ctx->S));
         }
         const double* McL = nullptr;
-        if (ctx->use_explicit && ctx->McL) {
+        if (ctx->McL) {
             // cluster-Jacobi: diagonal blocks of S over the update kernel's CTAs, summed over ranks, inverted
             TimedScope ts(ctx, T_PRECOND);
-            k_cluster_gather<NA><<<ctx->coop_grid, 128, 0, ctx->stream>>>(m, ctx->Np, ctx->S, ctx->Cblk);
-            ctx->launches++;
+            if (ctx->use_explicit) {
+                k_cluster_gather<NA><<<ctx->coop_grid, 128, 0, ctx->stream>>>(m, ctx->Np, ctx->S, ctx->Cblk);
+                ctx->launches++;
+            } else {
+                // implicit path: only the within-cluster blocks are assembled (pair lists restricted to them)
+                CU(cudaMemsetAsync(ctx->Cblk, 0, sizeof(double) * (size_t)ctx->coop_grid * 128 * 128, ctx->stream));
+                CHK(assemble_S<NA>(ctx, 0, ctx->Cblk, Cluster<NA>::kCams));
+            }
             CHK(allreduce(ctx, ctx->Cblk, (size_t)ctx->coop_grid * 128 * 128));
             CU(cudaFuncSetAttribute(k_cluster_inverse<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cluster<NA>::kSmem));
             k_cluster_inverse<NA><<<ctx->coop_grid, 256, Cluster<NA>::kSmem, ctx->stream>>>(m, 1, ctx->Cblk, ctx->Ud, ctx->McL);
@@ -704,7 +710,7 @@ int vlg_ba_get_reduced(vlg_ba_ctx* ctx, double* Vinv, double* S, double* e_, dou
         CU(cudaMalloc(&tmp, sizeof(double) * (size_t)Np * Np));
         CU(cudaMemsetAsync(tmp, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
         {
-            const int r = DISPATCH_NA(ctx, assemble_S)(ctx, 1, tmp);
+            const int r = DISPATCH_NA(ctx, assemble_S)(ctx, 1, tmp, 0);
             if (r != VLG_BA_OK) { cudaFree(tmp); return r; }
         }
         cudaError_t e = cudaMemcpy2DAsync(S, sizeof(double) * N, tmp, sizeof(double) * (size_t)Np, sizeof(double) * N, N,

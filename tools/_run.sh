@@ -1,5 +1,6 @@
-N=$1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-p2p > gpurun_out/bench_venice_${N}gpu_r01u.json 2> gpurun_out/bench_${N}gpu_u.err
-echo rc=$?
-python -c "
-import json;d=json.loads([l for l in open('gpurun_out/bench_venice_${N}gpu_r01u.json') if l.startswith('{')][0]);print(d['n_gpus'],d['value'],d['ms_per_step'],d['lm_iters_per_sec'],0,d['config'].get('pcg_vector_allreduce'),d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_${N}gpu_u.err
+set -x
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
+python bench.py --config trafalgar --solver pcg --steps 10 --warmup 3 --no-cpu-baseline --no-e2e | python -c "
+import json,sys;d=json.loads(sys.stdin.read());print(d['ms_per_step'],d['lm_iters_per_sec'],d['cost_first_last'],d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"
+timeout 1200 python bench.py --config final --steps 3 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_final_r01v.json 2> gpurun_out/bench_final_v.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_final_r01v.json'));print(d['ms_per_step'],d['lm_iters_per_sec'],d['cost_first_last'],d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_final_v.err
