@@ -115,8 +115,8 @@ def workload_name(args, P, world):
 def cpu_trial_steps(args, P, a, b, steps, warmup):
     from oracle import lm
     lib = lm.sparse_lib()
-    if args.cpu_threads > 0:
-        lib.orc_set_num_threads(args.cpu_threads)
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: do not inherit that)
+    lib.orc_set_num_threads(args.cpu_threads if args.cpu_threads > 0 else len(os.sched_getaffinity(0)))
     cores = int(lib.orc_num_threads())
     obs = lm.ObsList(P.m, P.n, P.obs_xy, P.obs_pt, P.obs_cam)
     aa, bb, lam = a.T.copy(), b.T.copy(), 1e-3

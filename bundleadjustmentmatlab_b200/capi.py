@@ -59,7 +59,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse",
 ]
 
 

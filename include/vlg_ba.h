@@ -207,6 +207,16 @@ int  vlg_ba_bundle_euclid(const vlg_ba_opts *opts, int m, int n, const double *K
                           const double *pivot, double *K_, double *Te_, double *w_, double *Xe_,
                           double *error_, int *n_error);
 
+/* The same on an observation list (no dense n x m array anywhere): obs_xy 2 x nobs, obs_pt / obs_cam
+ * 0-based, in the reference's traversal order (ascending i + n*j).  Replaces the dense `x` (3 x n x m)
+ * and `visibility` (n x m) arguments of bundle_euclid.m:9,18 for problems the dense interface cannot
+ * express.  mex/mex_bundle_euclid_gpu_sparse.c + mex/bundle_euclid_gpu_sparse.m. */
+int  vlg_ba_bundle_euclid_sparse(const vlg_ba_opts *opts, int m, int n,
+                                 const double *K, const double *Te, const double *w, const double *Xe,
+                                 int64_t nobs, const double *obs_xy, const int32_t *obs_pt, const int32_t *obs_cam,
+                                 const double *pivot /*m or NULL*/,
+                                 double *K_, double *Te_, double *w_, double *Xe_, double *error_, int *n_error);
+
 /* Introspection for tests and benches. */
 int  vlg_ba_get_schur_structure(vlg_ba_ctx *ctx, int64_t *n_blocks, int32_t *blk_j, int32_t *blk_k);
 int64_t vlg_ba_kernel_launches(const vlg_ba_ctx *ctx);

@@ -309,16 +309,48 @@ def test_empty_and_ragged_inputs():
     obs = lm.ObsList(P.m, P.n, np.ascontiguousarray(P.obs_xy[keep]), P.obs_pt[keep], P.obs_cam[keep])
     o = lm.parse_options(P.m, P.n, np.ones((2, 1, 1)), ["fix_calibration", "visibility", np.zeros(0)])
     t = lm.lm_trial(P.K, a, b, obs, 1e-3, o, backend="sparse")
-    ctx = capi.Context(num_variableK=0, solver=capi.SOLVER_CHOL)
-    ctx.set_problem_sparse(P.K.T, a.T, b.T, obs.xy, obs.pt, obs.cam)
-    info = ctx.trial_step()
-    assert rel(info["old_cost"], t["old"]) <= 1e-12 and rel(info["new_cost"], t["new"]) <= COST_RTOL
-    ctx.close()
+    for solver in (capi.SOLVER_CHOL, capi.SOLVER_PCG, capi.SOLVER_PCG_EXPLICIT):
+        ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-12)
+        ctx.set_problem_sparse(P.K.T, a.T, b.T, obs.xy, obs.pt, obs.cam)
+        info = ctx.trial_step()
+        assert rel(info["old_cost"], t["old"]) <= 1e-12 and rel(info["new_cost"], t["new"]) <= COST_RTOL, (solver, info)
+        ctx.close()
     # out-of-order list is refused
     ctx = capi.Context(num_variableK=0)
     with pytest.raises(capi.VlgBaError):
         ctx.set_problem_sparse(P.K.T, a.T, b.T, obs.xy[::-1].copy(), obs.pt[::-1].copy(), obs.cam[::-1].copy())
     ctx.close()
+
+
+def test_incremental_cadence_context_reuse():
+    """The reference's heaviest caller adds one camera at a time and runs BA on the growing problem
+    (incr_reconstruction.m:223-348, about 3 bundle_euclid calls per camera; estimate_camera.m:247-253 is a
+    single-camera motion-only BA).  One context is re-used for every call -- set_problem_* on a live context
+    must rebuild every structure (solver path, tile lists, optional buffers) -- and each call must match the
+    CPU oracle run on the same sub-problem."""
+    P = synth.make_problem(12, 400, 2600, seed=21)
+    a_all = np.vstack([P.w, P.Te]); b_all = P.Xe[:3].copy()
+    o = lm.parse_options(P.m, P.n, np.ones((2, 1, 1)), ["fix_calibration", "visibility", np.zeros(0)])
+    ctx = capi.Context(num_variableK=0)
+    ctx_fs = capi.Context(num_variableK=0, fix_structure=1)
+    for mc in (2, 3, 5, 8, 12):
+        keep = P.obs_cam < mc
+        obs = lm.ObsList(mc, P.n, np.ascontiguousarray(P.obs_xy[keep]), P.obs_pt[keep], P.obs_cam[keep])
+        a = a_all[:, :mc].copy()
+        # (i) motion-only BA of the newest camera alone (fix_structure, one camera)
+        k1 = P.obs_cam[keep] == mc - 1
+        obs1 = lm.ObsList(1, P.n, np.ascontiguousarray(obs.xy[k1]), obs.pt[k1], np.zeros(int(k1.sum()), dtype=np.int32))
+        o1 = dict(o); o1["fix_structure"] = True
+        t1 = lm.lm_trial(P.K[:, mc - 1:mc], a[:, mc - 1:mc], b_all, obs1, 1e-3, o1, backend="sparse")
+        ctx_fs.set_problem_sparse(P.K.T[mc - 1:mc], a.T[mc - 1:mc], b_all.T, obs1.xy, obs1.pt, obs1.cam)
+        i1 = ctx_fs.trial_step()
+        assert rel(i1["old_cost"], t1["old"]) <= 1e-12 and rel(i1["new_cost"], t1["new"]) <= COST_RTOL, (mc, i1, t1["new"])
+        # (ii) full BA over the cameras so far, same context as the previous (smaller) problem
+        t = lm.lm_trial(P.K[:, :mc], a, b_all, obs, 1e-3, o, backend="sparse")
+        ctx.set_problem_sparse(P.K.T[:mc], a.T, b_all.T, obs.xy, obs.pt, obs.cam)
+        info = ctx.trial_step()
+        assert rel(info["old_cost"], t["old"]) <= 1e-12 and rel(info["new_cost"], t["new"]) <= COST_RTOL, (mc, info, t["new"])
+    ctx.close(); ctx_fs.close()
 
 
 def test_large_problem_invariants():

@@ -22,9 +22,10 @@ def build_shim():
 
 
 def test_mex_wrappers_compile_and_export():
-    """CPU: the four wrappers compile against a mex.h and export their entry points."""
+    """CPU: the five wrappers compile against a mex.h and export their entry points."""
     L = C.CDLL(build_shim())
-    for s in ("vlgref_mex1", "vlgref_mex2", "vlgref_mex3", "vlggpu_mex_euclid", "vlgref_stage1", "vlgref_stage2", "vlgref_stage3"):
+    for s in ("vlgref_mex1", "vlgref_mex2", "vlgref_mex3", "vlggpu_mex_euclid", "vlggpu_mex_euclid_sparse", "vlgref_stage1",
+              "vlgref_stage2", "vlgref_stage3"):
         assert hasattr(L, s), s
 
 
@@ -141,3 +142,36 @@ def test_fused_mex_entry_point():
     Xe_ = np.array([pout[3].contents.pr[k] for k in range(4 * n)]).reshape(n, 4).T
     # the points themselves are only defined up to the gauge the two linear solvers drift along
     assert np.array_equal(Xe_[3], g["Xe"][3]) and np.abs(Xe_ - g["Xe_"]).max() <= 0.1
+
+
+@pytest.mark.gpu
+def test_fused_sparse_mex_entry_point():
+    """mex_bundle_euclid_gpu_sparse: the same solve from an observation list (1-based, reference order) --
+    no dense n x m array crosses the boundary -- must reproduce the dense entry's error_ bit for bit."""
+    g = load_golden("euclid_fixpivot")
+    L = C.CDLL(build_shim())
+    flags = mx(np.array([0.0, 0.0, 0.0, 0.0]))
+    piv = mx(np.asarray(g["pivot"], dtype=np.float64).reshape(1, -1))
+    # dense call
+    ins = [mx(g["K"]), mx(g["Te"]), mx(g["w"]), mx(g["Xe"]), mx(g["x"]), mx(g["visible"]), piv, flags]
+    pin = (C.POINTER(MxArray) * 8)(*[C.pointer(t) for t in ins])
+    pd = (C.POINTER(MxArray) * 5)()
+    L.vlggpu_mex_euclid(C.c_int(5), pd, C.c_int(8), pin)
+    # list call
+    xy = np.asfortranarray(g["obs_xy"].T)                       # 2 x nobs
+    pt1 = (g["obs_pt"] + 1).astype(np.float64).reshape(1, -1)
+    cam1 = (g["obs_cam"] + 1).astype(np.float64).reshape(1, -1)
+    ins2 = [mx(g["K"]), mx(g["Te"]), mx(g["w"]), mx(g["Xe"]), mx(xy), mx(pt1), mx(cam1), piv, flags]
+    pin2 = (C.POINTER(MxArray) * 9)(*[C.pointer(t) for t in ins2])
+    ps = (C.POINTER(MxArray) * 5)()
+    L.vlggpu_mex_euclid_sparse(C.c_int(5), ps, C.c_int(9), pin2)
+    ne = int(pd[4].contents.dims[1])
+    assert int(ps[4].contents.dims[1]) == ne and ne >= 2
+    ed = np.array([pd[4].contents.pr[k] for k in range(ne)]); es = np.array([ps[4].contents.pr[k] for k in range(ne)])
+    assert np.array_equal(ed, es)
+    ref = g["error_"]
+    assert rel(es[0], ref[0]) <= 1e-12 and rel(np.sqrt(es[-1]), np.sqrt(ref[-1])) <= 1e-6
+    n = int(g["n"])
+    for k, cnt in ((0, 4 * int(g["m"])), (3, 4 * n)):
+        assert np.array_equal(np.array([pd[k].contents.pr[t] for t in range(cnt)]), np.array([ps[k].contents.pr[t] for t in range(cnt)]))
+
