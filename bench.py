@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--model", default="euclid", choices=["euclid", "projective"],
+                    help="euclid: bundle_euclid.m with 'fix_calibration' (num_a = 6, the headline); projective: bundle_projective.m (num_a = 12)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: all-reduce the PCG vector with NCCL instead of peer-memory mailboxes")
     return ap.parse_args()
 
@@ -99,7 +101,21 @@ class ClockSampler:
 def make_shard(args, rank):
     from bundleadjustmentmatlab_b200 import synth
     P = synth.make_config(args.config, seed=args.seed, scale=args.scale, point_seed=rank)
-    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T)
+    if getattr(args, "model", "euclid") == "projective":
+        # a = vec(P_j), P_j = K_j [R(w_j) T_j]  (bundle_projective.m:69-72)
+        a = np.zeros((P.m, 12))
+        for j in range(P.m):
+            w = P.w[:, j]; th = np.linalg.norm(w)
+            if th < 1e-6:
+                R = np.eye(3)
+            else:
+                k = w / th
+                Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+                R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+            Kj = np.array([[P.K[0, j], 0, P.K[2, j]], [0, P.K[1, j], P.K[3, j]], [0, 0, 1]])
+            a[j] = (Kj @ np.hstack([R, P.Te[:, j:j + 1]])).reshape(12, order="F")
+    else:
+        a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T)
     b = np.ascontiguousarray(P.Xe[:3].T)
     return P, a, b
 
@@ -139,6 +155,10 @@ def cpu_trial_steps(args, P, a, b, steps, warmup):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.model == "projective":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU port (oracle_sparse.c) restates the Euclidean model only; "
+                          "the projective reference runs dense through oracle/_ref at test sizes"}), flush=True)
         return
     P, a, b = make_shard(args, 0)
     times, iters, cores = cpu_trial_steps(args, P, a, b, args.steps, args.warmup)
@@ -202,14 +222,17 @@ def run_ours(args):
     P, a0, b0 = make_shard(args, rank)
     solver = {"auto": capi.SOLVER_AUTO, "chol": capi.SOLVER_CHOL, "pcg": capi.SOLVER_PCG, "pcgx": capi.SOLVER_PCG_EXPLICIT}[args.solver]
     rtable = capi.RTABLE_HOST_LIBM if args.rtable == "host" else capi.RTABLE_DEVICE
-    ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=args.pcg_rtol, rtable=rtable, device=local)
+    proj = args.model == "projective"
+    na = 12 if proj else 6
+    ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=args.pcg_rtol, rtable=rtable, device=local,
+                       model=capi.MODEL_PROJECTIVE if proj else capi.MODEL_EUCLID)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(capi.Context.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         ctx.set_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
-    ctx.set_problem_sparse(P.K.T, a0, b0, P.obs_xy, P.obs_pt, P.obs_cam)
+    ctx.set_problem_sparse(None if proj else P.K.T, a0, b0, P.obs_xy, P.obs_pt, P.obs_cam)
     p2p = world > 1 and not args.no_p2p
     if p2p:
         # the per-iteration PCG vector goes through NVLink peer-memory mailboxes (CUDA IPC), not NCCL
@@ -289,8 +312,11 @@ def run_ours(args):
             info = ctx.trial_step_host(ha, hb, hxy, st["lam"], ha_new, hb_new)
             if info["accepted"]:
                 ha[:] = ha_new; hb[:] = hb_new
-                st["lam"] *= max(1.0 / 3.0, 1 - (2 * info["rho"] - 1) ** 3)
-                st["nu"] = 2.0
+                if proj:
+                    st["lam"] /= 10                      # bundle_projective.m:194
+                else:
+                    st["lam"] *= max(1.0 / 3.0, 1 - (2 * info["rho"] - 1) ** 3)
+                    st["nu"] = 2.0
                 e = st["err"]
                 while len(e) < st["it"] + 1:
                     e.append(0.0)
@@ -299,7 +325,11 @@ def run_ours(args):
                 e[st["it"] - 1] = info["new_cost"] / nvis
                 st["it2"] = 0
             else:
-                st["lam"] *= st["nu"]; st["nu"] *= 2; st["it2"] += 1
+                if proj:
+                    st["lam"] *= 10                      # bundle_projective.m:204
+                else:
+                    st["lam"] *= st["nu"]; st["nu"] *= 2
+                st["it2"] += 1
         for _ in range(args.warmup):
             one()
         barrier()
@@ -322,11 +352,11 @@ def run_ours(args):
             peaks = json.load(open(pk_path))
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        dom = max((g for g in groups if algorithmic_bytes(g, P) and groups[g]["count"] > 0),
+        dom = max((g for g in groups if algorithmic_bytes(g, P, na) and groups[g]["count"] > 0),
                   key=lambda g: groups[g]["total_ms"], default=None)
         roof = None
         if dom:
-            ab = algorithmic_bytes(dom, P)
+            ab = algorithmic_bytes(dom, P, na)
             ach = ab / (groups[dom]["avg_ms"] * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -339,12 +369,12 @@ def run_ours(args):
         per_kernel = {}
         for g, v in groups.items():
             if v["count"]:
-                ab = algorithmic_bytes(g, P)
+                ab = algorithmic_bytes(g, P, na)
                 per_kernel[g] = {"avg_ms": round(v["avg_ms"], 5), "count": v["count"],
                                  "GBps": (ab / (v["avg_ms"] * 1e-3) / 1e9) if ab else None}
         js = sum(groups[g]["total_ms"] for g in ("stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "pcg_sweep_pt", "pcg_sweep_cam", "pcg_symv"))
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not proj:     # the CPU port restates the Euclidean model only
             times, iters, cores = cpu_trial_steps(args, P, a0, b0, 1, 0)
             cpu = {"value": P.nobs * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"1 whole LM trial step on rank 0's shard ({P.nobs} observations, {iters[0]} PCG iterations, "
@@ -353,7 +383,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, P, world), "num_a": 6,
+            "config": {"workload": workload_name(args, P, world), "num_a": na, "model": args.model,
                        "solver": {capi.SOLVER_CHOL: "cholesky", capi.SOLVER_PCG: "pcg (block-Jacobi, implicit Schur)",
                                   capi.SOLVER_PCG_EXPLICIT: "pcg (block-Jacobi, assembled S, symmetric lower-triangle matvec)"}[infos[-1]["solver_used"]],
                        "pcg_rtol": args.pcg_rtol, "rtable": args.rtable,

@@ -148,3 +148,20 @@ def mex_bundle_3_db_new(W, da, eB, V_inv, K, a, b, X, visible):
                                         capi._d(V_inv), capi._d(K), capi._d(a), capi._d(b), capi._d(X), capi._d(visible),
                                         capi._d(db), capi._d(a_new), capi._d(b_new), capi._d(X_hat)))
     return db, a_new, b_new, X_hat
+
+
+def bundle_projective(Pp, Xp, x, *options, **ctx_opts):
+    """[Pp_ Xp_ error_] = bundle_projective(Pp, Xp, x, ...)  -- toolbox/bundle/bundle_projective.m:1-229.
+    Pp (3,4,m), Xp (4,n), x (3,n,m); options 'fix_structure', 'fix_motion', 'visibility', vis, 'verbose'."""
+    Pp = np.asarray(Pp, dtype=np.float64); Xp = np.asarray(Xp, dtype=np.float64); x = np.asarray(x, dtype=np.float64)
+    m, n = Pp.shape[2], x.shape[1]
+    o = parse_options(m, n, x, options)
+    opts = capi.default_opts(model=capi.MODEL_PROJECTIVE, fix_structure=int(o["fix_structure"]),
+                             fix_motion=int(o["fix_motion"]), verbose=int(o["verbose"]), **ctx_opts)
+    Ppf = np.asfortranarray(Pp); Xpf = np.asfortranarray(Xp); xf = np.asfortranarray(x)
+    vis = np.asfortranarray(np.asarray(o["visible"], dtype=np.float64).reshape(n, m))
+    Pp_ = np.zeros((3, 4, m), order="F"); Xp_ = np.zeros((4, n), order="F")
+    err = np.zeros(opts.max_iter + 2); ne = _C.c_int(0)
+    _check(capi.lib().vlg_ba_bundle_projective(_C.byref(opts), _C.c_int(m), _C.c_int(n), capi._d(Ppf), capi._d(Xpf), capi._d(xf),
+                                               capi._d(vis), capi._d(Pp_), capi._d(Xp_), capi._d(err), _C.byref(ne)))
+    return Pp_, Xp_, err[:ne.value].copy()

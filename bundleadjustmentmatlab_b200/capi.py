@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvlgba.so")
 
 SOLVER_AUTO, SOLVER_CHOL, SOLVER_PCG, SOLVER_PCG_EXPLICIT = 0, 1, 2, 3
+MODEL_EUCLID, MODEL_PROJECTIVE = 0, 1
 RTABLE_HOST_LIBM, RTABLE_DEVICE = 0, 1
 ORDER_CHUNKED, ORDER_REFERENCE = 0, 1
 
@@ -28,7 +29,7 @@ class Opts(C.Structure):
         ("rel_tol", C.c_double), ("abs_tol", C.c_double), ("backsub_all_rows", C.c_int),
         ("solver", C.c_int), ("chol_max_cams", C.c_int), ("pcg_rtol", C.c_double), ("pcg_max_iter", C.c_int),
         ("rtable", C.c_int), ("order", C.c_int), ("device", C.c_int), ("verbose", C.c_int),
-        ("pcg_deflate", C.c_int), ("pcg_cluster", C.c_int),
+        ("pcg_deflate", C.c_int), ("pcg_cluster", C.c_int), ("model", C.c_int),
     ]
 
 
@@ -59,7 +60,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective",
 ]
 
 
@@ -119,7 +120,7 @@ class Context:
         if r != 0:
             raise VlgBaError(f"vlg_ba_create failed ({r}): {self._L.vlg_ba_last_error(None).decode()}")
         self.m = self.n = 0
-        self.na = 6 + self.opts.num_variableK
+        self.na = 12 if self.opts.model == MODEL_PROJECTIVE else 6 + self.opts.num_variableK
 
     def close(self):
         if self._h:
@@ -160,8 +161,9 @@ class Context:
 
     # ---- problem
     def set_problem_sparse(self, K, a, b, obs_xy, obs_pt, obs_cam, pivot=None):
-        K, a, b = _c(K), _c(a), _c(b)
-        m, n = K.shape[0], b.shape[0]
+        a, b = _c(a), _c(b)
+        K = None if K is None else _c(K)          # the projective model has no K
+        m, n = a.shape[0], b.shape[0]
         assert a.shape == (m, self.na), (a.shape, m, self.na)
         obs_xy = _c(obs_xy)
         obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
@@ -174,8 +176,9 @@ class Context:
 
     def set_problem_dense(self, K, a, b, X, visible, pivot=None):
         """X (2,n,m) and visible (n,m) Fortran-ordered, as the reference's mex1 takes them."""
-        K, a, b = _c(K), _c(a), _c(b)
-        m, n = K.shape[0], b.shape[0]
+        a, b = _c(a), _c(b)
+        K = None if K is None else _c(K)
+        m, n = a.shape[0], b.shape[0]
         X = np.asfortranarray(X, dtype=np.float64)
         visible = np.asfortranarray(visible, dtype=np.float64)
         assert X.shape == (2, n, m) and visible.shape == (n, m)

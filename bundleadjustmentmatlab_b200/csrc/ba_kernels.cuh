@@ -66,12 +66,15 @@ k_stage1_cam(Stage1Args p)
     if (c >= p.nchunks) return;
     const int j = p.chunk_cam[c];
     const int beg = p.chunk_begin[c], end = p.chunk_end[c];
-    for (int t = lane; t < 36; t += 32) camR[t] = p.rtab[(size_t)36 * j + t];
+    constexpr bool kProj = NA == kNaProjective;        // projective model: the camera is its 12 parameters, no K, no rotation table
+    if (!kProj) {
+        for (int t = lane; t < 36; t += 32) camR[t] = p.rtab[(size_t)36 * j + t];
+        if (lane < 4) camK[lane] = p.K4[(size_t)4 * j + lane];
+    }
     if (lane < NA) cama[lane] = p.a[(size_t)NA * j + lane];
-    if (lane < 4) camK[lane] = p.K4[(size_t)4 * j + lane];
     __syncwarp();
-    double fx, fy, cx, cy;
-    effective_K<NA>(camK, cama, fx, fy, cx, cy);
+    double fx = 0.0, fy = 0.0, cx = 0.0, cy = 0.0;
+    if (!kProj) effective_K<NA>(camK, cama, fx, fy, cx, cy);
     const bool zeroW = p.fix_structure || p.cam_fixed[j];
 
     constexpr int NACC = (NU + 31) / 32;
@@ -87,7 +90,8 @@ k_stage1_cam(Stage1Args p)
             const int i = p.obs_pt[o];
             const double b0 = p.b[(size_t)3 * i], b1 = p.b[(size_t)3 * i + 1], b2 = p.b[(size_t)3 * i + 2];
             double X0[2], A[2 * NA], B[6], e[2];
-            obs_jacobian<NA>(camR, cama, fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
+            if constexpr (kProj) obs_jacobian_proj<true>(cama, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
+            else obs_jacobian<NA>(camR, cama, fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
             if (DIAG) {
                 if (p.dX_hat) { p.dX_hat[(size_t)2 * o] = X0[0]; p.dX_hat[(size_t)2 * o + 1] = X0[1]; }
                 if (p.dA) for (int k = 0; k < 2 * NA; k++) p.dA[(size_t)2 * NA * o + k] = A[k];
@@ -168,6 +172,36 @@ __global__ void k_stage1_cam_finalize(int m, const int* __restrict__ cam_chunk_p
     }
 }
 
+// B (2 x 3) and e of one observation of camera j, as the point passes need them: the camera's
+// parameters come through the read-only path (every lane has its own camera)
+template <int NA>
+__device__ __forceinline__ void point_terms(int j, const double* __restrict__ K4, const double* __restrict__ a,
+                                            const double* __restrict__ rtab, double b0, double b1, double b2,
+                                            double ox, double oy, double* __restrict__ B, double* __restrict__ e)
+{
+    const double* aj = a + (size_t)NA * j;
+    if constexpr (NA == kNaProjective) {
+        double Pl[12], X0[2];
+#pragma unroll
+        for (int k = 0; k < 12; k++) Pl[k] = __ldg(aj + k);
+        obs_jacobian_proj<false>(Pl, b0, b1, b2, ox, oy, X0, nullptr, B, e);
+    } else {
+        const double* R = rtab + (size_t)36 * j;
+        double Rl[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rl[k] = __ldg(R + k);
+        double al[NA];
+#pragma unroll
+        for (int k = 3; k < NA; k++) al[k] = __ldg(aj + k);
+        double fx, fy, cx, cy;
+        double Kl[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
+        effective_K<NA>(Kl, al, fx, fy, cx, cy);
+        obs_point_jacobian(Rl, al[3], al[4], al[5], fx, fy, cx, cy, b0, b1, b2, ox, oy, B, e);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // stage 1, point pass: one thread per point walks its track in ascending camera order
 // (the reference's order for V_i and eB_i, mex_bundle_1_XABeUVWeAeB.c:293-302,:326-332),
@@ -189,21 +223,8 @@ __global__ void k_stage1_pt(int n, const int* __restrict__ pt_ptr, const int* __
     for (int q = q0; q < q1; q++) {
         const int j = pt_cam[q];
         const double2 xy = pt_xy[q];
-        const double* R = rtab + (size_t)36 * j;
-        const double* aj = a + (size_t)NA * j;
-        double Rl[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rl[k] = __ldg(R + k);
-        double al[NA];
-#pragma unroll
-        for (int k = 3; k < NA; k++) al[k] = __ldg(aj + k);
-        double fx, fy, cx, cy;
-        double Kl[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
-        effective_K<NA>(Kl, al, fx, fy, cx, cy);
         double B[6], e[2];
-        obs_point_jacobian(Rl, al[3], al[4], al[5], fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, B, e);
+        point_terms<NA>(j, K4, a, rtab, b0, b1, b2, xy.x, xy.y, B, e);
         v00 = VLG_P(v00, dot2(B[0], B[1], B[0], B[1]));
         v10 = VLG_P(v10, dot2(B[2], B[3], B[0], B[1]));
         v20 = VLG_P(v20, dot2(B[4], B[5], B[0], B[1]));
@@ -252,21 +273,8 @@ k_stage1_pt_tiled(const int4* __restrict__ ptile_meta /* (q0, nob, p0, npts) */,
         const int j = pt_cam[q], i = pt_pt[q];
         const double2 xy = pt_xy[q];
         const double b0 = __ldg(b + (size_t)3 * i), b1 = __ldg(b + (size_t)3 * i + 1), b2 = __ldg(b + (size_t)3 * i + 2);
-        const double* R = rtab + (size_t)36 * j;
-        const double* aj = a + (size_t)NA * j;
-        double Rl[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rl[k] = __ldg(R + k);
-        double al[NA];
-#pragma unroll
-        for (int k = 3; k < NA; k++) al[k] = __ldg(aj + k);
-        double fx, fy, cx, cy;
-        double Kl[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
-        effective_K<NA>(Kl, al, fx, fy, cx, cy);
         double B[6], e[2];
-        obs_point_jacobian(Rl, al[3], al[4], al[5], fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, B, e);
+        point_terms<NA>(j, K4, a, rtab, b0, b1, b2, xy.x, xy.y, B, e);
         pr[0][tid] = dot2(B[0], B[1], B[0], B[1]);
         pr[1][tid] = dot2(B[2], B[3], B[0], B[1]);
         pr[2][tid] = dot2(B[4], B[5], B[0], B[1]);
@@ -965,17 +973,25 @@ __global__ void k_new_cost(int64_t nobs, const double2* __restrict__ obs_xy, con
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= nobs) return;
     const int i = obs_pt[o], j = obs_cam[o];
-    double R[9], al[NA], Kl[4];
+    double x, y;
+    if constexpr (NA == kNaProjective) {
+        double Pl[12];
 #pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = __ldg(rtab_new + (size_t)9 * j + k);
+        for (int k = 0; k < 12; k++) Pl[k] = __ldg(a_new + (size_t)NA * j + k);
+        project_P(Pl, b_new[(size_t)3 * i], b_new[(size_t)3 * i + 1], b_new[(size_t)3 * i + 2], x, y);
+    } else {
+        double R[9], al[NA], Kl[4];
 #pragma unroll
-    for (int k = 3; k < NA; k++) al[k] = __ldg(a_new + (size_t)NA * j + k);
+        for (int k = 0; k < 9; k++) R[k] = __ldg(rtab_new + (size_t)9 * j + k);
 #pragma unroll
-    for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
-    double fx, fy, cx, cy, x, y;
-    effective_K<NA>(Kl, al, fx, fy, cx, cy);
-    project_R(R, al[3], al[4], al[5], fx, fy, cx, cy, b_new[(size_t)3 * i], b_new[(size_t)3 * i + 1],
-              b_new[(size_t)3 * i + 2], x, y);
+        for (int k = 3; k < NA; k++) al[k] = __ldg(a_new + (size_t)NA * j + k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
+        double fx, fy, cx, cy;
+        effective_K<NA>(Kl, al, fx, fy, cx, cy);
+        project_R(R, al[3], al[4], al[5], fx, fy, cx, cy, b_new[(size_t)3 * i], b_new[(size_t)3 * i + 1],
+                  b_new[(size_t)3 * i + 2], x, y);
+    }
     const double2 xy = obs_xy[o];
     const double e0 = VLG_S(xy.x, x), e1 = VLG_S(xy.y, y);
     cost_obs[o] = e0 * e0 + e1 * e1;

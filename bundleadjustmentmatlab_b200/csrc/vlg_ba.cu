@@ -343,10 +343,11 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
 {
     const vlg_ba_opts& o = ctx->opt;
     if (m <= 0 || n < 0 || nobs < 0) return fail(ctx, VLG_BA_EINVAL, "bad sizes m=%d n=%d nobs=%lld", m, n, (long long)nobs);
-    if (!K || !a || (n > 0 && !b)) return fail(ctx, VLG_BA_EINVAL, "K, a and b are required");
+    if ((!K && ctx->opt.model != VLG_BA_MODEL_PROJECTIVE) || !a || (n > 0 && !b)) return fail(ctx, VLG_BA_EINVAL, "K, a and b are required");
     if (nobs >= (int64_t)1 << 31) return fail(ctx, VLG_BA_EINVAL, "nobs must be < 2^31 per context");
-    const int na = 6 + o.num_variableK;
-    if (!(o.num_variableK == 0 || o.num_variableK == 1 || o.num_variableK == 4))
+    const bool proj = o.model == VLG_BA_MODEL_PROJECTIVE;
+    const int na = proj ? kNaProjective : 6 + o.num_variableK;
+    if (!proj && !(o.num_variableK == 0 || o.num_variableK == 1 || o.num_variableK == 4))
         return fail(ctx, VLG_BA_EINVAL, "num_variableK must be 0, 1 or 4");
     // validate list order (ascending i + n*j) and ranges
     for (int64_t t = 0; t < nobs; t++) {
@@ -369,7 +370,8 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     ctx->num_vis = (double)nobs;
     const size_t N = (size_t)na * m;
 
-    ctx->h_K.assign(K, K + 4 * (size_t)m);
+    if (K) ctx->h_K.assign(K, K + 4 * (size_t)m);
+    else ctx->h_K.assign(4 * (size_t)m, 0.0);
     ctx->h_a.assign(a, a + N);
     ctx->h_a_new.assign(N, 0.0);
     ctx->h_da.assign(N, 0.0);
@@ -700,7 +702,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     }
     CHK(upload(ctx, ctx->cam_chunk_ptr, cam_chunk_ptr.data(), (size_t)m + 1));
     CHK(upload(ctx, ctx->cam_fixed, fixed.data(), (size_t)m));
-    CHK(upload(ctx, ctx->K4, K, (size_t)4 * m)); CHK(upload(ctx, ctx->a, a, N)); CHK(upload(ctx, ctx->b, b, (size_t)3 * n));
+    CHK(upload(ctx, ctx->K4, ctx->h_K.data(), (size_t)4 * m)); CHK(upload(ctx, ctx->a, a, N)); CHK(upload(ctx, ctx->b, b, (size_t)3 * n));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->have_problem = true;
     ctx->lambda = o.lambda0; ctx->nu = o.nu0; ctx->iter = 1; ctx->iter2 = 0;
@@ -713,6 +715,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
 template <int NA>
 int run_rtab(vlg_ba_ctx* ctx, const std::vector<double>& h_a, const double* d_a, int nmat, std::vector<double>& h_tab, double* d_tab)
 {
+    if (NA == kNaProjective) return VLG_BA_OK;      // no rotation in the projective model
     if (ctx->opt.rtable == VLG_BA_RTABLE_HOST_LIBM) {
         rtab_host(ctx->m, NA, h_a.data(), nmat, h_tab.data());
         CHK(upload(ctx, d_tab, h_tab.data(), (size_t)9 * nmat * ctx->m));

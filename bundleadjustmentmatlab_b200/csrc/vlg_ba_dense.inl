@@ -234,3 +234,51 @@ int vlg_ba_bundle_euclid_sparse(const vlg_ba_opts* opts, int m, int n, const dou
     vlg_ba_destroy(ctx);
     return r;
 }
+
+// bundle_projective.m:1-229 in one call (dense interface, like vlg_ba_bundle_euclid)
+int vlg_ba_bundle_projective(const vlg_ba_opts* opts, int m, int n, const double* Pp, const double* Xp, const double* x,
+                             const double* visible, double* Pp_, double* Xp_, double* error_, int* n_error)
+{
+    vlg_ba_opts o;
+    if (opts) o = *opts; else vlg_ba_opts_default(&o);
+    o.model = VLG_BA_MODEL_PROJECTIVE;
+    if (m <= 0 || n < 0 || !Pp || !Xp || !x) return fail(nullptr, VLG_BA_EINVAL, "bundle_projective: NULL argument");
+    // a(1:12,j) = reshape(Pp(:,:,j),12,1) is the memory layout of Pp itself (bundle_projective.m:69-72)
+    std::vector<double> b(3 * (size_t)n), X(2 * (size_t)n * m), vis((size_t)n * m);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) b[3 * (size_t)i + k] = Xp[4 * (size_t)i + k];                 // :75
+    for (size_t c = 0; c < (size_t)n * m; c++) {                                                    // :38, :61, :78
+        X[2 * c] = x[3 * c]; X[2 * c + 1] = x[3 * c + 1];
+        vis[c] = visible ? (visible[c] != 0.0 ? 1.0 : 0.0) : ((x[3 * c] != 0.0 || x[3 * c + 1] != 0.0) ? 1.0 : 0.0);
+    }
+    vlg_ba_ctx* ctx = nullptr;
+    int r = vlg_ba_create(&o, &ctx);
+    if (r != VLG_BA_OK) return r;
+    r = vlg_ba_set_problem_dense(ctx, m, n, nullptr, Pp, b.data(), X.data(), vis.data(), nullptr);
+    if (r == VLG_BA_OK) {
+        r = vlg_ba_lm_reset(ctx, nullptr, nullptr);
+        while (r == VLG_BA_OK && vlg_ba_lm_continue(ctx)) {
+            const int it = ctx->iter;
+            vlg_ba_trial_info info;
+            r = do_trial(ctx, &info);
+            if (r == VLG_BA_OK && info.accepted && o.verbose)
+                printf("iter %d: error= %.5g -> %.5g\n", it, ctx->err_hist[it - 1], ctx->err_hist[it]);
+        }
+    }
+    if (r == VLG_BA_OK) {
+        std::vector<double> bb(3 * (size_t)n);
+        r = vlg_ba_get_state(ctx, Pp_, bb.data(), nullptr, nullptr, nullptr, nullptr);      // Pp_ = reshape(a, 3, 4, m): :213-217
+        if (r == VLG_BA_OK && Xp_)
+            for (int i = 0; i < n; i++) {                                                   // Xp_ = [b; Xp(4,:)]: :219
+                for (int k = 0; k < 3; k++) Xp_[4 * (size_t)i + k] = bb[3 * (size_t)i + k];
+                Xp_[4 * (size_t)i + 3] = Xp[4 * (size_t)i + 3];
+            }
+        const int ne = ctx->err_hist.empty() ? 0 : ctx->iter;
+        if (error_) for (int k = 0; k < ne; k++) error_[k] = ctx->err_hist[k];
+        if (n_error) *n_error = ne;
+    }
+    if (r != VLG_BA_OK) snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err);
+    vlg_ba_destroy(ctx);
+    return r;
+}
+

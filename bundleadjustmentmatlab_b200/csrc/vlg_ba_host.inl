@@ -196,7 +196,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CU(cudaGetLastError());
             return VLG_BA_OK;
         };
-        const bool defl = ctx->opt.pcg_deflate && ctx->coop_grid > 0 && !ctx->opt.fix_structure;
+        const bool defl = ctx->opt.pcg_deflate && ctx->coop_grid > 0 && !ctx->opt.fix_structure && NA != kNaProjective;   // the gauge vectors are the Euclidean model's
         if (defl) {
             k_gauge_vectors<NA><<<cdiv(m, 128), 128, 0, ctx->stream>>>(m, ctx->a, ctx->rtab, ctx->cam_fixed, ctx->cam_chunk_ptr, ctx->Zd);
             ctx->launches++;
@@ -320,7 +320,7 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
 }
 
 #define DISPATCH_NA(ctx, call)                                                   \
-    ((ctx)->na == 6 ? call<6> : (ctx)->na == 7 ? call<7> : call<10>)
+    ((ctx)->na == 6 ? call<6> : (ctx)->na == 7 ? call<7> : (ctx)->na == 10 ? call<10> : call<12>)
 
 int do_stage1(vlg_ba_ctx* ctx)
 {
@@ -392,9 +392,13 @@ int do_trial(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
         std::swap(ctx->a, ctx->a_new);
         std::swap(ctx->b, ctx->b_new);
         ctx->h_a.swap(ctx->h_a_new);
-        const double f = 1 - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
-        ctx->lambda = lambda * std::max(1.0 / 3.0, f);                      // :227
-        ctx->nu = 2.0;
+        if (ctx->opt.model == VLG_BA_MODEL_PROJECTIVE) {
+            ctx->lambda = lambda / 10;                                      // bundle_projective.m:194
+        } else {
+            const double f = 1 - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
+            ctx->lambda = lambda * std::max(1.0 / 3.0, f);                  // bundle_euclid.m:227
+            ctx->nu = 2.0;
+        }
         if ((int)ctx->err_hist.size() < ctx->iter + 1) ctx->err_hist.resize((size_t)ctx->iter + 1, 0.0);
         ctx->err_hist[ctx->iter - 1] = old_cost / ctx->num_vis;             // :219-220,229-231
         ctx->err_hist[ctx->iter] = new_cost / ctx->num_vis;
@@ -402,8 +406,12 @@ int do_trial(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
         ctx->iter2 = 0;
         ctx->s1_valid = false;
     } else {
-        ctx->lambda = lambda * ctx->nu;                                     // :238-240
-        ctx->nu = 2 * ctx->nu;
+        if (ctx->opt.model == VLG_BA_MODEL_PROJECTIVE) {
+            ctx->lambda = lambda * 10;                                      // bundle_projective.m:204
+        } else {
+            ctx->lambda = lambda * ctx->nu;                                 // bundle_euclid.m:238-240
+            ctx->nu = 2 * ctx->nu;
+        }
         ctx->iter2 += 1;
     }
     ctx->s2_valid = false; ctx->s3_valid = false;
@@ -428,6 +436,7 @@ void vlg_ba_opts_default(vlg_ba_opts* o)
     o->rtable = VLG_BA_RTABLE_HOST_LIBM; o->order = VLG_BA_ORDER_CHUNKED; o->device = -1; o->verbose = 0;
     o->pcg_deflate = 1;
     o->pcg_cluster = 1;
+    o->model = VLG_BA_MODEL_EUCLID;
 }
 
 const char* vlg_ba_version(void) { return "vlgba 0.1 (sm_100a, fp64)"; }

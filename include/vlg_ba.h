@@ -46,6 +46,10 @@ extern "C" {
  * AUTO: CHOL when m <= chol_max_cams, else PCG_EXPLICIT when 6 (6m)^2 < 304 nobs and S fits in 8 GB, else PCG. */
 enum { VLG_BA_SOLVER_AUTO = 0, VLG_BA_SOLVER_CHOL = 1, VLG_BA_SOLVER_PCG = 2, VLG_BA_SOLVER_PCG_EXPLICIT = 3 };
 enum { VLG_BA_RTABLE_HOST_LIBM = 0, VLG_BA_RTABLE_DEVICE = 1 };
+/* EUCLID: bundle_euclid.m (a = [w; Te; K-part], num_a = 6 + num_variableK).  PROJECTIVE: bundle_projective.m
+ * (a = vec(P), P 3x4, num_a = 12, no K, no rotation table; lambda /10 on accept, x10 on reject,
+ * bundle_projective.m:187-205; K and num_variableK are ignored). */
+enum { VLG_BA_MODEL_EUCLID = 0, VLG_BA_MODEL_PROJECTIVE = 1 };
 enum { VLG_BA_ORDER_CHUNKED = 0, VLG_BA_ORDER_REFERENCE = 1 };
 
 /* Options.  Defaults (vlg_ba_opts_default) are the constants hard-coded in
@@ -70,8 +74,9 @@ typedef struct vlg_ba_opts {
     int    device;            /* CUDA device ordinal; -1 = current device */
     int    verbose;           /* 'verbose': print "iter k: error= a -> b" (bundle_euclid.m:221-224) */
     int    pcg_deflate;       /* 1 (default): deflate the 4 gauge directions (world translation, scale) in PCG */
-    int    pcg_cluster;       /* 1 (default): PCG_EXPLICIT preconditions with the inverses of 128/num_a-camera diagonal blocks of S
+    int    pcg_cluster;       /* 1 (default): PCG preconditions with the inverses of 128/num_a-camera diagonal blocks of S
                                  (cluster-Jacobi) instead of per-camera blocks */
+    int    model;             /* VLG_BA_MODEL_* (default EUCLID) */
 } vlg_ba_opts;
 
 typedef struct vlg_ba_ctx vlg_ba_ctx;
@@ -216,6 +221,13 @@ int  vlg_ba_bundle_euclid_sparse(const vlg_ba_opts *opts, int m, int n,
                                  int64_t nobs, const double *obs_xy, const int32_t *obs_pt, const int32_t *obs_cam,
                                  const double *pivot /*m or NULL*/,
                                  double *K_, double *Te_, double *w_, double *Xe_, double *error_, int *n_error);
+
+/* [Pp_ Xp_ error_] = bundle_projective(Pp, Xp, x, ...)  (toolbox/bundle/bundle_projective.m:1-229, called from
+ * mview_reconstruction.m:148 and multi_view.m:190): Pp 3x4xm, Xp 4xn, x 3xnxm, visible nxm or NULL (derived
+ * from x, bundle_projective.m:38); opts->fix_structure / fix_motion / verbose as the option strings. */
+int  vlg_ba_bundle_projective(const vlg_ba_opts *opts, int m, int n, const double *Pp, const double *Xp,
+                              const double *x, const double *visible,
+                              double *Pp_, double *Xp_, double *error_, int *n_error);
 
 /* Introspection for tests and benches. */
 int  vlg_ba_get_schur_structure(vlg_ba_ctx *ctx, int64_t *n_blocks, int32_t *blk_j, int32_t *blk_k);

@@ -457,6 +457,142 @@ def bundle_euclid(K, Te, w, Xe, x, *opts, backend="sparse", record=True, max_ite
 
 
 # ----------------------------------------------------------------------------------
+# projective BA: bundle_projective.m:1-229 over mex_bundle_proj_{1,2,3} (reference build only)
+# ----------------------------------------------------------------------------------
+def stage1_ref_proj(a, b, X, visible):
+    """mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible) -> 9 dense outputs (Fortran order)."""
+    lib = ref_lib()
+    na, m = a.shape
+    assert na == 12
+    n = b.shape[1]
+    o = dict(X_hat=np.zeros((2, n, m), order="F"), A=np.zeros((2, na, n, m), order="F"),
+             B=np.zeros((2, 3, n, m), order="F"), e=np.zeros((2, n, m), order="F"),
+             U=np.zeros((na, na, m), order="F"), V=np.zeros((3, 3, n), order="F"),
+             W=np.zeros((na, 3, n, m), order="F"), eA=np.zeros((na, m), order="F"),
+             eB=np.zeros((3, n), order="F"))
+    a, b, X, visible = _F(a), _F(b), _F(X), _F(visible)
+    lib.vlgref_pstage1(C.c_int(m), C.c_int(n), _d(a), _d(b), _d(X), _d(visible),
+                       _d(o["X_hat"]), _d(o["A"]), _d(o["B"]), _d(o["e"]), _d(o["U"]), _d(o["V"]),
+                       _d(o["W"]), _d(o["eA"]), _d(o["eB"]))
+    return o
+
+
+def stage2_ref_proj(Y, W, U_, eA, eB):
+    lib = ref_lib()
+    na, m = eA.shape
+    n = eB.shape[1]
+    S = np.zeros((na * m, na * m), order="F")
+    e_ = np.zeros(na * m)
+    lib.vlgref_pstage2(C.c_int(m), C.c_int(n), _d(_F(Y)), _d(_F(W)), _d(_F(U_)), _d(_F(eA)), _d(_F(eB)), _d(S), _d(e_))
+    return S, e_
+
+
+def stage3_ref_proj(W, da, eB, Vinv, a, b, X, visible):
+    lib = ref_lib()
+    na, m = a.shape
+    n = b.shape[1]
+    db = np.zeros((3, n), order="F"); a_new = np.zeros((na, m), order="F")
+    b_new = np.zeros((3, n), order="F"); X_hat = np.zeros((2, n, m), order="F")
+    lib.vlgref_pstage3(C.c_int(m), C.c_int(n), _d(_F(W)), _d(_f64(da)), _d(_F(eB)), _d(_F(Vinv)),
+                       _d(_F(a)), _d(_F(b)), _d(_F(X)), _d(_F(visible)), _d(db), _d(a_new), _d(b_new), _d(X_hat))
+    return db, a_new, b_new, X_hat
+
+
+def lm_trial_proj(a, b, X, vis, lam, fix_structure=False, fix_motion=False):
+    """One trip of the loop body of bundle_projective.m:116-178."""
+    na, m = a.shape
+    s1 = stage1_ref_proj(a, b, X, vis)
+    U, V, W, eA, eB, e = s1["U"], s1["V"], s1["W"], s1["eA"], s1["eB"], s1["e"]
+    if fix_structure:
+        V[...] = 0; W[...] = 0; eB[...] = 0
+    if fix_motion:
+        U[...] = 0; W[...] = 0; eA[...] = 0
+    U_ = U.copy(order="F"); V_ = V.copy(order="F")
+    for k in range(na):
+        U_[k, k, :] = (1 + lam) * U[k, k, :]
+    for k in range(3):
+        V_[k, k, :] = (1 + lam) * V[k, k, :]
+    Vinv = np.asfortranarray(np.transpose(pinv3_batch(np.ascontiguousarray(np.transpose(V_, (2, 0, 1)))), (1, 2, 0)))
+    Y = np.zeros_like(W)
+    for c in range(3):
+        Y[:, c] = (W[:, 0] * Vinv[0, c][None, :, None] + W[:, 1] * Vinv[1, c][None, :, None]
+                   + W[:, 2] * Vinv[2, c][None, :, None])
+    S, e_ = stage2_ref_proj(Y, W, U_, eA, eB)
+    da = pinv_matlab(S) @ e_
+    db, a_new, b_new, X_hat_new = stage3_ref_proj(W, da, eB, Vinv, a, b, X, vis)
+    e_new = X - X_hat_new
+    old = float(np.dot(e.reshape(-1, order="F"), e.reshape(-1, order="F")))
+    new = float(np.dot(e_new.reshape(-1, order="F"), e_new.reshape(-1, order="F")))
+    blocks = dict(U=np.transpose(U, (2, 1, 0)).copy(), V=np.transpose(V, (2, 1, 0)).copy(),
+                  eA=eA.T.copy(), eB=eB.T.copy(), Vinv=np.transpose(Vinv, (2, 1, 0)).copy(),
+                  S=np.array(S), e_=e_, W_dense=W, s1=s1)
+    return dict(old=old, new=new, da=np.array(da), db=np.array(db), a_new=np.array(a_new), b_new=np.array(b_new),
+                blocks=blocks)
+
+
+@dataclass
+class ProjResult:
+    Pp_: np.ndarray
+    Xp_: np.ndarray
+    error_: np.ndarray
+    trials: list
+
+
+def bundle_projective(Pp, Xp, x, *opts, record=True, max_iter=20, max_iter2=10):
+    """[Pp_ Xp_ error_] = bundle_projective(Pp, Xp, x, ...)  (bundle_projective.m:1-229).
+    Pp (3,4,m), Xp (4,n), x (3,n,m); options 'fix_structure', 'fix_motion', 'visibility', vis, 'verbose'."""
+    Pp = np.asarray(Pp, dtype=np.float64); Xp = np.asarray(Xp, dtype=np.float64); x = np.asarray(x, dtype=np.float64)
+    m = Pp.shape[2]; n = x.shape[1]
+    fix_structure = fix_motion = False
+    visible = ((x[0] != 0) | (x[1] != 0)).reshape(n, m)                     # :38
+    opts = list(opts); k = 0
+    while k < len(opts):
+        key = str(opts[k]).lower()
+        if key == "fix_structure": fix_structure = True
+        elif key == "fix_motion": fix_motion = True
+        elif key == "visibility": visible = np.asarray(opts[k + 1]); k += 1
+        k += 1
+    visible = np.asfortranarray(np.asarray(visible, dtype=np.float64).reshape(n, m))
+    num_vis = float(visible.sum())
+    a = np.asfortranarray(Pp.reshape(12, m, order="F"))                      # :69-72
+    b = Xp[0:3].copy()
+    X = np.asfortranarray(x[0:2])
+    lam = 0.001                                                              # :87
+    it, it2 = 1, 0
+    error_ = []
+    trials = []
+
+    def cont():
+        if not (it < max_iter and it2 < max_iter2):
+            return False
+        if it < 3:
+            return True
+        return error_[it - 1] > 1e-20 and error_[it - 2] - error_[it - 1] > 1e-3 * error_[it - 2]
+
+    while cont():
+        t = lm_trial_proj(a, b, X, visible, lam, fix_structure, fix_motion)
+        old_error, new_error = t["old"] / num_vis, t["new"] / num_vis      # :181-182
+        accept = new_error < old_error                                       # :187
+        if record:
+            trials.append(Trial(a.copy(), b.copy(), lam, 0.0, t["old"], t["new"], 0.0, bool(accept), t["da"], t["db"],
+                                t["a_new"], t["b_new"], 0.0))
+        if accept:
+            a = np.array(t["a_new"]); b = np.array(t["b_new"])
+            lam = lam / 10                                                   # :194
+            while len(error_) < it + 1:
+                error_.append(0.0)
+            error_[it - 1] = old_error
+            it += 1
+            error_[it - 1] = new_error
+            it2 = 0
+        else:
+            lam = lam * 10                                                   # :204
+            it2 += 1
+    Pp_ = np.asarray(a).reshape(3, 4, m, order="F").copy()
+    return ProjResult(Pp_, np.vstack([b, Xp[3:4]]), np.array(error_), trials)
+
+
+# ----------------------------------------------------------------------------------
 # CPU arm for the large configurations (port, PCG solve) -- see oracle_sparse.c
 # ----------------------------------------------------------------------------------
 def trial_step_pcg(K, a, b, obs: ObsList, lam, pcg_rtol=1e-8, pcg_max_iter=500):

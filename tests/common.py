@@ -10,7 +10,13 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Euclidean goldens (bundle_euclid.m over mex_bundle_{1,2,3}; tests/golden/make_golden.py)."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "euclid_*.npz")))
+
+
+def proj_golden_names():
+    """Projective goldens (bundle_projective.m over mex_bundle_proj_{1,2,3}; tests/golden/make_golden_proj.py)."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "proj_*.npz")))
 
 
 def load_golden(name):
