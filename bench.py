@@ -295,9 +295,11 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
-        ha, hb, hxy = pin(a0.shape), pin(b0.shape), pin(P.obs_xy.shape)
-        ha_new, hb_new = pin(a0.shape), pin(b0.shape)
-        ha[:] = a0; hb[:] = b0; hxy[:] = P.obs_xy
+        hxy = pin(P.obs_xy.shape)
+        # current and candidate parameters live in two pinned buffer pairs that swap roles on an accepted step
+        # (MATLAB's `a = a_new; b = b_new` is a reference rebind, bundle_euclid.m:225-226, not a 24 MB copy)
+        buf = {"cur": (pin(a0.shape), pin(b0.shape)), "new": (pin(a0.shape), pin(b0.shape))}
+        buf["cur"][0][:] = a0; buf["cur"][1][:] = b0; hxy[:] = P.obs_xy
         st = {"lam": 1e-3, "nu": 2.0, "it": 1, "it2": 0, "err": []}
         nvis = nobs_total
 
@@ -307,11 +309,11 @@ def run_ours(args):
             go = st["it"] < 20 and st["it2"] < 10 and (st["it"] < 3 or (
                 e[st["it"] - 1] > 1e-20 and e[st["it"] - 2] - e[st["it"] - 1] > 1e-3 * e[st["it"] - 2]))
             if not go:
-                ha[:] = a0; hb[:] = b0
+                buf["cur"][0][:] = a0; buf["cur"][1][:] = b0
                 st.update(lam=1e-3, nu=2.0, it=1, it2=0, err=[])
-            info = ctx.trial_step_host(ha, hb, hxy, st["lam"], ha_new, hb_new)
+            info = ctx.trial_step_host(buf["cur"][0], buf["cur"][1], hxy, st["lam"], buf["new"][0], buf["new"][1])
             if info["accepted"]:
-                ha[:] = ha_new; hb[:] = hb_new
+                buf["cur"], buf["new"] = buf["new"], buf["cur"]
                 if proj:
                     st["lam"] /= 10                      # bundle_projective.m:194
                 else:
@@ -340,8 +342,8 @@ def run_ours(args):
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = (ha.nbytes + hb.nbytes + hxy.nbytes) * 1
-        d2h = ha_new.nbytes + hb_new.nbytes + 64
+        h2d = (buf["cur"][0].nbytes + buf["cur"][1].nbytes + hxy.nbytes) * 1
+        d2h = buf["new"][0].nbytes + buf["new"][1].nbytes + 64
         e2e = {"value": nobs_total * args.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / args.steps}
 

@@ -432,7 +432,7 @@ void vlg_ba_opts_default(vlg_ba_opts* o)
     o->num_variableK = 4;
     o->lambda0 = 0.001; o->nu0 = 2.0; o->max_iter = 20; o->max_iter2 = 10; o->rel_tol = 1e-3; o->abs_tol = 1e-20;
     o->backsub_all_rows = 0;
-    o->solver = VLG_BA_SOLVER_AUTO; o->chol_max_cams = 300; o->pcg_rtol = 1e-8; o->pcg_max_iter = 1000;
+    o->solver = VLG_BA_SOLVER_AUTO; o->chol_max_cams = 600; o->pcg_rtol = 1e-8; o->pcg_max_iter = 1000;
     o->rtable = VLG_BA_RTABLE_HOST_LIBM; o->order = VLG_BA_ORDER_CHUNKED; o->device = -1; o->verbose = 0;
     o->pcg_deflate = 1;
     o->pcg_cluster = 1;

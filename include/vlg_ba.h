@@ -66,7 +66,7 @@ typedef struct vlg_ba_opts {
     double abs_tol;           /* 1e-20  bundle_euclid.m:123 */
     int    backsub_all_rows;  /* 0 = reference behaviour: only 6 camera rows enter db (mex_bundle_3_db_new.c:113-120) */
     int    solver;            /* VLG_BA_SOLVER_*: dense Cholesky of S, or block-Jacobi PCG on the implicit S */
-    int    chol_max_cams;     /* AUTO picks Cholesky when m <= this (default 300) */
+    int    chol_max_cams;     /* AUTO picks Cholesky when m <= this (default 600: measured crossover, profiles/crossover_chol_pcg_r01.txt) */
     double pcg_rtol;          /* relative residual stop for PCG (default 1e-8: one-step cost within ~1e-12 of the exact solve) */
     int    pcg_max_iter;      /* default 1000 */
     int    rtable;            /* VLG_BA_RTABLE_*: who evaluates vl_rodrigues' sin/cos (host libm = bit parity with the CPU reference) */
