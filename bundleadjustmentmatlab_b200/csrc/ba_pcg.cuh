@@ -468,7 +468,8 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
                   double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
                   PcgScalars* __restrict__ sc, double* __restrict__ blkpart /* 11 * gridDim.x */, double rtol,
                   const double* __restrict__ Z /* [kDefl][N] or NULL */, const double* __restrict__ SZ,
-                  const DeflScalars* __restrict__ ds, const double* __restrict__ McL /* cluster inverses or NULL */)
+                  const DeflScalars* __restrict__ ds, const double* __restrict__ McL /* cluster inverses or NULL */,
+                  int mcl_in_smem /* launched with room for the CTA's cluster inverse in dynamic shared memory */)
 {
     // one thread per reduced unknown; a CTA owns kCams whole cameras so that the NA x NA block
     // products (U* p, M^-1 r) only need the CTA's own slice of p and r (shared memory)
@@ -476,8 +477,23 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     constexpr int kCams = 128 / NA;
     __shared__ double shd[4 * ND];
     __shared__ double pv[128], rv[128];
+    __shared__ uint64_t mbar;
+    extern __shared__ __align__(128) unsigned char smraw[];   // the CTA's cluster inverse (NC columns x 128), when McL is given
+    double* Ms = reinterpret_cast<double*>(smraw);
     cg::grid_group grid = cg::this_grid();
     if (sc->done) return;                         // uniform: sc is only written after the last grid sync
+    if (McL && mcl_in_smem) {
+        // the 126 x 126 preconditioner block of this CTA is needed only after the first grid sync: pull it
+        // into shared memory now with one TMA bulk copy (129 KB, contiguous), so that z = M^-1 r reads shared
+        // memory instead of 126 dependent-latency L2 loads per thread
+        if (threadIdx.x == 0) {
+            mbar_init(&mbar, 1);
+            constexpr uint32_t bytes = (uint32_t)(kCams * NA) * 128u * 8u;
+            mbar_expect_tx(&mbar, bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(Ms)), "l"(McL + (size_t)blockIdx.x * 128 * 128), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+        }
+    }
     const double rz = sc->rz, r0n2 = sc->r0n2;
     const int nb = gridDim.x;
     const size_t N = (size_t)NA * m;
@@ -564,18 +580,21 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     if (act) {
         if (McL) {
             // cluster block of this CTA (column-major, ld 128: coalesced over threads), 4 independent chains
-            const double* M = McL + (size_t)blockIdx.x * 128 * 128 + threadIdx.x;
+            // column-major, ld 128: consecutive threads read consecutive words; from shared memory when it fits
+            // (one CTA per SM, <= 148 clusters), else from L2
+            if (mcl_in_smem) mbar_wait(&mbar, 0);
+            const double* M = mcl_in_smem ? Ms + threadIdx.x : McL + (size_t)blockIdx.x * 128 * 128 + threadIdx.x;
             double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
             constexpr int NC = kCams * NA;
 #pragma unroll 4
             for (int c = 0; c + 3 < NC; c += 4) {
-                z0 += __ldg(M + 128 * c) * rv[c];
-                z1 += __ldg(M + 128 * (c + 1)) * rv[c + 1];
-                z2 += __ldg(M + 128 * (c + 2)) * rv[c + 2];
-                z3 += __ldg(M + 128 * (c + 3)) * rv[c + 3];
+                z0 += M[128 * c] * rv[c];
+                z1 += M[128 * (c + 1)] * rv[c + 1];
+                z2 += M[128 * (c + 2)] * rv[c + 2];
+                z3 += M[128 * (c + 3)] * rv[c + 3];
             }
 #pragma unroll
-            for (int c = NC - NC % 4; c < NC; c++) z0 += __ldg(M + 128 * c) * rv[c];
+            for (int c = NC - NC % 4; c < NC; c++) z0 += M[128 * c] * rv[c];
             zt = (z0 + z1) + (z2 + z3);
         } else {
 #pragma unroll

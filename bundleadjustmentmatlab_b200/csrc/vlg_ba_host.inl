@@ -116,6 +116,10 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CHK(assemble_S<NA>(ctx, 0, ctx->S));
         }
         const double* McL = nullptr;
+        // the update kernel keeps its cluster inverse in shared memory when every cluster gets an SM of its own
+        const size_t upd_smem = sizeof(double) * (size_t)Cluster<NA>::NC * 128;
+        int mcl_in_smem = ctx->McL && ctx->coop_grid <= ctx->nsm ? 1 : 0;
+        if (mcl_in_smem) CU(cudaFuncSetAttribute(k_pcg_update_coop<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
         if (ctx->McL) {
             // cluster-Jacobi: diagonal blocks of S over the update kernel's CTAs, summed over ranks, inverted
             TimedScope ts(ctx, T_PRECOND);
@@ -234,8 +238,9 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                         const double* sz = defl ? ctx->SZd : nullptr;
                         const DeflScalars* dsc = ctx->defl_sc;
                         const double* mcl = McL;
-                        void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt, &zz, &sz, &dsc, &mcl};
-                        CU(cudaLaunchCooperativeKernel((void*)k_pcg_update_coop<NA>, dim3(ctx->coop_grid), dim3(128), args, 0, ctx->stream));
+                        void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt, &zz, &sz, &dsc, &mcl, &mcl_in_smem};
+                        CU(cudaLaunchCooperativeKernel((void*)k_pcg_update_coop<NA>, dim3(ctx->coop_grid), dim3(128), args,
+                                                       mcl_in_smem ? upd_smem : 0, ctx->stream));
                     } else {
                         k_pcg_update<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Ud, ctx->Minv, ctx->wq, ctx->da, ctx->pr, ctx->pz, ctx->pp,
                                                                       ctx->pq, ctx->pcg_sc, rtol);

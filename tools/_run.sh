@@ -1,1 +1,5 @@
-timeout 900 python tools/crossover.py 150 257 400 600 900 1300 2>&1 | tail -12
+set -x
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
+python bench.py --config venice --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_venice_r01x.json 2> gpurun_out/bench_x.err
+python -c "
+import json;d=json.load(open('gpurun_out/bench_venice_r01x.json'));print(d['ms_per_step'],d['lm_iters_per_sec'],d['e2e']['ms_per_step'],d['cost_first_last'],d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_x.err
