@@ -14,6 +14,7 @@
 // and chunks), so results are bit-reproducible run to run.
 #pragma once
 #include "ba_kernels.cuh"
+#include "ba_chol.cuh"      // grid_barrier, fast_rcp_pos
 #include <cooperative_groups.h>
 
 namespace vlgba {
@@ -539,10 +540,17 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     }
     grid.sync();
     // every warp folds the per-block partials the same way (strided by lane, xor tree)
-    for (int k = 0; k < nd; k++) {
-        double v = 0.0;
-        for (int b = lane; b < nb; b += 32) v += __ldcg(blkpart + (size_t)k * nb + b);
-        dots[k] = warp_sum(v);
+    {
+        double pv_[ND];                            // every partial load in flight before the first use
+#pragma unroll
+        for (int k = 0; k < ND; k++) {
+            double v = 0.0;
+            if (k < nd)
+                for (int b = lane; b < nb; b += 32) v += __ldcg(blkpart + (size_t)k * nb + b);
+            pv_[k] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < ND; k++) dots[k] = k < nd ? warp_sum(pv_[k]) : 0.0;
     }
     // deflated operator: w <- P S p = S p - SZ Einv Z' S p ;  p'(P S p) = p'Sp - (SZ'p)' Einv (Z'Sp)
     double y[kDefl];
@@ -978,7 +986,7 @@ namespace vlgba {
 constexpr int kSymvCols = 32;
 constexpr int kSymvRows = 256;    // rows per tile == threads per CTA
 constexpr int kSymvStages = 3;
-constexpr int kSymvSegRows = 1024;   // rows per work item (strip segment): granularity of the load balance
+constexpr int kSymvSegRows = 512;    // rows per work item (strip segment): granularity of the load balance
 
 // tile descriptor: x = strip, y = first row, z = rows | first-of-item << 16 | last-of-item << 17, w = segment
 struct SymvTile { int strip, r0, rows_flags, seg; };
@@ -1014,87 +1022,102 @@ __device__ __forceinline__ void consumer_sync()      // named barrier 1: the 256
 
 // warps 0..7 consume (thread t = row t of the tile), warp 8 produces: lane c issues the bulk copy of
 // column c, so a whole tile is requested by one warp instruction and the producer runs ahead of the
-// consumers by kSymvStages tiles (full/empty mbarrier pairs, no CTA-wide barrier per tile)
-__global__ void __launch_bounds__(kSymvRows + 32, 1)
-k_symv_lower(int Np, int ld, int N, const double* __restrict__ S, const double* __restrict__ x,
-             const int* __restrict__ tile_ptr /* [gridDim.x + 1] */, const int4* __restrict__ tiles,
-             const int* __restrict__ done, double* __restrict__ rowpart /* [Np/32][Np] */,
-             double* __restrict__ colpart /* [nseg][Np] */)
+// consumers by kSymvStages tiles (full/empty mbarrier pairs, no CTA-wide barrier per tile).
+// Both halves are device functions so that the persistent PCG kernel below runs the same code;
+// `kbase` is the number of tiles this CTA has already pushed through the ring (the mbarrier phases
+// go on across calls), `L2X` makes x a coherent L2 read (x written by other CTAs of the same kernel).
+struct SymvSmem {
+    double* st;        // kSymvStages x 32 x 256
+    double* cred;      // 8 x 32
+    double* xs;        // 32
+    uint64_t* full;    // kSymvStages
+    uint64_t* empty;   // kSymvStages
+};
+
+__device__ __forceinline__ SymvSmem symv_smem(unsigned char* smraw)
 {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    double* st = reinterpret_cast<double*>(smraw);                                   // kSymvStages x 32 x 256
-    double* cred = st + (size_t)kSymvStages * kSymvCols * kSymvRows;                 // 8 x 32
-    double* xs = cred + (kSymvRows / 32) * kSymvCols;                                // 32
-    uint64_t* full = reinterpret_cast<uint64_t*>(xs + kSymvCols);                    // kSymvStages
-    uint64_t* empty = full + kSymvStages;                                            // kSymvStages
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (done && *done) return;
-    const int t0 = tile_ptr[blockIdx.x], nt = tile_ptr[blockIdx.x + 1] - t0;
-    if (nt <= 0) return;
-    if (tid == 0)
-        for (int s = 0; s < kSymvStages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, kSymvRows / 32); }
-    __syncthreads();
-    if (warp == kSymvRows / 32) {
-        // ---- producer warp
-        const uint64_t policy = l2_evict_first_policy();
-        for (int k = 0; k < nt; k++) {
-            const int slot = k % kSymvStages;
-            const int4 d = __ldg(tiles + t0 + k);
-            const uint32_t bytes = (uint32_t)(d.z & 0xffff) * 8u;
-            if (k >= kSymvStages) mbar_wait(empty + slot, (uint32_t)((k / kSymvStages - 1) & 1));
-            if (lane == 0) mbar_expect_tx(full + slot, bytes * kSymvCols);
-            __syncwarp();
-            tma_load_1d_pol(st + ((size_t)slot * kSymvCols + lane) * kSymvRows,
-                            S + (size_t)ld * (kSymvCols * d.x + lane) + d.y, bytes, full + slot, policy);
-        }
-        return;
+    SymvSmem m;
+    m.st = reinterpret_cast<double*>(smraw);
+    m.cred = m.st + (size_t)kSymvStages * kSymvCols * kSymvRows;
+    m.xs = m.cred + (kSymvRows / 32) * kSymvCols;
+    m.full = reinterpret_cast<uint64_t*>(m.xs + kSymvCols);
+    m.empty = m.full + kSymvStages;
+    return m;
+}
+
+constexpr size_t kSymvSmemBytes =
+    sizeof(double) * ((size_t)kSymvStages * kSymvCols * kSymvRows + (kSymvRows / 32) * kSymvCols + kSymvCols) + 16 * kSymvStages + 16;
+
+__device__ __forceinline__ void symv_producer(const SymvSmem& sm, int ld, const double* __restrict__ S,
+                                              const int4* __restrict__ tiles, int t0, int nt, int kbase, int lane)
+{
+    const uint64_t policy = l2_evict_first_policy();
+    for (int k = 0; k < nt; k++) {
+        const int g = kbase + k, slot = g % kSymvStages;
+        const int4 d = __ldg(tiles + t0 + k);
+        const uint32_t bytes = (uint32_t)(d.z & 0xffff) * 8u;
+        if (g >= kSymvStages) mbar_wait(sm.empty + slot, (uint32_t)((g / kSymvStages - 1) & 1));
+        if (lane == 0) mbar_expect_tx(sm.full + slot, bytes * kSymvCols);
+        __syncwarp();
+        tma_load_1d_pol(sm.st + ((size_t)slot * kSymvCols + lane) * kSymvRows,
+                        S + (size_t)ld * (kSymvCols * d.x + lane) + d.y, bytes, sm.full + slot, policy);
     }
-    // ---- consumer warps
+}
+
+template <bool L2X>
+__device__ __forceinline__ double symv_ldx(const double* x) { return L2X ? __ldcg(x) : __ldg(x); }
+
+template <bool L2X>
+__device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int Np, int N, const double* __restrict__ x,
+                                              const int4* __restrict__ tiles, int t0, int nt, int kbase,
+                                              double* __restrict__ rowpart, double* __restrict__ colpart)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double colacc[kSymvCols];
 #pragma unroll
     for (int c = 0; c < kSymvCols; c++) colacc[c] = 0.0;
     // x of this thread's row, requested one tile ahead
     int4 dn = __ldg(tiles + t0);
     double xr_next = 0.0;
-    { const int r = dn.y + tid; if (tid < (dn.z & 0xffff) && r < N) xr_next = __ldg(x + r); }
+    { const int r = dn.y + tid; if (tid < (dn.z & 0xffff) && r < N) xr_next = symv_ldx<L2X>(x + r); }
     for (int k = 0; k < nt; k++) {
-        const int slot = k % kSymvStages;
+        const int g = kbase + k, slot = g % kSymvStages;
         const int4 d = dn;
         const int rows = d.z & 0xffff, c0 = kSymvCols * d.x, r = d.y + tid;
         double xr = xr_next;
         if (k + 1 < nt) {
             dn = __ldg(tiles + t0 + k + 1);
             const int rn = dn.y + tid;
-            xr_next = (tid < (dn.z & 0xffff) && rn < N) ? __ldg(x + rn) : 0.0;
+            xr_next = (tid < (dn.z & 0xffff) && rn < N) ? symv_ldx<L2X>(x + rn) : 0.0;
         }
         if (d.z & (1 << 16)) {                      // first tile of a work item: this strip's x
-            if (tid < kSymvCols) xs[tid] = (c0 + tid < N) ? __ldg(x + c0 + tid) : 0.0;
+            if (tid < kSymvCols) sm.xs[tid] = (c0 + tid < N) ? symv_ldx<L2X>(x + c0 + tid) : 0.0;
             consumer_sync();
         }
-        mbar_wait(full + slot, (uint32_t)((k / kSymvStages) & 1));
+        mbar_wait(sm.full + slot, (uint32_t)((g / kSymvStages) & 1));
         double ra = 0.0;
         if (tid < rows) {
             // the diagonal 32 x 32 block is stored in full: whole-row dot product there, no mirrored part
             if (r < c0 + kSymvCols) xr = 0.0;
-            const double* a = st + (size_t)slot * kSymvCols * kSymvRows + tid;
+            const double* a = sm.st + (size_t)slot * kSymvCols * kSymvRows + tid;
 #pragma unroll
             for (int c = 0; c < kSymvCols; c++) {
                 const double v = a[c * kSymvRows];
-                ra += v * xs[c];
+                ra += v * sm.xs[c];
                 colacc[c] += v * xr;
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + slot);   // this warp is done with the slot
+        if (lane == 0) mbar_arrive(sm.empty + slot);   // this warp is done with the slot
         if (tid < rows) rowpart[(size_t)d.x * Np + r] = ra;
         if (d.z & (1 << 17)) {                      // last tile of the work item: column sums out
             const double tot = warp_reduce_32(colacc, lane);
-            cred[warp * kSymvCols + lane] = tot;
+            sm.cred[warp * kSymvCols + lane] = tot;
             consumer_sync();
             if (tid < kSymvCols) {
                 double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < kSymvRows / 32; w++) s += cred[w * kSymvCols + tid];
+                for (int w = 0; w < kSymvRows / 32; w++) s += sm.cred[w * kSymvCols + tid];
                 colpart[(size_t)d.w * Np + c0 + tid] = s;
             }
 #pragma unroll
@@ -1103,8 +1126,25 @@ k_symv_lower(int Np, int ld, int N, const double* __restrict__ S, const double* 
     }
 }
 
-// out[r] = sign * ( sum_seg colpart[seg][r] + sum_{strip <= r/32} rowpart[strip][r] ), r < N.
-// CTA = 32 rows x 32 strip groups; group g adds strips g, g+32, ... in order, groups are folded in order.
+__global__ void __launch_bounds__(kSymvRows + 32, 1)
+k_symv_lower(int Np, int ld, int N, const double* __restrict__ S, const double* __restrict__ x,
+             const int* __restrict__ tile_ptr /* [gridDim.x + 1] */, const int4* __restrict__ tiles,
+             const int* __restrict__ done, double* __restrict__ rowpart /* [Np/32][Np] */,
+             double* __restrict__ colpart /* [nseg][Np] */)
+{
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const SymvSmem sm = symv_smem(smraw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (done && *done) return;
+    const int t0 = tile_ptr[blockIdx.x], nt = tile_ptr[blockIdx.x + 1] - t0;
+    if (nt <= 0) return;
+    if (tid == 0)
+        for (int s = 0; s < kSymvStages; s++) { mbar_init(sm.full + s, 1); mbar_init(sm.empty + s, kSymvRows / 32); }
+    __syncthreads();
+    if (warp == kSymvRows / 32) symv_producer(sm, ld, S, tiles, t0, nt, 0, lane);
+    else symv_consumer<false>(sm, Np, N, x, tiles, t0, nt, 0, rowpart, colpart);
+}
+
 struct P2PMail;
 __device__ __forceinline__ double p2p_allreduce_elem(const P2PMail& mb, unsigned int epoch, int t, double x);
 
@@ -1195,3 +1235,329 @@ k_p2p_allreduce(P2PMail mb, int n, unsigned int epoch, const int* __restrict__ d
 }
 
 }  // namespace vlgba
+
+// =========================================================================================
+// The whole PCG solve on the assembled S as ONE persistent cooperative kernel.
+// Launched per iteration, the loop is three kernels (matvec 75 us, fold of its partials 10 us,
+// vector update 22 us with two grid syncs) plus their launch gaps and a host check of the stop
+// flag every 8 iterations.  Here one CTA per SM stays resident for the whole solve and an
+// iteration is five phases separated by the light grid barrier of ba_chol.cuh:
+//   1. matvec tiles through the TMA ring (symv_producer / symv_consumer, same code as k_symv_lower);
+//   2. fold of the row/column partials into wq (each CTA folds the row blocks b = cta, cta + G, ...;
+//      the NVLink mailbox exchange of multi-GPU runs happens here, per element); meanwhile the TMA
+//      engine pulls this CTA's cluster inverse into the (now idle) ring memory;
+//   3. q = U* p - wq and the dot products p'q, Z'q, SZ'p (block partials);
+//   4. alpha, x, r, z = M^-1 r from shared memory, r'z and r'r (block partials);
+//   5. beta, p, stop flag.
+// Clusters (update CTAs) are the first `nclusters` CTAs; every CTA folds the scalar partials so
+// that alpha, beta and the stop decision are uniform without a broadcast.
+// =========================================================================================
+namespace vlgba {
+
+struct PcgPersistArgs {
+    int Np, ld, N, m, max_iter, nclusters;
+    double rtol;
+    const double* S;
+    const int* tile_ptr;
+    const int4* tiles;
+    double *rowpart, *colpart, *wq;
+    const double *Ud, *Minv, *McL;
+    double *x, *r, *p;
+    PcgScalars* sc;
+    double* blkpart;                 // 11 * nclusters
+    const double *Z, *SZ;            // deflation vectors or NULL
+    const DeflScalars* ds;
+    unsigned int* barrier;           // zero at launch
+    const P2PMail* mb;               // multi-GPU exchange or NULL
+    unsigned int epoch0;             // mailbox epoch of the first matvec of this launch
+    long long* prof;                 // optional: clock64 totals per phase seen by CTA 0 / thread 0 (VLG_BA_PERSIST_PROF), or NULL
+};
+
+#define PCG_PROF(slot)                                                           \
+    do {                                                                         \
+        if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                     \
+            const long long now_ = clock64();                                    \
+            a.prof[slot] += now_ - prof_t;                                       \
+            prof_t = now_;                                                       \
+        }                                                                        \
+    } while (0)
+
+template <int NA>
+__global__ void __launch_bounds__(kSymvRows + 32, 1)
+k_pcg_persistent(PcgPersistArgs a)
+{
+    constexpr int ND = 1 + 2 * kDefl;
+    constexpr int kCams = 128 / NA, NC = kCams * NA;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const SymvSmem sm = symv_smem(smraw);
+    __shared__ double shd[4 * ND], pv[128], rv[128], fold[4][8][33], bcast[ND + 2];
+    __shared__ uint64_t mbarM;
+    __shared__ double einv[kDefl * kDefl];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, G = gridDim.x, nb = a.nclusters;
+    const bool producer = warp == kSymvRows / 32;
+    const bool cluster_cta = cta < nb;
+    const int t0 = a.tile_ptr[cta], nt = a.tile_ptr[cta + 1] - t0;
+    const size_t N = (size_t)a.N;
+    if (tid == 0) {
+        for (int s = 0; s < kSymvStages; s++) { mbar_init(sm.full + s, 1); mbar_init(sm.empty + s, kSymvRows / 32); }
+        mbar_init(&mbarM, 1);
+    }
+    if (a.Z && tid < kDefl * kDefl) einv[tid] = a.ds->Einv[tid];     // constant over the solve
+    __syncthreads();
+    unsigned int bar_target = 0;
+    int kbase = 0;
+    const double r0n2 = a.sc->r0n2;
+    double rz = a.sc->rz;
+    const int lc = tid / NA, row = tid - lc * NA;             // update role: local camera, row (threads < 128)
+    const int j = cta * kCams + lc;
+    const bool act = cluster_cta && tid < 128 && lc < kCams && j < a.m;
+    const size_t t = (size_t)NA * j + row;
+    const int nrb = a.Np / 32;
+
+    long long prof_t = a.prof ? clock64() : 0;
+    for (int it = 0; it < a.max_iter; it++) {
+        // ---- 1. matvec tiles
+        if (nt > 0) {
+            if (producer) symv_producer(sm, a.ld, a.S, a.tiles, t0, nt, kbase, lane);
+            else symv_consumer<true>(sm, a.Np, a.N, a.p, a.tiles, t0, nt, kbase, a.rowpart, a.colpart);
+            kbase += nt;
+        }
+        PCG_PROF(0);
+        grid_barrier(a.barrier, bar_target, G);
+        PCG_PROF(1);
+        // ---- 2. cluster inverse -> ring memory (asynchronously), fold of the matvec partials -> wq
+        if (cluster_cta && a.McL && tid == 0) {
+            constexpr uint32_t bytes = (uint32_t)NC * 128u * 8u;
+            mbar_expect_tx(&mbarM, bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(sm.st)), "l"(a.McL + (size_t)cta * 128 * 128), "r"(bytes), "r"(smem_u32(&mbarM)) : "memory");
+        }
+        if (!producer) {
+            const int gq = tid >> 5;                               // strip group 0..7
+            // row blocks are dealt to the CTAs like a snake draft (block b costs ~b terms): round q gives CTA c the
+            // block q G + c (q even) or q G + G - 1 - c (q odd), counted from the LAST block down; per block the
+            // 256 threads are 32 rows x 8 groups, group gq takes terms gq, gq + 8, ... 16 loads in flight each
+            for (int q = 0; q * G < nrb; q++) {
+                const int idx = q * G + ((q & 1) ? G - 1 - cta : cta);
+                const int rb = nrb - 1 - idx;
+                const bool have = idx < nrb;                        // uniform over the CTA
+                const int r = rb * 32 + lane;
+                double acc = 0.0;
+                if (have) {
+                    // terms 0..rb: row partials of strips 0..rb; then the column partials of this block's segments
+                    const int nseg = (a.Np - kSymvCols * rb + kSymvSegRows - 1) / kSymvSegRows;
+                    const int nterm = rb + 1 + nseg;
+                    for (int q0 = gq; q0 < nterm; q0 += 128) {
+                        double v[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            const int tq = q0 + 8 * u;
+                            const double* src = tq <= rb ? a.rowpart + (size_t)tq * a.Np + r : a.colpart + (size_t)(tq - rb - 1) * a.Np + r;
+                            v[u] = tq < nterm ? __ldcg(src) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; u++) acc += v[u];
+                    }
+                }
+                fold[0][gq][lane] = acc;
+                consumer_sync();
+                if (have && gq == 0 && r < a.N) {
+                    double y = 0.0;
+#pragma unroll
+                    for (int g8 = 0; g8 < 8; g8++) y += fold[0][g8][lane];
+                    y = -y;
+                    if (a.mb) y = p2p_allreduce_elem(*a.mb, a.epoch0 + (unsigned int)it, r, y);
+                    a.wq[r] = y;
+                }
+                consumer_sync();
+            }
+        }
+        PCG_PROF(2);
+        grid_barrier(a.barrier, bar_target, G);
+        PCG_PROF(3);
+        // ---- 3. q = U* p - wq, dot products
+        double dots[ND];
+#pragma unroll
+        for (int k = 0; k < ND; k++) dots[k] = 0.0;
+        double pt = 0.0, qt = 0.0;
+        double xt = 0.0, rt0 = 0.0, szv[kDefl];            // phase-4 operands, requested a barrier early
+#pragma unroll
+        for (int d = 0; d < kDefl; d++) szv[d] = 0.0;
+        const int nd = a.Z ? ND : 1;
+        if (cluster_cta && tid < 128) {
+            if (act) {
+                pt = __ldcg(a.p + t); pv[tid] = pt;
+                xt = __ldcg(a.x + t); rt0 = __ldcg(a.r + t);
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (act) {
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < NA; c++) v += a.Ud[(size_t)NA * NA * j + row + NA * c] * pv[lc * NA + c];
+                qt = v - __ldcg(a.wq + t);
+                dots[0] = pt * qt;
+                if (a.Z) {
+#pragma unroll
+                    for (int d = 0; d < kDefl; d++) {
+                        szv[d] = a.SZ[d * N + t];
+                        dots[1 + d] = a.Z[d * N + t] * qt;
+                        dots[1 + kDefl + d] = szv[d] * pt;
+                    }
+                }
+            }
+            for (int k = 0; k < nd; k++) {
+                const double v = warp_sum(dots[k]);
+                if (lane == 0) shd[warp * ND + k] = v;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tid < nd) {
+                double v = 0.0;
+                for (int w = 0; w < 4; w++) v += shd[w * ND + tid];
+                a.blkpart[(size_t)tid * nb + cta] = v;
+            }
+        }
+        PCG_PROF(4);
+        grid_barrier(a.barrier, bar_target, G);
+        PCG_PROF(5);
+        // every warp of every CTA folds the block partials the same way: uniform alpha / stop decisions
+        // all the partial loads are requested before the first use (a loop over k with a runtime bound
+        // serialises one L2 round trip per scalar: measured 10 us of an iteration)
+        // ONE warp per CTA reads the partials (148 x 9 warps hammering the same 6 KB of L2 cost 9 us per
+        // iteration) and publishes the sums through shared memory
+        if (warp == 0) {
+            // every load is issued before the first add: an add placed right behind its load stalls the
+            // in-order issue for a whole L2 round trip (27 of them cost 6.7 us here)
+            constexpr int KB = 5;                      // nb <= 160 clusters covered in one pass
+            double ldv[ND][KB];
+#pragma unroll
+            for (int k = 0; k < ND; k++)
+#pragma unroll
+                for (int u = 0; u < KB; u++) {
+                    const int b = lane + 32 * u;
+                    ldv[k][u] = (k < nd && b < nb) ? __ldcg(a.blkpart + (size_t)k * nb + b) : 0.0;
+                }
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+                double v = 0.0;
+#pragma unroll
+                for (int u = 0; u < KB; u++) v += ldv[k][u];
+                if (k < nd)
+                    for (int b = lane + 32 * KB; b < nb; b += 32) v += __ldcg(a.blkpart + (size_t)k * nb + b);
+                v = k < nd ? warp_sum(v) : 0.0;
+                if (lane == 0) bcast[k] = v;
+            }
+        }
+        PCG_PROF(13);
+        __syncthreads();
+        PCG_PROF(14);
+#pragma unroll
+        for (int k = 0; k < ND; k++) dots[k] = bcast[k];
+        double y[kDefl];
+        double pq = dots[0];
+        if (a.Z) {
+#pragma unroll
+            for (int d = 0; d < kDefl; d++) {
+                double v = 0.0;
+#pragma unroll
+                for (int e = 0; e < kDefl; e++) v += einv[d + kDefl * e] * dots[1 + e];
+                y[d] = v;
+                pq -= dots[1 + kDefl + d] * v;
+            }
+        }
+        if (!(pq > 0.0)) {                            // breakdown: uniform over the grid
+            if (cta == 0 && tid == 0) { a.sc->done = 2; a.sc->pq = pq; a.sc->rz = rz; a.sc->iters += it; }
+            return;
+        }
+        const double alpha = rz / pq;
+        // ---- 4. x, r, z = M^-1 r
+        double rzn = 0.0, rr = 0.0, zt = 0.0;
+        double* bp2 = a.blkpart + (size_t)ND * nb;
+        if (cluster_cta && tid < 128) {
+            if (act) {
+                if (a.Z) {
+#pragma unroll
+                    for (int d = 0; d < kDefl; d++) qt -= szv[d] * y[d];
+                }
+                a.x[t] = xt + alpha * pt;
+                const double rt = rt0 - alpha * qt;
+                a.r[t] = rt;
+                rv[tid] = rt;
+                rr = rt * rt;
+            } else {
+                rv[tid] = 0.0;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            PCG_PROF(10);
+            if (act) {
+                if (a.McL) {
+                    mbar_wait(&mbarM, (uint32_t)(it & 1));
+                    PCG_PROF(11);
+                    const double* M = sm.st + tid;                  // column-major, ld 128
+                    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+#pragma unroll 4
+                    for (int c = 0; c + 3 < NC; c += 4) {
+                        z0 += M[128 * c] * rv[c]; z1 += M[128 * (c + 1)] * rv[c + 1];
+                        z2 += M[128 * (c + 2)] * rv[c + 2]; z3 += M[128 * (c + 3)] * rv[c + 3];
+                    }
+#pragma unroll
+                    for (int c = NC - NC % 4; c < NC; c++) z0 += M[128 * c] * rv[c];
+                    zt = (z0 + z1) + (z2 + z3);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NA; c++) zt += a.Minv[(size_t)NA * NA * j + row + NA * c] * rv[lc * NA + c];
+                }
+                rzn = rv[tid] * zt;
+            }
+            PCG_PROF(12);
+            rzn = warp_sum(rzn);
+            rr = warp_sum(rr);
+            if (lane == 0) { shd[warp * 2] = rzn; shd[warp * 2 + 1] = rr; }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tid < 2) {
+                double v = 0.0;
+                for (int w = 0; w < 4; w++) v += shd[w * 2 + tid];
+                bp2[2 * cta + tid] = v;
+            }
+        }
+        PCG_PROF(6);
+        grid_barrier(a.barrier, bar_target, G);
+        PCG_PROF(7);
+        if (warp == 0) {
+            constexpr int KB = 5;
+            double l0[KB], l1[KB];
+#pragma unroll
+            for (int u = 0; u < KB; u++) {
+                const int b = lane + 32 * u;
+                l0[u] = b < nb ? __ldcg(bp2 + 2 * b) : 0.0;
+                l1[u] = b < nb ? __ldcg(bp2 + 2 * b + 1) : 0.0;
+            }
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int u = 0; u < KB; u++) { v0 += l0[u]; v1 += l1[u]; }
+            for (int b = lane + 32 * KB; b < nb; b += 32) { v0 += __ldcg(bp2 + 2 * b); v1 += __ldcg(bp2 + 2 * b + 1); }
+            v0 = warp_sum(v0); v1 = warp_sum(v1);
+            if (lane == 0) { bcast[ND] = v0; bcast[ND + 1] = v1; }
+        }
+        __syncthreads();
+        rzn = bcast[ND]; rr = bcast[ND + 1];
+        // ---- 5. p = z + beta p, stop test
+        const double beta = rzn / rz;
+        if (act) a.p[t] = zt + beta * pt;
+        rz = rzn;
+        const bool stop = rr <= a.rtol * a.rtol * r0n2 || it + 1 == a.max_iter;
+        if (stop) {
+            if (cta == 0 && tid == 0) {
+                a.sc->rz = rzn; a.sc->rn2 = rr; a.sc->pq = pq; a.sc->iters += it + 1;
+                if (rr <= a.rtol * a.rtol * r0n2) a.sc->done = 1;
+            }
+            return;
+        }
+        PCG_PROF(8);
+        grid_barrier(a.barrier, bar_target, G);       // p complete before the next matvec reads it
+        PCG_PROF(9);
+    }
+}
+
+}  // namespace vlgba
+

@@ -60,9 +60,9 @@ bool nccl_load()
 
 char g_create_error[512] = "";
 
-enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_SYMV, T_PRECOND, T_COUNT };
+enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_SYMV, T_PRECOND, T_PCG_PERSIST, T_COUNT };
 const char* kTimerNames[T_COUNT] = {"stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt",
-                                    "pcg_sweep_cam", "stage3", "pcg_update", "w_copy", "pcg_symv", "precond"};
+                                    "pcg_sweep_cam", "stage3", "pcg_update", "w_copy", "pcg_symv", "precond", "pcg_persistent"};
 
 struct KTimer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -89,6 +89,8 @@ struct vlg_ba_ctx {
     int* symv_tile_ptr = nullptr;
     int symv_grid = 0, nsymv_seg = 0;
     double *symv_rowpart = nullptr, *symv_colpart = nullptr;
+    unsigned int* persist_bar = nullptr;   // grid barrier counter of k_pcg_persistent
+    bool persist_ok = false;
     double *Cblk = nullptr, *McL = nullptr;   // cluster-Jacobi preconditioner: gathered diagonal blocks of S, their inverses [coop_grid][128 x 128]
     int Np = 0;               // padded order of S
     int64_t nblocks = 0, npairs = 0;
@@ -619,7 +621,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         for (const Item& it : items) {
             int best = 0;
             for (int g = 1; g < G; g++) if (load[g] < load[best]) best = g;
-            mine[best].push_back(it); load[best] += (it.rows + kSymvRows - 1) / kSymvRows * 8 + 1;
+            mine[best].push_back(it); load[best] += it.rows + 24 * ((it.rows + kSymvRows - 1) / kSymvRows) + 40;   // rows + per-tile and per-item overheads
         }
         std::vector<int4> tiles;
         std::vector<int> tptr((size_t)G + 1, 0);
@@ -638,6 +640,11 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         CHK(upload(ctx, ctx->symv_tiles, tiles.data(), tiles.size()));
         CHK(upload(ctx, ctx->symv_tile_ptr, tptr.data(), tptr.size()));
         CU(cudaStreamSynchronize(ctx->stream));
+        CHK(dalloc(ctx, &ctx->persist_bar, 1));
+        {
+            const char* e = getenv("VLG_BA_PERSIST");      // 0: one launch per PCG phase instead of the persistent kernel
+            ctx->persist_ok = e ? atoi(e) != 0 : true;
+        }
         CHK(dalloc(ctx, &ctx->symv_rowpart, (size_t)nstrips * Np));
         CHK(dalloc(ctx, &ctx->symv_colpart, (size_t)ctx->nsymv_seg * Np));
     }

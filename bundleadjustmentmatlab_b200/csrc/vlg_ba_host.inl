@@ -107,7 +107,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         const size_t sm_cam = sizeof(double) * (kCamTile * NW + kCamWarps * NA) + 16;
         const bool tiled_cam = ctx->chunk_size <= kCamTile;
         const bool need_wq = ctx->nranks > 1 || ctx->coop_grid == 0 || ctx->use_explicit;
-        constexpr size_t kSymvSmem = sizeof(double) * ((size_t)kSymvStages * kSymvCols * kSymvRows + (kSymvRows / 32) * kSymvCols + kSymvCols) + 16 * kSymvStages + 16;
+        constexpr size_t kSymvSmem = kSymvSmemBytes;
         if (ctx->use_explicit) {
             CU(cudaFuncSetAttribute(k_symv_lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSymvSmem));
             // this rank's share of sum_i Y_ij W_ik' (S without U*; U* p is added by the update kernel)
@@ -219,6 +219,49 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         ctx->launches++;
         int launched = 0;
         const int batch = 8;
+        // assembled S on one GPU (or with the peer-memory exchange): the whole solve is one persistent kernel
+        const bool persistent = ctx->use_explicit && ctx->persist_ok && ctx->coop_grid > 0 && ctx->coop_grid <= ctx->symv_grid &&
+                                (ctx->nranks == 1 || ctx->p2p_ready) && ctx->opt.pcg_max_iter > 0;
+        if (persistent) {
+            TimedScope ts(ctx, T_PCG_PERSIST);
+            PcgPersistArgs pa;
+            pa.Np = ctx->Np; pa.ld = ctx->Np; pa.N = N; pa.m = m; pa.max_iter = ctx->opt.pcg_max_iter; pa.nclusters = ctx->coop_grid;
+            pa.rtol = rtol; pa.S = ctx->S; pa.tile_ptr = ctx->symv_tile_ptr; pa.tiles = ctx->symv_tiles;
+            pa.rowpart = ctx->symv_rowpart; pa.colpart = ctx->symv_colpart; pa.wq = ctx->wq;
+            pa.Ud = ctx->Ud; pa.Minv = ctx->Minv; pa.McL = McL; pa.x = ctx->da; pa.r = ctx->pr; pa.p = ctx->pp;
+            pa.sc = ctx->pcg_sc; pa.blkpart = ctx->blkpart; pa.Z = defl ? ctx->Zd : nullptr; pa.SZ = defl ? ctx->SZd : nullptr;
+            pa.ds = ctx->defl_sc; pa.barrier = ctx->persist_bar;
+            pa.mb = ctx->nranks > 1 ? ctx->p2p_dev : nullptr; pa.epoch0 = ctx->p2p_epoch + 1;
+            pa.prof = nullptr;
+            static long long* d_prof = nullptr;
+            const bool want_prof = getenv("VLG_BA_PERSIST_PROF") != nullptr;
+            if (want_prof) {
+                if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+                cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), ctx->stream);
+                pa.prof = d_prof;
+            }
+            CU(cudaMemsetAsync(ctx->persist_bar, 0, sizeof(unsigned int), ctx->stream));
+            CU(cudaFuncSetAttribute(k_pcg_persistent<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSymvSmemBytes));
+            void* args[] = {&pa};
+            CU(cudaLaunchCooperativeKernel((void*)k_pcg_persistent<NA>, dim3(ctx->symv_grid), dim3(kSymvRows + 32), args, kSymvSmemBytes,
+                                           ctx->stream));
+            ctx->launches++;
+            launched = ctx->opt.pcg_max_iter;
+            CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (ctx->nranks > 1) ctx->p2p_epoch += (unsigned int)ctx->h_pcg->iters;       // one mailbox epoch per matvec, on every rank
+            if (want_prof) {
+                long long hp[16];
+                cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+                int khz = 0;
+                cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+                const char* nm[15] = {"matvec", "barrier", "fold", "barrier", "phase3", "barrier", "phase4-rest", "barrier", "phase5", "barrier",
+                                      "p4:x,r", "p4:wait-McL", "p4:matvec", "p4:partials", "p4:sync"};
+                fprintf(stderr, "k_pcg_persistent, %d iterations, us per iteration (CTA 0):", ctx->h_pcg->iters);
+                for (int k = 0; k < 15; k++) fprintf(stderr, " %s %.1f", nm[k], hp[k] / (khz * 1e-3) / std::max(ctx->h_pcg->iters, 1));
+                fprintf(stderr, "\n");
+            }
+        }
         while (launched < ctx->opt.pcg_max_iter) {
             for (int it = 0; it < batch && launched < ctx->opt.pcg_max_iter; it++, launched++) {
                 CHK(sweeps(ctx->pp, done));
