@@ -541,16 +541,26 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     grid.sync();
     // every warp folds the per-block partials the same way (strided by lane, xor tree)
     {
-        double pv_[ND];                            // every partial load in flight before the first use
+        // every partial load is issued before the first add (an add right behind its load stalls the
+        // in-order issue for an L2 round trip per partial: measured in k_pcg_persistent)
+        constexpr int KB = 4;
+        double ldv[ND][KB];
+#pragma unroll
+        for (int k = 0; k < ND; k++)
+#pragma unroll
+            for (int u = 0; u < KB; u++) {
+                const int b = lane + 32 * u;
+                ldv[k][u] = (k < nd && b < nb) ? __ldcg(blkpart + (size_t)k * nb + b) : 0.0;
+            }
 #pragma unroll
         for (int k = 0; k < ND; k++) {
             double v = 0.0;
-            if (k < nd)
-                for (int b = lane; b < nb; b += 32) v += __ldcg(blkpart + (size_t)k * nb + b);
-            pv_[k] = v;
-        }
 #pragma unroll
-        for (int k = 0; k < ND; k++) dots[k] = k < nd ? warp_sum(pv_[k]) : 0.0;
+            for (int u = 0; u < KB; u++) v += ldv[k][u];
+            if (k < nd)
+                for (int b = lane + 32 * KB; b < nb; b += 32) v += __ldcg(blkpart + (size_t)k * nb + b);
+            dots[k] = k < nd ? warp_sum(v) : 0.0;
+        }
     }
     // deflated operator: w <- P S p = S p - SZ Einv Z' S p ;  p'(P S p) = p'Sp - (SZ'p)' Einv (Z'Sp)
     double y[kDefl];
