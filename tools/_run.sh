@@ -1,8 +1,5 @@
-set -x
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/mgpu_check.py > gpurun_out/mgpu.log 2>&1
-grep -E "MGPU|Error|error|assert" gpurun_out/mgpu.log | head -5
-for mode in "" "--no-p2p"; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e $mode > gpurun_out/bench_2gpu_p2p$mode.json 2> gpurun_out/bench_2gpu.err
+N=$1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_venice_${N}gpu_r01z.json 2> gpurun_out/bench_${N}gpu_z.err
+echo rc=$?
 python -c "
-import json,sys;d=json.loads([l for l in open('gpurun_out/bench_2gpu_p2p$mode.json') if l.startswith('{')][0]);print(d['ms_per_step'],d['lm_iters_per_sec'],d['config'].get('pcg_vector_allreduce'),d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -2 gpurun_out/bench_2gpu.err
-done
+import json;d=json.loads([l for l in open('gpurun_out/bench_venice_${N}gpu_r01z.json') if l.startswith('{')][0]);print(d['n_gpus'],d['value'],d['ms_per_step'],d['lm_iters_per_sec'],d['e2e']['value'],d['config'].get('pcg_vector_allreduce'),d['pcg_iters'],{k:v['avg_ms'] for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_${N}gpu_z.err
