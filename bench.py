@@ -365,7 +365,10 @@ def run_ours(args):
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp):
-                traffic = json.load(open(tp)).get(args.config, {}).get(dom)
+                tj = json.load(open(tp)).get(args.config, {})
+                traffic = tj.get(dom)
+                if traffic is None and tj.get(dom + "_per_iteration"):
+                    traffic = tj[dom + "_per_iteration"] * its2       # per launch = per iteration x mean iterations of a launch
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": groups[dom]["avg_ms"],
                     "launches": groups[dom]["count"], "peak_source": peak_kind,

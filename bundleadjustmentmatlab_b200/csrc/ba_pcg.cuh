@@ -462,7 +462,11 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* sh)
 constexpr int kDefl = 4;
 struct DeflScalars { double Einv[kDefl * kDefl]; double c0[kDefl]; };
 
-template <int NA>
+// BATCH: the scalar partials of all blocks are loaded into registers before they are summed (faster: no
+// L2 round trip per partial on the in-order issue path, but ~125 registers: at most 4 CTAs per SM); the
+// host falls back to BATCH = false (48 registers) when the grid would not be co-resident (Final shape:
+// 652 clusters).
+template <int NA, bool BATCH>
 __global__ void __launch_bounds__(128)
 k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __restrict__ qpart,
                   const double* __restrict__ wq, const double* __restrict__ Ud, const double* __restrict__ Minv,
@@ -540,7 +544,13 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     }
     grid.sync();
     // every warp folds the per-block partials the same way (strided by lane, xor tree)
-    {
+    if constexpr (!BATCH) {
+        for (int k = 0; k < nd; k++) {
+            double v = 0.0;
+            for (int b = lane; b < nb; b += 32) v += __ldcg(blkpart + (size_t)k * nb + b);
+            dots[k] = warp_sum(v);
+        }
+    } else {
         // every partial load is issued before the first add (an add right behind its load stalls the
         // in-order issue for an L2 round trip per partial: measured in k_pcg_persistent)
         constexpr int KB = 4;
@@ -738,6 +748,138 @@ k_pcg_init_defl(int m, const double* __restrict__ ebar, const double* __restrict
     if (threadIdx.x == 0) {
         sc->rz = rz; sc->r0n2 = bb; sc->rn2 = bb; sc->pq = 0.0; sc->iters = 0;
         sc->done = (bb == 0.0 || rz == 0.0) ? 1 : 0;
+    }
+}
+
+// The same set-up on the update kernel's grid (one CTA per cluster, thread per unknown, two grid
+// barriers): the single-CTA version above is a chain of 16 block reductions plus the cluster
+// product by 1024 threads -- 0.39 ms per LM step at Venice shape, 3.8 % of the step.
+template <int NA>
+__global__ void __launch_bounds__(128)
+k_pcg_init_defl_coop(int m, const double* __restrict__ ebar, const double* __restrict__ Minv, const double* __restrict__ Z,
+                     const double* __restrict__ SZ, DeflScalars* __restrict__ ds, double* __restrict__ x,
+                     double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, PcgScalars* __restrict__ sc,
+                     const double* __restrict__ McL, double* __restrict__ part /* 17 * gridDim.x */,
+                     unsigned int* __restrict__ barrier)
+{
+    constexpr int kCams = 128 / NA, NC = kCams * NA;
+    constexpr int NP = kDefl * (kDefl + 1) / 2 + kDefl + 1;      // E (upper triangle), c0, b'b
+    __shared__ double shd[4 * NP], bc[NP + 1], rv[128];
+    __shared__ double E[kDefl * kDefl], Ei[kDefl * kDefl], y0[kDefl];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, nb = gridDim.x;
+    const size_t N = (size_t)NA * m;
+    const int lc = tid / NA, row = tid - lc * NA;
+    const int j = cta * kCams + lc;
+    const bool act = lc < kCams && j < m;
+    const size_t t = (size_t)NA * j + row;
+    unsigned int bar_target = 0;
+    double zt[kDefl], st[kDefl], bt = 0.0;
+#pragma unroll
+    for (int d = 0; d < kDefl; d++) { zt[d] = act ? Z[d * N + t] : 0.0; st[d] = act ? SZ[d * N + t] : 0.0; }
+    if (act) bt = ebar[t];
+    double pr[NP];
+    {
+        int k = 0;
+#pragma unroll
+        for (int d = 0; d < kDefl; d++)
+#pragma unroll
+            for (int e = d; e < kDefl; e++) pr[k++] = 0.5 * (zt[d] * st[e] + zt[e] * st[d]);
+#pragma unroll
+        for (int d = 0; d < kDefl; d++) pr[k++] = zt[d] * bt;
+        pr[k] = bt * bt;
+    }
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        const double v = warp_sum(pr[k]);
+        if (lane == 0) shd[warp * NP + k] = v;
+    }
+    __syncthreads();
+    if (tid < NP) {
+        double v = 0.0;
+        for (int w = 0; w < 4; w++) v += shd[w * NP + tid];
+        part[(size_t)tid * nb + cta] = v;
+    }
+    grid_barrier(barrier, bar_target, nb);
+    if (warp == 0) {
+        constexpr int KB = 5;
+        double ldv[NP][KB];
+#pragma unroll
+        for (int k = 0; k < NP; k++)
+#pragma unroll
+            for (int u = 0; u < KB; u++) {
+                const int b = lane + 32 * u;
+                ldv[k][u] = b < nb ? __ldcg(part + (size_t)k * nb + b) : 0.0;
+            }
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            double v = 0.0;
+#pragma unroll
+            for (int u = 0; u < KB; u++) v += ldv[k][u];
+            for (int b = lane + 32 * KB; b < nb; b += 32) v += __ldcg(part + (size_t)k * nb + b);
+            v = warp_sum(v);
+            if (lane == 0) bc[k] = v;
+        }
+        if (lane == 0) {
+            int k = 0;
+            for (int d = 0; d < kDefl; d++)
+                for (int e = d; e < kDefl; e++) { E[d + kDefl * e] = bc[k]; E[e + kDefl * d] = bc[k]; k++; }
+            sym_pinv<kDefl>(E, Ei);
+            for (int d = 0; d < kDefl; d++) {
+                double v = 0.0;
+                for (int e = 0; e < kDefl; e++) v += Ei[d + kDefl * e] * bc[kDefl * (kDefl + 1) / 2 + e];
+                y0[d] = v;
+            }
+            if (cta == 0) {
+                for (int d = 0; d < kDefl; d++) ds->c0[d] = bc[kDefl * (kDefl + 1) / 2 + d];
+                for (int q = 0; q < kDefl * kDefl; q++) ds->Einv[q] = Ei[q];
+            }
+        }
+    }
+    __syncthreads();
+    double rt = 0.0, zz = 0.0;
+    if (act) {
+        rt = bt;
+#pragma unroll
+        for (int d = 0; d < kDefl; d++) rt -= st[d] * y0[d];
+        r[t] = rt; x[t] = 0.0;
+    }
+    rv[tid] = rt;
+    __syncthreads();
+    if (act) {
+        if (McL) {
+            const double* M = McL + (size_t)cta * 128 * 128 + tid;
+            double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+#pragma unroll 4
+            for (int c = 0; c + 3 < NC; c += 4) {
+                z0 += __ldg(M + 128 * c) * rv[c]; z1 += __ldg(M + 128 * (c + 1)) * rv[c + 1];
+                z2 += __ldg(M + 128 * (c + 2)) * rv[c + 2]; z3 += __ldg(M + 128 * (c + 3)) * rv[c + 3];
+            }
+#pragma unroll
+            for (int c = NC - NC % 4; c < NC; c++) z0 += __ldg(M + 128 * c) * rv[c];
+            zz = (z0 + z1) + (z2 + z3);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NA; c++) zz += Minv[(size_t)NA * NA * j + row + NA * c] * rv[lc * NA + c];
+        }
+        z[t] = zz; p[t] = zz;
+    }
+    {
+        const double v = warp_sum(act ? rt * zz : 0.0);
+        if (lane == 0) shd[warp] = v;
+    }
+    __syncthreads();
+    if (tid == 0) part[(size_t)NP * nb + cta] = (shd[0] + shd[1]) + (shd[2] + shd[3]);
+    grid_barrier(barrier, bar_target, nb);
+    if (cta == 0 && warp == 0) {
+        double v = 0.0;
+        for (int b = lane; b < nb; b += 32) v += __ldcg(part + (size_t)NP * nb + b);
+        v = warp_sum(v);
+        if (lane == 0) {
+            const double bb = bc[NP - 1];
+            sc->rz = v; sc->r0n2 = bb; sc->rn2 = bb; sc->pq = 0.0; sc->iters = 0;
+            sc->done = (bb == 0.0 || v == 0.0) ? 1 : 0;
+        }
     }
 }
 

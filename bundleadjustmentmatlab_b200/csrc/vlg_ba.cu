@@ -90,6 +90,9 @@ struct vlg_ba_ctx {
     int symv_grid = 0, nsymv_seg = 0;
     double *symv_rowpart = nullptr, *symv_colpart = nullptr;
     unsigned int* persist_bar = nullptr;   // grid barrier counter of k_pcg_persistent
+    unsigned int* init_bar = nullptr;      // ... of k_pcg_init_defl_coop
+    double* init_part = nullptr;           // its block partials [17 x coop_grid]
+    int init_coop_cap = -1;                // CTAs of k_pcg_init_defl_coop that can be co-resident (-1: not asked yet)
     bool persist_ok = false;
     double *Cblk = nullptr, *McL = nullptr;   // cluster-Jacobi preconditioner: gathered diagonal blocks of S, their inverses [coop_grid][128 x 128]
     int Np = 0;               // padded order of S
@@ -362,6 +365,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     }
     free_problem(ctx);
     // optional buffers: which of them exist depends on the solver path of THIS problem
+    ctx->init_part = nullptr; ctx->init_bar = nullptr; ctx->persist_bar = nullptr; ctx->init_coop_cap = -1;
     ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr;
     ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr; ctx->pt_pt = nullptr;
     ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
@@ -589,6 +593,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         const int g = cdiv(m, 128 / na);            // k_pcg_update_coop: a CTA owns 128/na whole cameras
         if (coop && g <= nsm * 8) ctx->coop_grid = g;
         CHK(dalloc(ctx, &ctx->blkpart, (size_t)11 * std::max(g, 1)));
+        if (ctx->coop_grid > 0) { CHK(dalloc(ctx, &ctx->init_part, (size_t)17 * g)); CHK(dalloc(ctx, &ctx->init_bar, 1)); }
         if (cluster_pc && ctx->coop_grid > 0) {
             CHK(dalloc(ctx, &ctx->Cblk, (size_t)g * 128 * 128)); CHK(dalloc(ctx, &ctx->McL, (size_t)g * 128 * 128));
         }

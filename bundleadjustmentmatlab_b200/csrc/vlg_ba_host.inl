@@ -119,7 +119,16 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         // the update kernel keeps its cluster inverse in shared memory when every cluster gets an SM of its own
         const size_t upd_smem = sizeof(double) * (size_t)Cluster<NA>::NC * 128;
         int mcl_in_smem = ctx->McL && ctx->coop_grid <= ctx->nsm ? 1 : 0;
-        if (mcl_in_smem) CU(cudaFuncSetAttribute(k_pcg_update_coop<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+        if (mcl_in_smem) {
+            CU(cudaFuncSetAttribute(k_pcg_update_coop<NA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+            CU(cudaFuncSetAttribute(k_pcg_update_coop<NA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+        }
+        bool upd_batch = false;
+        if (ctx->coop_grid > 0) {
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_update_coop<NA, true>, 128, mcl_in_smem ? upd_smem : 0));
+            upd_batch = ctx->coop_grid <= per_sm * ctx->nsm;
+        }
         if (ctx->McL) {
             // cluster-Jacobi: diagonal blocks of S over the update kernel's CTAs, summed over ranks, inverted
             TimedScope ts(ctx, T_PRECOND);
@@ -211,8 +220,27 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                                                                                     ctx->Zd + (size_t)d * N, ctx->SZd + (size_t)d * N);
                 ctx->launches++;
             }
-            k_pcg_init_defl<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->Zd, ctx->SZd, ctx->defl_sc, ctx->da, ctx->pr,
-                                                           ctx->pz, ctx->pp, ctx->pcg_sc, McL);
+            if (ctx->init_part && ctx->init_coop_cap < 0) {
+                // can the whole update grid be co-resident with this kernel's register footprint?
+                int per_sm = 0;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_init_defl_coop<NA>, 128, 0));
+                ctx->init_coop_cap = per_sm * ctx->nsm;
+            }
+            if (ctx->init_part && ctx->coop_grid <= ctx->init_coop_cap) {
+                // cooperative set-up on the update kernel's grid
+                int m_ = m;
+                const double *eb = ctx->ebar, *mi = ctx->Minv, *zz = ctx->Zd, *sz = ctx->SZd, *mcl = McL;
+                DeflScalars* dsc = ctx->defl_sc;
+                double *xx = ctx->da, *rr = ctx->pr, *pzv = ctx->pz, *ppv = ctx->pp, *ip = ctx->init_part;
+                PcgScalars* sc = ctx->pcg_sc;
+                unsigned int* ib = ctx->init_bar;
+                CU(cudaMemsetAsync(ctx->init_bar, 0, sizeof(unsigned int), ctx->stream));
+                void* args[] = {&m_, &eb, &mi, &zz, &sz, &dsc, &xx, &rr, &pzv, &ppv, &sc, &mcl, &ip, &ib};
+                CU(cudaLaunchCooperativeKernel((void*)k_pcg_init_defl_coop<NA>, dim3(ctx->coop_grid), dim3(128), args, 0, ctx->stream));
+            } else {
+                k_pcg_init_defl<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->Zd, ctx->SZd, ctx->defl_sc, ctx->da, ctx->pr,
+                                                               ctx->pz, ctx->pp, ctx->pcg_sc, McL);
+            }
         } else {
             k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol, McL);
         }
@@ -282,8 +310,8 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                         const DeflScalars* dsc = ctx->defl_sc;
                         const double* mcl = McL;
                         void* args[] = {&m_, &ccp, &qp, &wqp, &ud, &mi, &xx, &rr, &ppv, &sc, &bp, &rt, &zz, &sz, &dsc, &mcl, &mcl_in_smem};
-                        CU(cudaLaunchCooperativeKernel((void*)k_pcg_update_coop<NA>, dim3(ctx->coop_grid), dim3(128), args,
-                                                       mcl_in_smem ? upd_smem : 0, ctx->stream));
+                        CU(cudaLaunchCooperativeKernel(upd_batch ? (void*)k_pcg_update_coop<NA, true> : (void*)k_pcg_update_coop<NA, false>,
+                                                       dim3(ctx->coop_grid), dim3(128), args, mcl_in_smem ? upd_smem : 0, ctx->stream));
                     } else {
                         k_pcg_update<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->Ud, ctx->Minv, ctx->wq, ctx->da, ctx->pr, ctx->pz, ctx->pp,
                                                                       ctx->pq, ctx->pcg_sc, rtol);

@@ -394,9 +394,29 @@ def test_venice_shape_invariants():
             ctx.set_state(a=a, b=b, lam=1e-3, nu=2.0)
             i2 = ctx.trial_step()
             assert i2["new_cost"] == i1["new_cost"] and i2["old_cost"] == i1["old_cost"] and i2["pcg_iters"] == i1["pcg_iters"]
+        else:
+            assert i1["solver_used"] == capi.SOLVER_PCG
         news[solver] = (i1["old_cost"], i1["new_cost"], i1["pcg_iters"])
         ctx.close()
     print("venice: (old, new, PCG iterations) assembled / implicit:", news[capi.SOLVER_AUTO], news[capi.SOLVER_PCG])
     assert news[capi.SOLVER_AUTO][0] == news[capi.SOLVER_PCG][0]
     assert rel(news[capi.SOLVER_AUTO][1], news[capi.SOLVER_PCG][1]) <= COST_RTOL
+
+
+def test_many_clusters_implicit_path():
+    """4 000 cameras = 667 preconditioner clusters: more update CTAs than can be co-resident with the
+    register-hungry kernel variants (cooperative launches must fall back to the light variants, as at Final
+    shape with 13 682 cameras).  Cluster-Jacobi on/off must give the same step."""
+    P = synth.make_problem(4000, 40000, 200000, seed=23)
+    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T); b = np.ascontiguousarray(P.Xe[:3].T)
+    out = {}
+    for cl in (0, 1):
+        ctx = capi.Context(num_variableK=0, pcg_cluster=cl, pcg_rtol=1e-10)
+        ctx.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
+        out[cl] = ctx.trial_step()
+        assert out[cl]["solver_used"] == capi.SOLVER_PCG
+        ctx.close()
+    print("many clusters: PCG iterations per-camera/cluster blocks:", out[0]["pcg_iters"], out[1]["pcg_iters"])
+    assert out[0]["old_cost"] == out[1]["old_cost"]
+    assert rel(out[0]["new_cost"], out[1]["new_cost"]) <= COST_RTOL
 
