@@ -695,7 +695,47 @@ k_schur_blocks_heavy(int nlist, const int* __restrict__ list, int ld, int ccams,
     double acc[NA * NA];
 #pragma unroll
     for (int u = 0; u < NA * NA; u++) acc[u] = 0.0;
-    for (int64_t q = blk_ptr[b] + lane; q < blk_ptr[b + 1]; q += 32) schur_pair<NA>(Y, W, pairs[q], acc);
+    if constexpr (NA % 2 == 0) {
+        // Y W' = sum over the 3 point coordinates c of (column c of Y)(column c of W)': three lanes share a pair, lane
+        // s takes column s of both blocks (NA doubles = 3 x 16 B when NA = 6) and adds its outer product into its own
+        // accumulators -- the warp reduction below sums the three anyway.  The three lanes of a pair read the same
+        // one or two lines, so a load instruction costs ~1/3 of the LSU wavefronts of the lane-per-pair form.
+        const int ps = lane / 3, sc = lane - 3 * ps;                 // pair slot 0..9, column; lanes 30, 31 idle
+        if (ps < 10) {
+            // software pipeline: the pair index is fetched two iterations ahead and the two half-blocks one
+            // iteration ahead, so that an iteration costs FMAs, not two dependent memory round trips
+            const int64_t q1 = blk_ptr[b + 1];
+            int64_t q = blk_ptr[b] + ps;
+            int2 prn = q < q1 ? pairs[q] : make_int2(0, 0);
+            int2 prnn = q + 10 < q1 ? pairs[q + 10] : make_int2(0, 0);
+            double2 yn[NA / 2], wn[NA / 2];
+            if (q < q1) {
+                const double2* ys = reinterpret_cast<const double2*>(Y + (size_t)3 * NA * prn.x + NA * sc);
+                const double2* ws = reinterpret_cast<const double2*>(W + (size_t)3 * NA * prn.y + NA * sc);
+#pragma unroll
+                for (int h = 0; h < NA / 2; h++) { yn[h] = __ldg(ys + h); wn[h] = __ldg(ws + h); }
+            }
+            for (; q < q1; q += 10) {
+                double yc[NA], wc[NA];
+#pragma unroll
+                for (int h = 0; h < NA / 2; h++) { yc[2 * h] = yn[h].x; yc[2 * h + 1] = yn[h].y; wc[2 * h] = wn[h].x; wc[2 * h + 1] = wn[h].y; }
+                const int2 pnext = prnn;
+                if (q + 20 < q1) prnn = pairs[q + 20];
+                if (q + 10 < q1) {
+                    const double2* ys = reinterpret_cast<const double2*>(Y + (size_t)3 * NA * pnext.x + NA * sc);
+                    const double2* ws = reinterpret_cast<const double2*>(W + (size_t)3 * NA * pnext.y + NA * sc);
+#pragma unroll
+                    for (int h = 0; h < NA / 2; h++) { yn[h] = __ldg(ys + h); wn[h] = __ldg(ws + h); }
+                }
+#pragma unroll
+                for (int col = 0; col < NA; col++)
+#pragma unroll
+                    for (int row = 0; row < NA; row++) acc[row + NA * col] += yc[row] * wc[col];
+            }
+        }
+    } else {
+        for (int64_t q = blk_ptr[b] + lane; q < blk_ptr[b + 1]; q += 32) schur_pair<NA>(Y, W, pairs[q], acc);
+    }
     double mine[(NA * NA + 31) / 32];
 #pragma unroll
     for (int u = 0; u < NA * NA; u++) {

@@ -11,6 +11,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <omp.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -94,6 +95,7 @@ struct vlg_ba_ctx {
     double* init_part = nullptr;           // its block partials [17 x coop_grid]
     int init_coop_cap = -1;                // CTAs of k_pcg_init_defl_coop that can be co-resident (-1: not asked yet)
     bool persist_ok = false;
+    bool S_zeroed = false;                 // explicit-S PCG: structurally zero blocks of S cleared for this problem
     double *Cblk = nullptr, *McL = nullptr;   // cluster-Jacobi preconditioner: gathered diagonal blocks of S, their inverses [coop_grid][128 x 128]
     int Np = 0;               // padded order of S
     int64_t nblocks = 0, npairs = 0;
@@ -312,6 +314,10 @@ void rodrigues_host(double w0, double w1, double w2, double* R)
 void rtab_host(int m, int na, const double* a, int nmat, double* out)
 {
     const double h = 1e-10;
+    // cameras are independent: a few host threads (explicit count: torchrun exports OMP_NUM_THREADS=1) take the
+    // 0.3 ms of libm calls at Venice shape off the critical path between two GPU stages
+    const int nthr = m >= 256 ? std::max(1, std::min(8, omp_get_num_procs())) : 1;
+#pragma omp parallel for num_threads(nthr) schedule(static)
     for (int j = 0; j < m; j++) {
         const double* w = a + (size_t)na * j;
         for (int k = 0; k < nmat; k++) {
@@ -365,7 +371,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     }
     free_problem(ctx);
     // optional buffers: which of them exist depends on the solver path of THIS problem
-    ctx->init_part = nullptr; ctx->init_bar = nullptr; ctx->persist_bar = nullptr; ctx->init_coop_cap = -1;
+    ctx->init_part = nullptr; ctx->init_bar = nullptr; ctx->persist_bar = nullptr; ctx->init_coop_cap = -1; ctx->S_zeroed = false;
     ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr;
     ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr; ctx->pt_pt = nullptr;
     ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
