@@ -420,3 +420,34 @@ def test_many_clusters_implicit_path():
     assert out[0]["old_cost"] == out[1]["old_cost"]
     assert rel(out[0]["new_cost"], out[1]["new_cost"]) <= COST_RTOL
 
+
+def test_long_tracks_fall_back_to_untiled_kernels():
+    """Points seen by more than 512 cameras do not fit a point tile: the stage-1 point pass, the back-substitution
+    and the implicit PCG point sweep fall back to their thread-per-point forms.  All three solvers must still agree
+    with each other and with the tiled result structure (first step accepted, same cost)."""
+    rng = np.random.default_rng(5)
+    P = synth.make_problem(640, 300, 5000, seed=9)
+    # rebuild the observation list so that every point is seen by every camera (tracks of 640)
+    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T); b = np.ascontiguousarray(P.Xe[:3].T)
+    m, n = P.m, P.n
+    cam = np.repeat(np.arange(m, dtype=np.int32), n)
+    pt = np.tile(np.arange(n, dtype=np.int32), m)
+    # observations = exact projections of the initial estimate + noise (so the problem is well posed)
+    ctx = capi.Context(num_variableK=0, solver=capi.SOLVER_CHOL)
+    xy0 = np.zeros((m * n, 2))
+    ctx.set_problem_sparse(P.K.T, a, b, xy0, pt, cam)
+    xhat = ctx.get_jacobians()["X_hat"]
+    ctx.close()
+    xy = np.ascontiguousarray(xhat + rng.normal(0.0, 0.5, xhat.shape))
+    res = {}
+    for solver in (capi.SOLVER_CHOL, capi.SOLVER_PCG, capi.SOLVER_PCG_EXPLICIT):
+        ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=1e-11)
+        ctx.set_problem_sparse(P.K.T, a, b, xy, pt, cam)
+        info = ctx.trial_step()
+        assert info["solver_used"] == solver and info["accepted"], (solver, info)
+        res[solver] = info
+        ctx.close()
+    for solver in (capi.SOLVER_PCG, capi.SOLVER_PCG_EXPLICIT):
+        assert res[solver]["old_cost"] == res[capi.SOLVER_CHOL]["old_cost"]
+        assert rel(res[solver]["new_cost"], res[capi.SOLVER_CHOL]["new_cost"]) <= COST_RTOL, (solver, res)
+
