@@ -60,7 +60,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors",
 ]
 
 
@@ -208,6 +208,16 @@ class Context:
         it, it2 = C.c_int(), C.c_int()
         self._ck(self._L.vlg_ba_get_state(self._h, _d(a), _d(b), C.byref(lam), C.byref(nu), C.byref(it), C.byref(it2)))
         return dict(a=a, b=b, lam=lam.value, nu=nu.value, iter=it.value, iter2=it2.value)
+
+    def reproj_errors(self, depth_max: float = 10.0) -> dict:
+        """error_reproj.m / remove_outlier statistics of the current state (vlg_ba_reproj_errors)."""
+        no = self.nobs
+        err = np.zeros(no); depth = np.zeros(no)
+        mean, mx = C.c_double(), C.c_double()
+        arg, nbad = C.c_int64(), C.c_int64()
+        self._ck(self._L.vlg_ba_reproj_errors(self._h, C.c_double(depth_max), _d(err), _d(depth), C.byref(mean), C.byref(mx),
+                                              C.byref(arg), C.byref(nbad)))
+        return dict(err=err, depth=depth, mean_err=mean.value, max_sq_err=mx.value, argmax=arg.value, n_bad_depth=nbad.value)
 
     # ---- stages
     def stage1(self) -> float:

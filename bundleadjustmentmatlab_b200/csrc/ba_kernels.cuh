@@ -1073,4 +1073,78 @@ __global__ void __launch_bounds__(1024) k_denom_cam(int N, const double* __restr
     if (threadIdx.x == 0) *out = v;
 }
 
+// ---------------------------------------------------------------------------------------
+// reprojection-error map of the current state on the observation list:
+// error_reproj.m:72-84 (err(i,j) = ||x(1:2,i,j) - x_reproj(1:2)||) and the statistics of
+// remove_outlier (incr_reconstruction.m:363-390: depth test x_reproj(3) < 0 || > depth_max, largest
+// squared error and where).  One thread per observation; the projection is project_R / project_P.
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__global__ void k_reproj_errors(int64_t nobs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_pt,
+                                const int* __restrict__ obs_cam, const double* __restrict__ K4, const double* __restrict__ a,
+                                const double* __restrict__ b, const double* __restrict__ rtab /* [m][4][9] */,
+                                double depth_max, double* __restrict__ err, double* __restrict__ depth,
+                                double* __restrict__ bad /* 1.0 where the depth test fails */)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nobs) return;
+    const int i = obs_pt[o], j = obs_cam[o];
+    const double b0 = b[(size_t)3 * i], b1 = b[(size_t)3 * i + 1], b2 = b[(size_t)3 * i + 2];
+    double x, y, z;
+    if constexpr (NA == kNaProjective) {
+        double Pl[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) Pl[k] = __ldg(a + (size_t)NA * j + k);
+        project_P(Pl, b0, b1, b2, x, y);
+        z = VLG_P(VLG_P(VLG_P(VLG_M(Pl[2], b0), VLG_M(Pl[5], b1)), VLG_M(Pl[8], b2)), Pl[11]);
+    } else {
+        double R[9], al[NA], Kl[4];
+#pragma unroll
+        for (int k = 0; k < 9; k++) R[k] = __ldg(rtab + (size_t)36 * j + k);
+#pragma unroll
+        for (int k = 3; k < NA; k++) al[k] = __ldg(a + (size_t)NA * j + k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
+        double fx, fy, cx, cy;
+        effective_K<NA>(Kl, al, fx, fy, cx, cy);
+        project_R(R, al[3], al[4], al[5], fx, fy, cx, cy, b0, b1, b2, x, y);
+        z = VLG_P(VLG_P(VLG_P(VLG_M(R[2], b0), VLG_M(R[5], b1)), VLG_M(R[8], b2)), al[5]);
+    }
+    const double2 xy = obs_xy[o];
+    const double dx = xy.x - x, dy = xy.y - y;
+    const bool isbad = z < 0.0 || z > depth_max;
+    err[o] = sqrt(dx * dx + dy * dy);
+    depth[o] = z;
+    bad[o] = isbad ? 1.0 : 0.0;
+}
+
+// largest squared error over the observations that pass the depth test, first occurrence in list order
+// (remove_outlier uses a strict '>' while walking j outer / i inner = the list order); one CTA.
+__global__ void __launch_bounds__(1024) k_argmax_sq(int64_t nobs, const double* __restrict__ err, const double* __restrict__ bad,
+                                                    double* __restrict__ out_val, long long* __restrict__ out_idx)
+{
+    __shared__ double sv[1024];
+    __shared__ long long si[1024];
+    double best = -1.0;
+    long long bi = -1;
+    for (int64_t o = threadIdx.x; o < nobs; o += 1024) {
+        if (bad[o] != 0.0) continue;
+        const double v = err[o] * err[o];
+        if (v > best) { best = v; bi = o; }
+    }
+    sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double v = sv[threadIdx.x + s];
+            const long long k = si[threadIdx.x + s];
+            if (v > sv[threadIdx.x] || (v == sv[threadIdx.x] && k >= 0 && (si[threadIdx.x] < 0 || k < si[threadIdx.x]))) {
+                sv[threadIdx.x] = v; si[threadIdx.x] = k;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *out_val = sv[0] < 0.0 ? 0.0 : sv[0]; *out_idx = si[0]; }
+}
+
 }  // namespace vlgba

@@ -44,6 +44,20 @@ int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S, int ccams = 0)
     return VLG_BA_OK;
 }
 
+// reprojection-error map of the current state (vlg_ba_reproj_errors)
+template <int NA>
+int run_reproj_errors(vlg_ba_ctx* ctx, double depth_max, double* d_err, double* d_depth, double* d_bad)
+{
+    CHK(run_rtab<NA>(ctx, ctx->h_a, ctx->a, 4, ctx->h_rtab, ctx->rtab));
+    if (ctx->nobs > 0) {
+        k_reproj_errors<NA><<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->obs_xy, ctx->obs_pt, ctx->obs_cam, ctx->K4, ctx->a,
+                                                                          ctx->b, ctx->rtab, depth_max, d_err, d_depth, d_bad);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return VLG_BA_OK;
+}
+
 // damping + V*^-1 + camera-keyed Schur sums + (Cholesky: S, factor, solve | PCG)  ->  da
 template <int NA>
 int run_stage2(vlg_ba_ctx* ctx, double lambda)
@@ -811,6 +825,44 @@ int vlg_ba_get_reduced(vlg_ba_ctx* ctx, double* Vinv, double* S, double* e_, dou
     }
     CU(cudaStreamSynchronize(ctx->stream));
     return VLG_BA_OK;
+}
+
+int vlg_ba_reproj_errors(vlg_ba_ctx* ctx, double depth_max, double* err, double* depth, double* mean_err, double* max_sq_err,
+                         int64_t* argmax, int64_t* n_bad_depth)
+{
+    if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
+    CU(cudaSetDevice(ctx->device));
+    const size_t no = (size_t)ctx->nobs;
+    double *d_err = nullptr, *d_depth = nullptr, *d_bad = nullptr, *d_sc = nullptr;
+    long long* d_idx = nullptr;
+    CU(cudaMalloc(&d_err, sizeof(double) * std::max<size_t>(no, 1)));
+    CU(cudaMalloc(&d_depth, sizeof(double) * std::max<size_t>(no, 1)));
+    CU(cudaMalloc(&d_bad, sizeof(double) * std::max<size_t>(no, 1)));
+    CU(cudaMalloc(&d_sc, sizeof(double) * 4));
+    CU(cudaMalloc(&d_idx, sizeof(long long)));
+    auto body = [&]() -> int {
+        CHK(DISPATCH_NA(ctx, run_reproj_errors)(ctx, depth_max, d_err, d_depth, d_bad));
+        CHK(reduce_to(ctx, d_err, no, d_sc));
+        CHK(reduce_to(ctx, d_bad, no, d_sc + 1));
+        k_argmax_sq<<<1, 1024, 0, ctx->stream>>>((int64_t)no, d_err, d_bad, d_sc + 2, d_idx);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        double h[4];
+        long long hi = -1;
+        CHK(download(ctx, h, d_sc, 3));
+        CU(cudaMemcpyAsync(&hi, d_idx, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CHK(download(ctx, err, d_err, no));
+        CHK(download(ctx, depth, d_depth, no));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (mean_err) *mean_err = no ? h[0] / (double)no : 0.0;
+        if (n_bad_depth) *n_bad_depth = (int64_t)(h[1] + 0.5);
+        if (max_sq_err) *max_sq_err = h[2];
+        if (argmax) *argmax = (int64_t)hi;
+        return VLG_BA_OK;
+    };
+    const int r = body();
+    cudaFree(d_err); cudaFree(d_depth); cudaFree(d_bad); cudaFree(d_sc); cudaFree(d_idx);
+    return r;
 }
 
 int vlg_ba_set_da(vlg_ba_ctx* ctx, const double* da)

@@ -121,6 +121,16 @@ int  vlg_ba_set_comm(vlg_ba_ctx *ctx, int rank, int nranks, const void *unique_i
 int  vlg_ba_p2p_export(vlg_ba_ctx *ctx, void *ipc_handle_64);
 int  vlg_ba_p2p_import(vlg_ba_ctx *ctx, const void *ipc_handles /* nranks x 64 bytes */);
 
+/* Reprojection-error map of the CURRENT state on the observation list (toolbox/test/error_reproj.m:72-84) and the
+ * statistics remove_outlier() derives from it (toolbox/geometry/incr_reconstruction.m:363-390):
+ *   err[t]   = || x(1:2) - x_reproj(1:2) ||  of observation t (list order);  depth[t] = x_reproj(3) before division;
+ *   *mean_err = sum(err) / nobs  (error_reproj's `err`);  *n_bad_depth = #{ depth < 0 or depth > depth_max };
+ *   *max_sq_err / *argmax = largest squared error among the observations that pass the depth test and its index
+ *   (first occurrence, the reference's strict '>' in list order).  err / depth may be NULL.  All points are treated as
+ *   finite (the reference skips points with X(4,i) != 1). */
+int  vlg_ba_reproj_errors(vlg_ba_ctx *ctx, double depth_max, double *err, double *depth, double *mean_err,
+                          double *max_sq_err, int64_t *argmax, int64_t *n_bad_depth);
+
 /* Problem definition.  Replaces the argument packing of bundle_euclid.m:81-102 and the
  * positional inputs of mex_bundle_1_XABeUVWeAeB.c:76-83.  `pivot` (m doubles or NULL) is
  * the 'fix_pivot' mask (bundle_euclid.m:150-154); non-zero = camera held fixed. */

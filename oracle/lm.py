@@ -593,6 +593,62 @@ def bundle_projective(Pp, Xp, x, *opts, record=True, max_iter=20, max_iter2=10):
 
 
 # ----------------------------------------------------------------------------------
+# reprojection-error map: toolbox/test/error_reproj.m:1-88 and remove_outlier, incr_reconstruction.m:354-414
+# ----------------------------------------------------------------------------------
+def _rodr(w):
+    """vl_rodr, the formula of oracle/shim/vl/rodrigues.h."""
+    th = float(np.sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]))
+    if th < 1e-6:
+        return np.eye(3)
+    x, y, z = w[0] / th, w[1] / th, w[2] / th
+    s, c = np.sin(th), np.cos(th)
+    mc = 1.0 - c
+    return np.array([[1 - mc * (y * y + z * z), -s * z + mc * x * y, s * y + mc * x * z],
+                     [s * z + mc * x * y, 1 - mc * (z * z + x * x), -s * x + mc * y * z],
+                     [-s * y + mc * x * z, s * x + mc * y * z, 1 - mc * (x * x + y * y)]])
+
+
+def error_reproj(x, K, T, w, X, vis=None):
+    """[err error] = error_reproj(x, K, T, w, X, 'visibility', vis)  (error_reproj.m:1-88), K as 4 x m parameters.
+    Restated literally, including its test `vis(n,m)` (the LAST cell, error_reproj.m:76) where `vis(i,j)` was meant:
+    with the last cell visible every cell is evaluated, also the invisible ones."""
+    m, n = T.shape[1], X.shape[1]
+    if vis is None:
+        vis = np.ones((n, m))
+    error = np.zeros((n, m))
+    for j in range(m):
+        Kj = np.array([[K[0, j], 0, K[2, j]], [0, K[1, j], K[3, j]], [0, 0, 1]])      # calibration_matrix.m:9-11
+        Pj = Kj @ np.hstack([_rodr(w[:, j]), T[:, j:j + 1]])
+        for i in range(n):
+            if X[3, i] == 1 and vis[n - 1, m - 1]:
+                xr = Pj @ X[:, i]
+                xr = xr / xr[2]
+                error[i, j] = np.linalg.norm(x[0:2, i, j] - xr[0:2])
+    return float(error.sum() / vis.sum()), error
+
+
+def remove_outlier_stats(K, T, Omega, X, x, vis, depth_max=10.0):
+    """The quantities remove_outlier() computes before it edits vis / X (incr_reconstruction.m:363-390):
+    number of cells failing the depth test, largest squared reprojection error and its (point, frame), 0-based."""
+    m, n = K.shape[1], X.shape[1]
+    max_error, arg, negative = 0.0, (-1, -1), 0
+    for j in range(m):
+        Kj = np.array([[K[0, j], 0, K[2, j]], [0, K[1, j], K[3, j]], [0, 0, 1]])
+        Pj = Kj @ np.hstack([_rodr(Omega[:, j]), T[:, j:j + 1]])
+        for i in range(n):
+            if X[3, i] == 1 and vis[i, j]:
+                xr = Pj @ X[:, i]
+                if xr[2] < 0 or xr[2] > depth_max:
+                    negative += 1
+                else:
+                    xr = xr / xr[2]
+                    e = float(np.linalg.norm(x[0:2, i, j] - xr[0:2]) ** 2)
+                    if e > max_error:
+                        max_error, arg = e, (i, j)
+    return dict(n_bad_depth=negative, max_sq_err=max_error, argmax=arg)
+
+
+# ----------------------------------------------------------------------------------
 # CPU arm for the large configurations (port, PCG solve) -- see oracle_sparse.c
 # ----------------------------------------------------------------------------------
 def trial_step_pcg(K, a, b, obs: ObsList, lam, pcg_rtol=1e-8, pcg_max_iter=500):

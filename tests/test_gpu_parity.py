@@ -451,3 +451,32 @@ def test_long_tracks_fall_back_to_untiled_kernels():
         assert res[solver]["old_cost"] == res[capi.SOLVER_CHOL]["old_cost"]
         assert rel(res[solver]["new_cost"], res[capi.SOLVER_CHOL]["new_cost"]) <= COST_RTOL, (solver, res)
 
+
+def test_reprojection_error_map_vs_error_reproj():
+    """vlg_ba_reproj_errors against the restated error_reproj.m / remove_outlier
+    (oracle/lm.py).  Fully visible problem, so that error_reproj.m's `vis(n,m)` slip (it tests the last cell instead of
+    cell (i,j)) does not matter; a few points are pushed behind their cameras to exercise the depth test."""
+    P = synth.make_problem(5, 40, 200, seed=17)
+    m, n = P.m, P.n
+    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T); b = np.ascontiguousarray(P.Xe[:3].T).copy()
+    b[3] *= -1.0; b[11] *= -1.0                                   # behind the cameras
+    cam = np.repeat(np.arange(m, dtype=np.int32), n); pt = np.tile(np.arange(n, dtype=np.int32), m)
+    rng = np.random.default_rng(3)
+    xy = rng.uniform(0.0, 500.0, (m * n, 2))
+    x = np.zeros((3, n, m)); x[0, pt, cam] = xy[:, 0]; x[1, pt, cam] = xy[:, 1]; x[2] = 1.0
+    X4 = np.vstack([b.T, np.ones((1, n))])
+    vis = np.ones((n, m))
+    ctx = capi.Context(num_variableK=0)
+    ctx.set_problem_sparse(P.K.T, a, b, xy, pt, cam)
+    depth_max = 1e4
+    g = ctx.reproj_errors(depth_max=depth_max)
+    ctx.close()
+    err_ref, emap = lm.error_reproj(x, P.K, P.Te, P.w, X4, vis)
+    st = lm.remove_outlier_stats(P.K, P.Te, P.w, X4, x, vis, depth_max=depth_max)
+    got = np.zeros((n, m)); got[pt, cam] = g["err"]
+    assert np.abs(got - emap).max() <= 1e-10 * emap.max()
+    assert rel(g["mean_err"], err_ref) <= 1e-12
+    assert g["n_bad_depth"] == st["n_bad_depth"] and g["n_bad_depth"] >= 2
+    assert rel(g["max_sq_err"], st["max_sq_err"]) <= 1e-10
+    assert (int(pt[g["argmax"]]), int(cam[g["argmax"]])) == st["argmax"]
+
