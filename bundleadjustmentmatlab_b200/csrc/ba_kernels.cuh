@@ -49,7 +49,7 @@ struct Stage1Args {
 // the reference.
 // ---------------------------------------------------------------------------------------
 template <int NA, bool DIAG>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NA == 6 ? 4 : 1)      // NA = 6: <= 128 registers, 4 CTAs (16 warps) per SM
 k_stage1_cam(Stage1Args p)
 {
     constexpr int NU = nu_of(NA);
