@@ -239,7 +239,7 @@ def run_ours(args):
     if p2p:
         # the per-iteration PCG vector goes through NVLink peer-memory mailboxes (CUDA IPC), not NCCL
         mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
-        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        allh = [torch.zeros(capi.P2P_HANDLE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
         dist.all_gather(allh, mine)
         ctx.p2p_import(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
 

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvlgba.so")
 
 SOLVER_AUTO, SOLVER_CHOL, SOLVER_PCG, SOLVER_PCG_EXPLICIT = 0, 1, 2, 3
 MODEL_EUCLID, MODEL_PROJECTIVE = 0, 1
+P2P_HANDLE_BYTES = 128      # VLG_BA_P2P_HANDLE_BYTES
 RTABLE_HOST_LIBM, RTABLE_DEVICE = 0, 1
 ORDER_CHUNKED, ORDER_REFERENCE = 0, 1
 
@@ -150,13 +151,13 @@ class Context:
         self._ck(self._L.vlg_ba_set_comm(self._h, C.c_int(rank), C.c_int(nranks), C.c_char_p(unique_id)))
 
     def p2p_export(self) -> bytes:
-        """64-byte CUDA IPC handle of this rank's PCG mailbox (after set_comm and set_problem_*)."""
-        buf = C.create_string_buffer(64)
+        """P2P_HANDLE_BYTES of CUDA IPC handles (PCG mailbox, share of S) of this rank (after set_comm and set_problem_*)."""
+        buf = C.create_string_buffer(P2P_HANDLE_BYTES)
         self._ck(self._L.vlg_ba_p2p_export(self._h, buf))
         return buf.raw
 
     def p2p_import(self, handles: bytes):
-        """`handles`: the ranks' 64-byte handles concatenated in rank order."""
+        """`handles`: the ranks' P2P_HANDLE_BYTES blobs concatenated in rank order."""
         self._ck(self._L.vlg_ba_p2p_import(self._h, C.c_char_p(handles)))
 
     # ---- problem

@@ -1305,7 +1305,7 @@ __device__ __forceinline__ double p2p_allreduce_elem(const P2PMail& mb, unsigned
 __global__ void __launch_bounds__(1024)
 k_symv_finish(int Np, int N, double sign, const double* __restrict__ rowpart, const double* __restrict__ colpart,
               const int* __restrict__ done, double* __restrict__ out, const P2PMail* __restrict__ mb = nullptr,
-              unsigned int epoch = 0)
+              unsigned int epoch = 0, int J0 = 0, int J1 = 1 << 30 /* strips [J0, J1) are this rank's (multi-GPU split of S) */)
 {
     __shared__ double red[32][33];
     if (done && *done) return;
@@ -1313,12 +1313,13 @@ k_symv_finish(int Np, int N, double sign, const double* __restrict__ rowpart, co
     const int r = blockIdx.x * 32 + lane;
     const int jb = blockIdx.x;                       // r / 32: strips 0..jb have this row
     double s = 0.0;
-    for (int J = g; J <= jb; J += 32) s += __ldcs(rowpart + (size_t)J * Np + r);
+    const int jend = min(jb, J1 - 1);
+    for (int J = J0 + g; J <= jend; J += 32) s += __ldcs(rowpart + (size_t)J * Np + r);
     red[g][lane] = s;
     __syncthreads();
     if (g == 0 && r < N) {
         double y = 0.0;
-        const int nseg = (Np - kSymvCols * jb + kSymvSegRows - 1) / kSymvSegRows;
+        const int nseg = (jb >= J0 && jb < J1) ? (Np - kSymvCols * jb + kSymvSegRows - 1) / kSymvSegRows : 0;
         for (int sg = 0; sg < nseg; sg++) y += __ldcs(colpart + (size_t)sg * Np + r);
 #pragma unroll
         for (int q = 0; q < 32; q++) y += red[q][lane];
@@ -1423,6 +1424,7 @@ struct PcgPersistArgs {
     const P2PMail* mb;               // multi-GPU exchange or NULL
     unsigned int epoch0;             // mailbox epoch of the first matvec of this launch
     long long* prof;                 // optional: clock64 totals per phase seen by CTA 0 / thread 0 (VLG_BA_PERSIST_PROF), or NULL
+    int J0, J1;                      // strips of S this rank multiplies (all of them on one GPU)
 };
 
 #define PCG_PROF(slot)                                                           \
@@ -1498,14 +1500,16 @@ k_pcg_persistent(PcgPersistArgs a)
                 double acc = 0.0;
                 if (have) {
                     // terms 0..rb: row partials of strips 0..rb; then the column partials of this block's segments
-                    const int nseg = (a.Np - kSymvCols * rb + kSymvSegRows - 1) / kSymvSegRows;
-                    const int nterm = rb + 1 + nseg;
+                    // (multi-GPU split of S: only this rank's strips [J0, J1) have partials)
+                    const int nseg = (rb >= a.J0 && rb < a.J1) ? (a.Np - kSymvCols * rb + kSymvSegRows - 1) / kSymvSegRows : 0;
+                    const int nrow = max(0, min(rb, a.J1 - 1) - a.J0 + 1);
+                    const int nterm = nrow + nseg;
                     for (int q0 = gq; q0 < nterm; q0 += 128) {
                         double v[16];
 #pragma unroll
                         for (int u = 0; u < 16; u++) {
                             const int tq = q0 + 8 * u;
-                            const double* src = tq <= rb ? a.rowpart + (size_t)tq * a.Np + r : a.colpart + (size_t)(tq - rb - 1) * a.Np + r;
+                            const double* src = tq < nrow ? a.rowpart + (size_t)(a.J0 + tq) * a.Np + r : a.colpart + (size_t)(tq - nrow) * a.Np + r;
                             v[u] = tq < nterm ? __ldcg(src) : 0.0;
                         }
 #pragma unroll
@@ -1711,5 +1715,29 @@ k_pcg_persistent(PcgPersistArgs a)
     }
 }
 
-}  // namespace vlgba
+// ---- multi-GPU: sum of the ranks' shares of S, column block by column block, over peer memory -----------
+// Every rank assembles its share of S (its points) in full.  Rank r then PULLS the column block it will
+// multiply (strips [J0, J1)) from every peer's S through NVLink (CUDA-IPC mapped pointers) and adds the
+// shares in rank order -- only the rows the symmetric matvec reads (row >= 32 J, i.e. the lower triangle
+// and the full diagonal tile).  One thread block per column, 16-byte loads along the column.  (A grouped
+// ncclReduce per block did the same in 1.1 ms at 2 GPUs but serialised to ~24 ms at 8.)
+struct PeerS { const double* S[kP2pMaxRanks]; int nranks, rank; };
 
+__global__ void __launch_bounds__(256)
+k_pull_reduce_block(PeerS ps, int Np, int J0, double* __restrict__ Sown)
+{
+    const int col = kSymvCols * J0 + blockIdx.x;            // global column
+    const int r0 = kSymvCols * (col / kSymvCols);           // first row the matvec reads in this column
+    const size_t off = (size_t)Np * col;
+    for (int r = r0 + 2 * threadIdx.x; r < Np; r += 2 * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int q = 0; q < ps.nranks; q++) {
+            const double2 v = q == ps.rank ? *reinterpret_cast<const double2*>(Sown + off + r)
+                                           : __ldcs(reinterpret_cast<const double2*>(ps.S[q] + off + r));
+            acc.x += v.x; acc.y += v.y;
+        }
+        *reinterpret_cast<double2*>(Sown + off + r) = acc;
+    }
+}
+
+}  // namespace vlgba

@@ -11,7 +11,6 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
-#include <omp.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -36,6 +35,9 @@ struct NcclApi {
     int (*GetUniqueId)(nccl_uid*) = nullptr;
     int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(nccl_comm) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -54,6 +56,9 @@ bool nccl_load()
     g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(g_nccl.h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(g_nccl.h, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.Reduce = (int (*)(const void*, void*, size_t, int, int, int, nccl_comm, cudaStream_t))dlsym(g_nccl.h, "ncclReduce");
+    g_nccl.GroupStart = (int (*)())dlsym(g_nccl.h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.h, "ncclGroupEnd");
     g_nccl.CommDestroy = (int (*)(nccl_comm))dlsym(g_nccl.h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
     return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
@@ -95,6 +100,9 @@ struct vlg_ba_ctx {
     double* init_part = nullptr;           // its block partials [17 x coop_grid]
     int init_coop_cap = -1;                // CTAs of k_pcg_init_defl_coop that can be co-resident (-1: not asked yet)
     bool persist_ok = false;
+    bool s_split = false;                  // multi-GPU: S is reduce-scattered by column blocks, each rank multiplies its own
+    int s_J0 = 0, s_J1 = 0;                // this rank's strips [J0, J1)
+    std::vector<int> s_bounds;             // strip boundaries of all ranks (nranks + 1), equal lower-triangle areas
     bool S_zeroed = false;                 // explicit-S PCG: structurally zero blocks of S cleared for this problem
     double *Cblk = nullptr, *McL = nullptr;   // cluster-Jacobi preconditioner: gathered diagonal blocks of S, their inverses [coop_grid][128 x 128]
     int Np = 0;               // padded order of S
@@ -167,6 +175,9 @@ struct vlg_ba_ctx {
     std::vector<void*> p2p_peer_base;     // opened peer mailboxes (own entry = p2p_base)
     P2PMail p2p;
     P2PMail* p2p_dev = nullptr;           // device copy (argument of k_symv_finish)
+    PeerS peer_S;                         // peers' S allocations (IPC), for the column-block pull
+    bool peer_S_ready = false;
+    std::vector<void*> p2p_peer_S;        // opened peer S mappings
     bool p2p_ready = false;
     unsigned int p2p_epoch = 0;
     // accounting
@@ -314,10 +325,8 @@ void rodrigues_host(double w0, double w1, double w2, double* R)
 void rtab_host(int m, int na, const double* a, int nmat, double* out)
 {
     const double h = 1e-10;
-    // cameras are independent: a few host threads (explicit count: torchrun exports OMP_NUM_THREADS=1) take the
-    // 0.3 ms of libm calls at Venice shape off the critical path between two GPU stages
-    const int nthr = m >= 256 ? std::max(1, std::min(8, omp_get_num_procs())) : 1;
-#pragma omp parallel for num_threads(nthr) schedule(static)
+    // serial on purpose: a host thread team per rank (8 ranks x 8 spinning libgomp threads) cost 20 ms per LM step on
+    // the 8-GPU box, while the table itself is ~0.1 ms at Venice shape
     for (int j = 0; j < m; j++) {
         const double* w = a + (size_t)na * j;
         for (int k = 0; k < nmat; k++) {
@@ -371,7 +380,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     }
     free_problem(ctx);
     // optional buffers: which of them exist depends on the solver path of THIS problem
-    ctx->init_part = nullptr; ctx->init_bar = nullptr; ctx->persist_bar = nullptr; ctx->init_coop_cap = -1; ctx->S_zeroed = false;
+    ctx->init_part = nullptr; ctx->init_bar = nullptr; ctx->persist_bar = nullptr; ctx->init_coop_cap = -1; ctx->S_zeroed = false; ctx->s_split = false;
     ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr;
     ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr; ctx->pt_pt = nullptr;
     ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
@@ -591,6 +600,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(dalloc(ctx, &ctx->pcg_sc, 1));
     CHK(dalloc(ctx, &ctx->db, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->denom_pt, (size_t)n));
     CHK(dalloc(ctx, &ctx->cost_obs, (size_t)nobs)); CHK(dalloc(ctx, &ctx->scal3, 4));
+    CU(cudaMemsetAsync(ctx->scal3, 0, 4 * sizeof(double), ctx->stream));      // scal3[3] doubles as the operand of barrier all-reduces
     ctx->coop_grid = 0;
     if (!ctx->use_chol) {
         int coop = 0, nsm = 0;
@@ -622,7 +632,22 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         const int Np = ctx->Np, nstrips = Np / kSymvCols;
         struct Item { int strip, seg, r0, rows; };
         std::vector<Item> items;
-        for (int J = 0; J < nstrips; J++)
+        // multi-GPU (set_comm before set_problem): every rank assembles its share of S in full, one grouped
+        // ncclReduce per LM step leaves rank r with the SUM of its column block (strips [J_r, J_r+1), chosen so
+        // that every rank gets the same lower-triangle area), and the matvec of rank r only walks those strips;
+        // the partial products meet in the same vector exchange as before
+        ctx->s_split = ctx->nranks > 1 && g_nccl.Reduce && g_nccl.GroupStart && g_nccl.GroupEnd;
+        ctx->s_bounds.assign((size_t)ctx->nranks + 1, nstrips);
+        ctx->s_bounds[0] = 0;
+        if (ctx->s_split) {
+            // strip J of the lower triangle has nstrips - J tiles: boundaries of equal area
+            for (int r = 1; r < ctx->nranks; r++)
+                ctx->s_bounds[(size_t)r] = std::min(nstrips, std::max(ctx->s_bounds[(size_t)r - 1],
+                                                    (int)lround(nstrips * (1.0 - sqrt(1.0 - (double)r / ctx->nranks)))));
+        }
+        ctx->s_J0 = ctx->s_split ? ctx->s_bounds[(size_t)ctx->rank] : 0;
+        ctx->s_J1 = ctx->s_split ? ctx->s_bounds[(size_t)ctx->rank + 1] : nstrips;
+        for (int J = ctx->s_J0; J < ctx->s_J1; J++)
             for (int sg = 0, r0 = kSymvCols * J; r0 < Np; sg++, r0 += kSymvSegRows)
                 items.push_back({J, sg, r0, std::min(kSymvSegRows, Np - r0)});
         std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.rows > b.rows; });
@@ -672,7 +697,9 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         const int64_t tiles = (int64_t)nb * (nb + 1) / 2;
         ctx->chol_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->nsm, (tiles + kCholWarps - 1) / kCholWarps));
     }
-    if (need_S) CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));
+    if (need_S) {
+        CHK(dalloc(ctx, &ctx->S, (size_t)ctx->Np * ctx->Np));
+    }
     if (need_S || cluster_blocks) {
         CHK(dalloc(ctx, &ctx->blk_j, (size_t)ctx->nblocks)); CHK(dalloc(ctx, &ctx->blk_k, (size_t)ctx->nblocks));
         CHK(dalloc(ctx, &ctx->blk_ptr, (size_t)ctx->nblocks + 1)); CHK(dalloc(ctx, &ctx->pairs, (size_t)ctx->npairs));

@@ -131,6 +131,10 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             if (!ctx->S_zeroed) {
                 CU(cudaMemsetAsync(ctx->S, 0, sizeof(double) * (size_t)ctx->Np * ctx->Np, ctx->stream));
                 ctx->S_zeroed = true;
+            } else if (ctx->s_split) {
+                // this rank's column block holds last step's SUM over ranks, whose pattern is wider than the local one
+                const size_t off = (size_t)ctx->Np * kSymvCols * ctx->s_J0, cnt = (size_t)ctx->Np * kSymvCols * (ctx->s_J1 - ctx->s_J0);
+                if (cnt) CU(cudaMemsetAsync(ctx->S + off, 0, sizeof(double) * cnt, ctx->stream));
             }
             CHK(assemble_S<NA>(ctx, 0, ctx->S));
         }
@@ -179,6 +183,33 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         if (ring_cam) CU(cudaFuncSetAttribute(k_sweep_cam_ring<NA, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ring_cam));
         if (ring_pt) CU(cudaFuncSetAttribute(k_sweep_pt_ring<NA, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ring_pt));
         // the two sweeps of W V*^-1 W' v: chunk partials land in qpart (and, all-reduced, in wq)
+        if (ctx->use_explicit && ctx->s_split) {
+            // S <- sum over ranks, column block r on rank r (in place, one grouped ncclReduce per block); the cluster blocks
+            // above were taken from the local shares and all-reduced on their own
+            TimedScope ts(ctx, T_SCHUR_BLK);
+            if (ctx->peer_S_ready) {
+                // every rank's share must be complete before anyone pulls: a 1-element all-reduce is the barrier (the solve
+                // itself keeps the ranks in lockstep afterwards, so nobody rewrites its share while it is being read)
+                CHK(allreduce(ctx, ctx->scal3 + 3, 1));
+                const int ncols = kSymvCols * (ctx->s_J1 - ctx->s_J0);
+                if (ncols > 0) {
+                    k_pull_reduce_block<<<ncols, 256, 0, ctx->stream>>>(ctx->peer_S, ctx->Np, ctx->s_J0, ctx->S);
+                    ctx->launches++;
+                }
+                CU(cudaGetLastError());
+                // ... and before anyone's next assembly overwrites a share, every pull must be over: same barrier
+                CHK(allreduce(ctx, ctx->scal3 + 3, 1));
+            } else {
+            int rc = g_nccl.GroupStart();
+            for (int r = 0; r < ctx->nranks && rc == 0; r++) {
+                const size_t off = (size_t)ctx->Np * kSymvCols * ctx->s_bounds[(size_t)r];
+                const size_t cnt = (size_t)ctx->Np * kSymvCols * (ctx->s_bounds[(size_t)r + 1] - ctx->s_bounds[(size_t)r]);
+                if (cnt) rc = g_nccl.Reduce(ctx->S + off, ctx->S + off, cnt, kNcclFloat64, kNcclSum, r, ctx->comm, ctx->stream);
+            }
+            if (rc == 0) rc = g_nccl.GroupEnd();
+            if (rc != 0) return fail(ctx, VLG_BA_ENCCL, "ncclReduce (column blocks of S): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+            }
+        }
         auto sweeps = [&](const double* v, const int* dn) -> int {
             if (ctx->use_explicit) {
                 // wq = (sum Y W') v = -(S - U*) v from the lower triangle of the assembled S
@@ -188,7 +219,8 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                 const bool fused = ctx->nranks > 1 && ctx->p2p_ready;     // the exchange with the peers happens inside the finish kernel
                 if (fused) ctx->p2p_epoch++;
                 k_symv_finish<<<ctx->Np / 32, 1024, 0, ctx->stream>>>(ctx->Np, N, -1.0, ctx->symv_rowpart, ctx->symv_colpart, dn, ctx->wq,
-                                                                      fused ? ctx->p2p_dev : nullptr, ctx->p2p_epoch);
+                                                                      fused ? ctx->p2p_dev : nullptr, ctx->p2p_epoch,
+                                                                      ctx->s_split ? ctx->s_J0 : 0, ctx->s_split ? ctx->s_J1 : 1 << 30);
                 ctx->launches += 2;
                 CU(cudaGetLastError());
                 if (!fused) CHK(allreduce_pcg_vector(ctx, ctx->wq, N, dn));
@@ -279,6 +311,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             pa.sc = ctx->pcg_sc; pa.blkpart = ctx->blkpart; pa.Z = defl ? ctx->Zd : nullptr; pa.SZ = defl ? ctx->SZd : nullptr;
             pa.ds = ctx->defl_sc; pa.barrier = ctx->persist_bar;
             pa.mb = ctx->nranks > 1 ? ctx->p2p_dev : nullptr; pa.epoch0 = ctx->p2p_epoch + 1;
+            pa.J0 = ctx->s_split ? ctx->s_J0 : 0; pa.J1 = ctx->s_split ? ctx->s_J1 : 1 << 30;
             pa.prof = nullptr;
             static long long* d_prof = nullptr;
             const bool want_prof = getenv("VLG_BA_PERSIST_PROF") != nullptr;
@@ -616,6 +649,10 @@ int vlg_ba_set_comm(vlg_ba_ctx* ctx, int rank, int nranks, const void* unique_id
 
 static void p2p_close(vlg_ba_ctx* ctx)
 {
+    for (void* q : ctx->p2p_peer_S)
+        if (q) cudaIpcCloseMemHandle(q);
+    ctx->p2p_peer_S.clear();
+    ctx->peer_S_ready = false;
     for (size_t r = 0; r < ctx->p2p_peer_base.size(); r++)
         if (ctx->p2p_peer_base[r] && ctx->p2p_peer_base[r] != ctx->p2p_base) cudaIpcCloseMemHandle(ctx->p2p_peer_base[r]);
     ctx->p2p_peer_base.clear();
@@ -644,7 +681,12 @@ int vlg_ba_p2p_export(vlg_ba_ctx* ctx, void* ipc_handle_64)
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, ctx->p2p_base));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memset(ipc_handle_64, 0, VLG_BA_P2P_HANDLE_BYTES);
     memcpy(ipc_handle_64, &h, 64);
+    if (ctx->use_explicit && ctx->s_split && ctx->S) {       // second handle: this rank's share of S
+        CU(cudaIpcGetMemHandle(&h, ctx->S));
+        memcpy((char*)ipc_handle_64 + 64, &h, 64);
+    }
     return VLG_BA_OK;
 }
 
@@ -659,12 +701,39 @@ int vlg_ba_p2p_import(vlg_ba_ctx* ctx, const void* ipc_handles)
         void* base = ctx->p2p_base;
         if (r != mb.rank) {
             cudaIpcMemHandle_t h;
-            memcpy(&h, (const char*)ipc_handles + 64 * (size_t)r, 64);
+            memcpy(&h, (const char*)ipc_handles + VLG_BA_P2P_HANDLE_BYTES * (size_t)r, 64);
             cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) return fail(ctx, VLG_BA_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
         }
         ctx->p2p_peer_base[(size_t)r] = base;
         mb.data[r] = (uint4*)base;
+    }
+    // the peers' shares of S (column-block pull), when every rank exported one
+    ctx->peer_S_ready = false;
+    if (ctx->use_explicit && ctx->s_split && ctx->S) {
+        bool all = true;
+        for (int r = 0; r < mb.nranks && all; r++) {
+            const char* hp = (const char*)ipc_handles + VLG_BA_P2P_HANDLE_BYTES * (size_t)r + 64;
+            bool nz = false;
+            for (int k = 0; k < 64; k++) nz = nz || hp[k] != 0;
+            all = nz;
+        }
+        if (all) {
+            ctx->p2p_peer_S.assign((size_t)mb.nranks, nullptr);
+            ctx->peer_S.nranks = mb.nranks; ctx->peer_S.rank = mb.rank;
+            for (int r = 0; r < mb.nranks; r++) {
+                void* base = ctx->S;
+                if (r != mb.rank) {
+                    cudaIpcMemHandle_t h;
+                    memcpy(&h, (const char*)ipc_handles + VLG_BA_P2P_HANDLE_BYTES * (size_t)r + 64, 64);
+                    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+                    if (e != cudaSuccess) return fail(ctx, VLG_BA_ECUDA, "cudaIpcOpenMemHandle(S of rank %d): %s", r, cudaGetErrorString(e));
+                    ctx->p2p_peer_S[(size_t)r] = base;
+                }
+                ctx->peer_S.S[r] = (const double*)base;
+            }
+            ctx->peer_S_ready = true;
+        }
     }
     CU(cudaMemcpy(ctx->p2p_dev, &mb, sizeof(P2PMail), cudaMemcpyHostToDevice));
     ctx->p2p_epoch = 0;

@@ -113,13 +113,15 @@ const char *vlg_ba_last_error(const vlg_ba_ctx *ctx);      /* ctx may be NULL: e
  * the caller.  After this call the per-camera sums and scalars are all-reduced over ranks. */
 int  vlg_ba_nccl_unique_id(void *unique_id_128);
 int  vlg_ba_set_comm(vlg_ba_ctx *ctx, int rank, int nranks, const void *unique_id_128);
-/* Optional, after set_problem_* on every rank: all-reduce the per-iteration PCG vector through NVLink
- * peer memory instead of ncclAllReduce (one kernel: stores into every peer's mailbox, release/acquire
- * flags, sum in rank order).  Each rank exports the 64-byte CUDA IPC handle of its mailbox, the host
- * gathers them (rank order) and every rank imports the nranks x 64 bytes.  Ranks must be processes on
- * one node with peer access. */
-int  vlg_ba_p2p_export(vlg_ba_ctx *ctx, void *ipc_handle_64);
-int  vlg_ba_p2p_import(vlg_ba_ctx *ctx, const void *ipc_handles /* nranks x 64 bytes */);
+/* Optional, after set_problem_* on every rank: peer-memory paths over NVLink (ranks = processes on one node with
+ * peer access).  (1) the per-iteration PCG vector is all-reduced through mailboxes instead of ncclAllReduce (one kernel:
+ * stores into every peer's mailbox, flags riding with the data, sum in rank order); (2) on the assembled-S path each
+ * rank pulls the column block of S it multiplies from the peers' shares and sums it (instead of every rank multiplying
+ * its own full share).  Each rank exports VLG_BA_P2P_HANDLE_BYTES bytes (two CUDA IPC handles: mailbox, S), the host
+ * gathers them in rank order (any transport) and every rank imports the nranks x VLG_BA_P2P_HANDLE_BYTES bytes. */
+#define VLG_BA_P2P_HANDLE_BYTES 128
+int  vlg_ba_p2p_export(vlg_ba_ctx *ctx, void *ipc_handles_128);
+int  vlg_ba_p2p_import(vlg_ba_ctx *ctx, const void *ipc_handles /* nranks x VLG_BA_P2P_HANDLE_BYTES */);
 
 /* Reprojection-error map of the CURRENT state on the observation list (toolbox/test/error_reproj.m:72-84) and the
  * statistics remove_outlier() derives from it (toolbox/geometry/incr_reconstruction.m:363-390):

@@ -47,9 +47,9 @@ def main():
     lo_hi = shard.point_ranges(np.asarray(P.obs_pt), b.shape[0], world)
     lo, hi = int(lo_hi[rank]), int(lo_hi[rank + 1])
     def exchange_mailboxes(ctx):
-        # every rank's 64-byte CUDA IPC handle, gathered in rank order
+        # every rank's CUDA IPC handles (mailbox, share of S), gathered in rank order
         mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
-        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        allh = [torch.zeros(capi.P2P_HANDLE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
         dist.all_gather(allh, mine)
         ctx.p2p_import(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
 
