@@ -1,6 +1,5 @@
-set -x
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py > gpurun_out/bench_default_r01F.json 2> gpurun_out/bench_F.err
+N=$1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_venice_${N}gpu_r01E.json 2> gpurun_out/bench_${N}gpu_E.err
+echo rc=$?
 python -c "
-import json;d=json.load(open('gpurun_out/bench_default_r01F.json'));print(d['value'],d['ms_per_step'],d['lm_iters_per_sec'],d['e2e'],d['roofline'],d['cpu_baseline']['value'],d['gpu_launches'],d['clocks'])"; tail -3 gpurun_out/bench_F.err
+import json;d=json.loads([l for l in open('gpurun_out/bench_venice_${N}gpu_r01E.json') if l.startswith('{')][0]);print(d['n_gpus'],d['value'],d['ms_per_step'],d['lm_iters_per_sec'],d['e2e']['value'],d['config'].get('pcg_vector_allreduce'),d['pcg_iters'],{k:(v['avg_ms'],v['count']) for k,v in d['kernels'].items()})"; tail -3 gpurun_out/bench_${N}gpu_E.err
