@@ -150,6 +150,39 @@ def mex_bundle_3_db_new(W, da, eB, V_inv, K, a, b, X, visible):
     return db, a_new, b_new, X_hat
 
 
+def mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible):
+    """[X_hat A B e U V W eA eB] = mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible)  (a is 12 x m)."""
+    a, b, X, visible = _F(a), _F(b), _F(X), _F(visible)
+    na, m = a.shape
+    if na != 12:
+        raise ValueError("projective cameras have 12 parameters (a must be 12 x m)")
+    n = b.shape[1]
+    o = [np.zeros(s, order="F") for s in ((2, n, m), (2, na, n, m), (2, 3, n, m), (2, n, m), (na, na, m), (3, 3, n),
+                                          (na, 3, n, m), (na, m), (3, n))]
+    _check(capi.lib().vlg_ba_mex1_dense(_C.c_int(m), _C.c_int(n), _C.c_int(na), None, capi._d(a), capi._d(b),
+                                        capi._d(X), capi._d(visible), *[capi._d(t) for t in o]))
+    return tuple(o)
+
+
+def mex_bundle_proj_2_Se_(Y, W, U_, eA, eB):
+    """[S e_] = mex_bundle_proj_2_Se_(Y, W, U_, eA, eB)  (12-row blocks)."""
+    return mex_bundle_2_Se_(Y, W, U_, eA, eB)
+
+
+def mex_bundle_proj_3_db_new(W, da, eB, V_inv, a, b, X, visible):
+    """[db a_new b_new X_hat] = mex_bundle_proj_3_db_new(W, da, eB, V_inv, a, b, X, visible)."""
+    W, eB, V_inv, a, b, X, visible = _F(W), _F(eB), _F(V_inv), _F(a), _F(b), _F(X), _F(visible)
+    da = np.ascontiguousarray(da, dtype=np.float64).reshape(-1)
+    na, m = a.shape
+    n = b.shape[1]
+    db = np.zeros((3, n), order="F"); a_new = np.zeros((na, m), order="F"); b_new = np.zeros((3, n), order="F")
+    X_hat = np.zeros((2, n, m), order="F")
+    _check(capi.lib().vlg_ba_mex3_dense(_C.c_int(m), _C.c_int(n), _C.c_int(na), capi._d(W), capi._d(da), capi._d(eB),
+                                        capi._d(V_inv), None, capi._d(a), capi._d(b), capi._d(X), capi._d(visible),
+                                        capi._d(db), capi._d(a_new), capi._d(b_new), capi._d(X_hat)))
+    return db, a_new, b_new, X_hat
+
+
 def bundle_projective(Pp, Xp, x, *options, **ctx_opts):
     """[Pp_ Xp_ error_] = bundle_projective(Pp, Xp, x, ...)  -- toolbox/bundle/bundle_projective.m:1-229.
     Pp (3,4,m), Xp (4,n), x (3,n,m); options 'fix_structure', 'fix_motion', 'visibility', vis, 'verbose'."""

@@ -13,7 +13,8 @@ int vlg_ba_mex1_dense(int m, int n, int num_a, const double* K, const double* a,
 {
     vlg_ba_opts o;
     vlg_ba_opts_default(&o);
-    o.num_variableK = num_a - 6;
+    // num_a = 12 (and K = NULL) is the projective model: mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible)
+    if (num_a == kNaProjective) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
     o.order = VLG_BA_ORDER_REFERENCE;            // U, eA in the reference's exact accumulation order
     o.solver = VLG_BA_SOLVER_PCG;                // no block structure needed for stage 1
     vlg_ba_ctx* ctx = nullptr;
@@ -69,7 +70,7 @@ int vlg_ba_mex2_dense(int m, int n, int num_a, const double* Y, const double* W,
     const size_t no = pt.size();
     vlg_ba_opts o;
     vlg_ba_opts_default(&o);
-    o.num_variableK = num_a - 6;
+    if (num_a == kNaProjective) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
     o.solver = VLG_BA_SOLVER_CHOL;               // builds the block structure of S
     vlg_ba_ctx* ctx = nullptr;
     int r = vlg_ba_create(&o, &ctx);
@@ -95,7 +96,7 @@ int vlg_ba_mex2_dense(int m, int n, int num_a, const double* Y, const double* W,
                                                        ctx->pairs, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->Ud, ctx->S, dY);   \
         k_ebar_from_Y<NA_><<<g2, 128, 0, ctx->stream>>>(m, ctx->cam_ptr, ctx->obs_pt, dY, ctx->eA, ctx->eB, ctx->ebar);    \
     } while (0)
-        if (num_a == 6) VLG_MEX2(6); else if (num_a == 7) VLG_MEX2(7); else VLG_MEX2(10);
+        if (num_a == 6) VLG_MEX2(6); else if (num_a == 7) VLG_MEX2(7); else if (num_a == 10) VLG_MEX2(10); else VLG_MEX2(12);
 #undef VLG_MEX2
         ctx->launches += 2;
         CU(cudaGetLastError());
@@ -120,7 +121,8 @@ int vlg_ba_mex3_dense(int m, int n, int num_a, const double* W, const double* da
 {
     vlg_ba_opts o;
     vlg_ba_opts_default(&o);
-    o.num_variableK = num_a - 6;
+    // num_a = 12 (and K = NULL): mex_bundle_proj_3_db_new(W, da, eB, V_inv, a, b, X, visible)
+    if (num_a == kNaProjective) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
     o.solver = VLG_BA_SOLVER_PCG;
     vlg_ba_ctx* ctx = nullptr;
     int r = vlg_ba_create(&o, &ctx);

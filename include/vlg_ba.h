@@ -206,7 +206,11 @@ int  vlg_ba_trial_step_host(vlg_ba_ctx *ctx, const double *a, const double *b,
  *         (mex_bundle_1_XABeUVWeAeB.c:76-83 inputs, :136-175 outputs)
  *   mex2: [S e_] = mex_bundle_2_Se_(Y, W, U_, eA, eB)          (mex_bundle_2_Se_.c:21-27,:59-66)
  *   mex3: [db a_new b_new X_hat] = mex_bundle_3_db_new(W, da, eB, V_inv, K, a, b, X, visible)
- *         (mex_bundle_3_db_new.c:18-29,:67-86) */
+ *         (mex_bundle_3_db_new.c:18-29,:67-86)
+ * num_a = 12 with K = NULL selects the projective model and makes the same three entries the
+ * drop-ins for mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible) (mex_bundle_proj_1_XABeUVWeAeB.c:95-98),
+ * mex_bundle_proj_2_Se_ (mex_bundle_proj_2_Se_.c:22-26) and
+ * mex_bundle_proj_3_db_new(W, da, eB, V_inv, a, b, X, visible) (mex_bundle_proj_3_db_new.c:42-49). */
 int  vlg_ba_mex1_dense(int m, int n, int num_a, const double *K, const double *a, const double *b,
                        const double *X, const double *visible, double *X_hat, double *A, double *B,
                        double *e, double *U, double *V, double *W, double *eA, double *eB);

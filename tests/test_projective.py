@@ -45,11 +45,8 @@ def test_projective_stage1_bit_exact(name):
         assert np.array_equal(J[k], g[k]), f"{k}: {ulp_diff(J[k], g[k])} ulp"
     cost = ctx.stage1()
     blk = ctx.get_blocks()
-    fs = "fix_structure" in g["options"]
-    for k in ("W", "V", "eB", "U", "eA"):
+    for k in ("W", "V", "eB", "U", "eA"):      # golden blocks are post fix_structure (bundle_projective.m:119-123)
         ref = g[k]
-        if k == "W" and fs:
-            ref = np.zeros_like(ref)          # bundle_projective.m:119-123 zeroes V, W, eB after mex1
         assert np.array_equal(blk[k], ref), f"{k}: {ulp_diff(blk[k], ref)} ulp"
     assert rel(cost, float(g["t_old"][0])) <= 1e-13
     ctx.close()
