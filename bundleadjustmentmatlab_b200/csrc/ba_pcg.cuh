@@ -316,82 +316,159 @@ struct Cluster {
     static constexpr int NC = kCams * NA;          // unknowns per cluster (<= 128)
     static constexpr int LD = NC | 1;              // odd row stride in shared memory: conflict-free rows
     static constexpr size_t kSmem = sizeof(double) * (size_t)NC * LD;
+    // second, SHIFTED partition (overlapping additive Schwarz, see k_cluster_inverse): shifted block k covers the
+    // cameras [k kCams - kShift, k kCams + kHalf), i.e. the last kShift cameras of cluster k-1 and the first kHalf
+    // cameras of cluster k
+    static constexpr int kHalf = kCams / 2;
+    static constexpr int kShift = kCams - kHalf;
 };
 
-// Cblk[cl][r + 128 c] = this rank's S block of cluster cl (without U*: added after the all-reduce)
+// Cblk[cl][r + 128 c] = this rank's S block of cluster cl (without U*: added after the all-reduce); `shift` > 0
+// gathers the blocks of the shifted partition (gridDim.x = clusters + 1), cameras outside [0, m) give zeros
 template <int NA>
 __global__ void __launch_bounds__(128)
-k_cluster_gather(int m, int ld, const double* __restrict__ S, double* __restrict__ Cblk)
+k_cluster_gather(int m, int ld, const double* __restrict__ S, double* __restrict__ Cblk, int shift)
 {
     using C = Cluster<NA>;
     const int cl = blockIdx.x, t = threadIdx.x;
-    const int nc = min(C::kCams, m - cl * C::kCams) * NA;
-    const size_t base = (size_t)C::NC * cl;
-    for (int c = 0; c < 128; c++)
-        Cblk[((size_t)cl * 128 + c) * 128 + t] = (t < nc && c < nc) ? S[(base + t) + (size_t)ld * (base + c)] : 0.0;
+    const long long base = (long long)NA * ((long long)cl * C::kCams - shift), N = (long long)NA * m;
+    const long long gr = base + t;
+    const bool rok = t < C::NC && gr >= 0 && gr < N;
+    for (int c = 0; c < 128; c++) {
+        const long long gc = base + c;
+        Cblk[((size_t)cl * 128 + c) * 128 + t] = (rok && c < C::NC && gc >= 0 && gc < N) ? S[gr + (long long)ld * gc] : 0.0;
+    }
 }
 
-// In-place Gauss-Jordan inversion of the cluster block in shared memory (SPD => no pivot search): per
-// pivot every thread updates its half row with INDEPENDENT FMAs against the broadcast pivot row, so the
-// ~30-cycle FP64 latency is hidden (the first version -- Cholesky, triangular inverse, L^-T L^-1 -- was
-// three phases of dependent dot-product chains: 0.66 ms; this one: see DESIGN.md).  Two threads per
-// row.  A non-positive pivot eliminates its row and column (zero row/column of the inverse).
+// In-place Gauss-Jordan inversion of a cluster block (SPD => no pivot search).  The block lives in REGISTERS:
+// 256 threads as a 16 x 16 grid, thread (ty, tx) owns the 8 x 8 elements (ty + 16 i, tx + 16 j).  Per pivot k the
+// owners of row k and of column k publish them through shared memory (double-buffered: one barrier per pivot)
+// and every thread does 64 independent FMAs on its registers against 8 + 8 broadcast values -- the first
+// version kept the block in shared memory and was bound by its bandwidth (3 accesses per FMA: 0.36 ms for 85
+// blocks at Venice shape; this one: see DESIGN.md).  The pivot loop is unrolled over i (the register index of
+// the pivot row/column must be static) and runs over the 16 owners inside.  A non-positive pivot eliminates
+// its row and column (zero row/column of the inverse: pinv-like, as sym_pinv and the dense Cholesky do).
+//
+// shift == 0: block cl = cluster cl, inverse -> McL[cl] (column-major, ld 128, symmetric by construction).
+// shift  > 0: block cl of the shifted partition.  Its rows go to the COMPOSITE Mc2: cluster c's unknown t gets
+//   the row of the shifted block that contains its camera -- block c for the first kHalf cameras of the
+//   cluster (block rows kShift NA + t), block c + 1 for the rest (block rows t - kHalf NA) -- as
+//   Mc2[c][t + 128 col], col = the block's column.  z = (M1^-1 + M2^-1) r is then two 126-term dot products
+//   per unknown, the second against the r of the cameras [c kCams - kShift, ...) or [c kCams + kHalf, ...).
 template <int NA>
 __global__ void __launch_bounds__(256)
-k_cluster_inverse(int m, int add_U, const double* __restrict__ Cblk, const double* __restrict__ Ud, double* __restrict__ McL)
+k_cluster_inverse(int m, int add_U, int shift, int nclusters, const double* __restrict__ Cblk, const double* __restrict__ Ud,
+                  double* __restrict__ Mout)
 {
     using C = Cluster<NA>;
-    extern __shared__ double A[];                  // NC x LD, row-major
-    __shared__ double rowk[128], colk[128];
+    extern __shared__ double A[];                  // NC x LD, row-major: only for the symmetric copy-out
+    __shared__ double rowb[2][128], colb[2][128];
     const int cl = blockIdx.x, tid = threadIdx.x;
-    const int t = tid & 127, half = tid >> 7;      // row, column half
-    const int nc = min(C::kCams, m - cl * C::kCams) * NA;
-    static_assert(C::NC % 2 == 0, "cluster size");
-    const int c0 = half * (C::NC / 2), c1 = c0 + C::NC / 2;
-    if (t < C::NC) {
-        const int jt = t / NA, rt = t - jt * NA;
-        for (int c = c0; c < c1; c++) {
-            double v = (t < nc && c < nc) ? Cblk[((size_t)cl * 128 + c) * 128 + t] : 0.0;
-            if (add_U && t < nc && c / NA == jt) v += Ud[(size_t)NA * NA * (cl * C::kCams + jt) + rt + NA * (c - jt * NA)];
-            A[t * C::LD + c] = v;
-        }
-    }
-    __syncthreads();
-    for (int k = 0; k < nc; k++) {
-        const double p = fast_rcp_pos(A[k * C::LD + k]);      // 0 for a non-positive pivot
-        // pivot row scaled by 1/d, pivot column as it is now
-        if (tid < C::NC) rowk[tid] = A[k * C::LD + tid] * p;
-        else if (tid >= 128 && tid - 128 < C::NC) colk[tid - 128] = A[(tid - 128) * C::LD + k];
-        __syncthreads();
-        if (t < nc) {
-            // fixed trip count + unrolling: the loads and FMAs of a row are independent, keep 8 in flight
-            const double f = t == k ? 0.0 : colk[t];
-            double* __restrict__ row = A + t * C::LD + c0;        // restrict: lets the unrolled loads run ahead of the stores
-            const double* __restrict__ rk = rowk + c0;
-            if (t == k) {
-#pragma unroll 8
-                for (int cc = 0; cc < C::NC / 2; cc++) row[cc] = rk[cc];
-            } else {
-#pragma unroll 8
-                for (int cc = 0; cc < C::NC / 2; cc++) row[cc] = row[cc] - f * rk[cc];
+    const int ty = tid & 15, tx = tid >> 4;
+    const int cam0 = cl * C::kCams - shift;
+    double a[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
+            const int jr = cam0 + r / NA, jc = cam0 + c / NA;
+            double v = 0.0;
+            if (r < C::NC && c < C::NC && jr >= 0 && jr < m && jc >= 0 && jc < m) {
+                v = Cblk[((size_t)cl * 128 + c) * 128 + r];
+                if (add_U && jr == jc) v += Ud[(size_t)NA * NA * jr + (r - (r / NA) * NA) + NA * (c - (c / NA) * NA)];
             }
-            if (k >= c0 && k < c1) A[t * C::LD + k] = t == k ? p : -f * p;     // the pivot column itself
+            a[i][j] = v;
         }
-        __syncthreads();
+    int buf = 0;
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+        for (int kq = 0; kq < 16; kq++) {
+            const int k = kq + 16 * kk;
+            if (k >= C::NC) break;                 // uniform
+            if (ty == kq) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) rowb[buf][tx + 16 * j] = a[kk][j];
+            }
+            if (tx == kq) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) colb[buf][ty + 16 * i] = a[i][kk];
+            }
+            __syncthreads();
+            const double p = fast_rcp_pos(rowb[buf][k]);      // 0 for a non-positive pivot
+            double rk[8], ci[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) rk[j] = rowb[buf][tx + 16 * j] * p;
+#pragma unroll
+            for (int i = 0; i < 8; i++) ci[i] = colb[buf][ty + 16 * i];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[i][j] = fma(-ci[i], rk[j], a[i][j]);
+            if (ty == kq) {                        // the pivot row: scaled by 1/d
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[kk][j] = rk[j];
+            }
+            if (tx == kq) {                        // the pivot column
+#pragma unroll
+                for (int i = 0; i < 8; i++) a[i][kk] = -ci[i] * p;
+            }
+            if (ty == kq && tx == kq) a[kk][kk] = p;
+            buf ^= 1;
+        }
     }
-    // symmetric copy out (lower triangle mirrored); rows/columns past nc are zero
-    double* out = McL + (size_t)cl * 128 * 128;
-    for (int c = half; c < 128; c += 2) {
-        double v = 0.0;
-        if (t < nc && c < nc) v = t >= c ? A[t * C::LD + c] : A[c * C::LD + t];
-        out[t + 128 * c] = v;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
+            if (r < C::NC && c < C::NC) A[r * C::LD + c] = a[i][j];
+        }
+    __syncthreads();
+    // symmetric copy out (lower triangle mirrored); rows/columns of absent cameras are zero
+    const int t = tid & 127, half = tid >> 7;
+    if (shift == 0) {
+        double* out = Mout + (size_t)cl * 128 * 128;
+        for (int c = half; c < 128; c += 2) {
+            double v = 0.0;
+            if (t < C::NC && c < C::NC) v = t >= c ? A[t * C::LD + c] : A[c * C::LD + t];
+            out[t + 128 * c] = v;
+        }
+    } else if (t < C::NC) {
+        const bool upper = t >= C::kShift * NA;                // first kHalf cameras of cluster cl
+        const int dst = upper ? cl : cl - 1;
+        const int trow = upper ? t - C::kShift * NA : t + C::kHalf * NA;
+        if (dst >= 0 && dst < nclusters) {
+            double* out = Mout + (size_t)dst * 128 * 128 + trow;
+            for (int c = half; c < C::NC; c += 2) out[128 * c] = t >= c ? A[t * C::LD + c] : A[c * C::LD + t];
+        }
     }
+}
+
+// second term of the overlapping preconditioner for unknown t from a global r: the composite row of Mc2 against
+// the r of the shifted block that holds t's camera
+template <int NA, bool COHERENT>
+__device__ __forceinline__ double apply_cluster2_global(int m, int t, const double* __restrict__ Mc2, const double* r)
+{
+    using C = Cluster<NA>;
+    const int cl = t / C::NC, lt = t - cl * C::NC;
+    const long long N = (long long)NA * m;
+    const long long base = (long long)NA * ((long long)cl * C::kCams - C::kShift) + (lt < C::kHalf * NA ? 0 : C::NC);
+    const double* M = Mc2 + (size_t)cl * 128 * 128 + lt;
+    double z0 = 0.0, z1 = 0.0;
+    for (int c = 0; c < C::NC; c += 2) {
+        const long long g0 = base + c, g1 = g0 + 1;
+        if (g0 >= 0 && g0 < N) z0 += M[128 * c] * (COHERENT ? __ldcg(r + g0) : r[g0]);
+        if (g1 >= 0 && g1 < N) z1 += M[128 * (c + 1)] * (COHERENT ? __ldcg(r + g1) : r[g1]);
+    }
+    return z0 + z1;
 }
 
 // z_t = (M^-1 r)_t for unknown t from global r: per-camera blocks, or the cluster blocks when McL is given
 template <int NA>
 __device__ __forceinline__ double apply_precond_global(int m, int t, const double* __restrict__ Minv,
-                                                       const double* __restrict__ McL, const double* __restrict__ r)
+                                                       const double* __restrict__ McL, const double* __restrict__ r,
+                                                       const double* __restrict__ Mc2 = nullptr)
 {
     using C = Cluster<NA>;
     double zz = 0.0;
@@ -408,6 +485,7 @@ __device__ __forceinline__ double apply_precond_global(int m, int t, const doubl
         }
         for (; c < nc; c++) z0 += M[128 * c] * rc[c];
         zz = (z0 + z1) + (z2 + z3);
+        if (Mc2) zz += apply_cluster2_global<NA, false>(m, t, Mc2, r);
     } else {
         const int j = t / NA, row = t - j * NA;
 #pragma unroll
@@ -421,13 +499,13 @@ template <int NA>
 __global__ void __launch_bounds__(1024) k_pcg_init(int m, const double* __restrict__ ebar, const double* __restrict__ Minv,
                                                    double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
                                                    double* __restrict__ p, PcgScalars* __restrict__ sc, double rtol,
-                                                   const double* __restrict__ McL = nullptr)
+                                                   const double* __restrict__ McL = nullptr, const double* __restrict__ Mc2 = nullptr)
 {
     __shared__ double sh[32];
     const int N = NA * m;
     double rz = 0.0, rr = 0.0;
     for (int t = threadIdx.x; t < N; t += 1024) {
-        const double zz = apply_precond_global<NA>(m, t, Minv, McL, ebar);
+        const double zz = apply_precond_global<NA>(m, t, Minv, McL, ebar, Mc2);
         const double rv = ebar[t];
         x[t] = 0.0; r[t] = rv; z[t] = zz; p[t] = zz;
         rz += rv * zz; rr += rv * rv;
@@ -700,7 +778,7 @@ __global__ void __launch_bounds__(1024)
 k_pcg_init_defl(int m, const double* __restrict__ ebar, const double* __restrict__ Minv, const double* __restrict__ Z,
                 const double* __restrict__ SZ, DeflScalars* __restrict__ ds, double* __restrict__ x,
                 double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, PcgScalars* __restrict__ sc,
-                const double* __restrict__ McL)
+                const double* __restrict__ McL, const double* __restrict__ Mc2 = nullptr)
 {
     __shared__ double sh[32];
     __shared__ double E[kDefl * kDefl], Ei[kDefl * kDefl], c0[kDefl], y0[kDefl];
@@ -739,7 +817,7 @@ k_pcg_init_defl(int m, const double* __restrict__ ebar, const double* __restrict
     }
     __syncthreads();
     for (int t = threadIdx.x; t < N; t += 1024) {
-        const double zz = apply_precond_global<NA>(m, t, Minv, McL, r);
+        const double zz = apply_precond_global<NA>(m, t, Minv, McL, r, Mc2);
         z[t] = zz; p[t] = zz;
         rz += r[t] * zz;
     }
@@ -760,7 +838,7 @@ k_pcg_init_defl_coop(int m, const double* __restrict__ ebar, const double* __res
                      const double* __restrict__ SZ, DeflScalars* __restrict__ ds, double* __restrict__ x,
                      double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, PcgScalars* __restrict__ sc,
                      const double* __restrict__ McL, double* __restrict__ part /* 17 * gridDim.x */,
-                     unsigned int* __restrict__ barrier)
+                     unsigned int* __restrict__ barrier, const double* __restrict__ Mc2)
 {
     constexpr int kCams = 128 / NA, NC = kCams * NA;
     constexpr int NP = kDefl * (kDefl + 1) / 2 + kDefl + 1;      // E (upper triangle), c0, b'b
@@ -846,6 +924,7 @@ k_pcg_init_defl_coop(int m, const double* __restrict__ ebar, const double* __res
     }
     rv[tid] = rt;
     __syncthreads();
+    if (Mc2) grid_barrier(barrier, bar_target, nb);     // the overlapping term reads the neighbours' r
     if (act) {
         if (McL) {
             const double* M = McL + (size_t)cta * 128 * 128 + tid;
@@ -858,6 +937,7 @@ k_pcg_init_defl_coop(int m, const double* __restrict__ ebar, const double* __res
 #pragma unroll
             for (int c = NC - NC % 4; c < NC; c++) z0 += __ldg(M + 128 * c) * rv[c];
             zz = (z0 + z1) + (z2 + z3);
+            if (Mc2) zz += apply_cluster2_global<NA, true>(m, (int)t, Mc2, r);
         } else {
 #pragma unroll
             for (int c = 0; c < NA; c++) zz += Minv[(size_t)NA * NA * j + row + NA * c] * rv[lc * NA + c];
@@ -1415,6 +1495,7 @@ struct PcgPersistArgs {
     const int4* tiles;
     double *rowpart, *colpart, *wq;
     const double *Ud, *Minv, *McL;
+    const double* Mc2;               // composite rows of the shifted partition's inverses (overlapping preconditioner) or NULL
     double *x, *r, *p;
     PcgScalars* sc;
     double* blkpart;                 // 11 * nclusters
@@ -1425,6 +1506,7 @@ struct PcgPersistArgs {
     unsigned int epoch0;             // mailbox epoch of the first matvec of this launch
     long long* prof;                 // optional: clock64 totals per phase seen by CTA 0 / thread 0 (VLG_BA_PERSIST_PROF), or NULL
     int J0, J1;                      // strips of S this rank multiplies (all of them on one GPU)
+    int mcl_evict_first;             // stage the cluster inverses with an L2 evict-first hint (VLG_BA_MCL_EVICT overrides)
 };
 
 #define PCG_PROF(slot)                                                           \
@@ -1441,11 +1523,18 @@ __global__ void __launch_bounds__(kSymvRows + 32, 1)
 k_pcg_persistent(PcgPersistArgs a)
 {
     constexpr int ND = 1 + 2 * kDefl;
+    using CL = Cluster<NA>;
     constexpr int kCams = 128 / NA, NC = kCams * NA;
+    // overlapping preconditioner: the ring memory holds 192 columns of 128 doubles -- M1 (NC columns) and the first CA
+    // columns of the composite M2; its last CB columns replace M1's first CB once those have been used
+    constexpr int kRingCols = kSymvStages * kSymvCols * kSymvRows / 128, CA = kRingCols - NC, CB = NC - CA;
+    constexpr int kOwn0 = CL::kShift * NA;        // rx: r of the cameras [cta kCams - kShift, cta kCams + kCams + kHalf), own part at kOwn0
+    static_assert(CA > 0 && CB > 0 && CB <= NC && 2 * NC <= 256, "ring window of the overlapping preconditioner");
     extern __shared__ __align__(128) unsigned char smraw[];
     const SymvSmem sm = symv_smem(smraw);
-    __shared__ double shd[4 * ND], pv[128], rv[128], fold[4][8][33], bcast[ND + 2];
-    __shared__ uint64_t mbarM;
+    __shared__ double shd[4 * ND], pv[128], pv2[128], rx[256], z2s[128], fold[1][8][33], bcast[ND + 2];
+    double* const rv = rx + kOwn0;
+    __shared__ uint64_t mbarM, mbarM2;
     __shared__ double einv[kDefl * kDefl];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, G = gridDim.x, nb = a.nclusters;
@@ -1455,7 +1544,7 @@ k_pcg_persistent(PcgPersistArgs a)
     const size_t N = (size_t)a.N;
     if (tid == 0) {
         for (int s = 0; s < kSymvStages; s++) { mbar_init(sm.full + s, 1); mbar_init(sm.empty + s, kSymvRows / 32); }
-        mbar_init(&mbarM, 1);
+        mbar_init(&mbarM, 1); mbar_init(&mbarM2, 1);
     }
     if (a.Z && tid < kDefl * kDefl) einv[tid] = a.ds->Einv[tid];     // constant over the solve
     __syncthreads();
@@ -1468,24 +1557,44 @@ k_pcg_persistent(PcgPersistArgs a)
     const bool act = cluster_cta && tid < 128 && lc < kCams && j < a.m;
     const size_t t = (size_t)NA * j + row;
     const int nrb = a.Np / 32;
+    // halo role (threads 128..255 of a cluster CTA, overlapping preconditioner): r of the neighbouring cameras is
+    // recomputed here with the owner's arithmetic instead of being fetched after one more grid barrier
+    const bool ovl = cluster_cta && a.McL && a.Mc2;
+    const int h = tid - 128;
+    const int eh = h < kOwn0 ? h : NC + h;
+    const long long gh = (long long)NA * ((long long)cta * kCams - CL::kShift) + eh;
+    const bool hrole = ovl && tid >= 128 && tid < 256;
+    const bool hact = hrole && h < NC && gh >= 0 && gh < (long long)N;
+    const int jh = hact ? (int)(gh / NA) : 0, rowh = hact ? (int)(gh - (long long)NA * jh) : 0, lch = (h & 127) / NA;
 
     long long prof_t = a.prof ? clock64() : 0;
     for (int it = 0; it < a.max_iter; it++) {
         // ---- 1. matvec tiles
+        const long long mv_t0 = a.prof ? clock64() : 0;
         if (nt > 0) {
             if (producer) symv_producer(sm, a.ld, a.S, a.tiles, t0, nt, kbase, lane);
             else symv_consumer<true>(sm, a.Np, a.N, a.p, a.tiles, t0, nt, kbase, a.rowpart, a.colpart);
             kbase += nt;
         }
+        if (a.prof && tid == 0) a.prof[16 + cta] += clock64() - mv_t0;      // per-CTA matvec time (load balance of the tile list)
         PCG_PROF(0);
         grid_barrier(a.barrier, bar_target, G);
         PCG_PROF(1);
         // ---- 2. cluster inverse -> ring memory (asynchronously), fold of the matvec partials -> wq
         if (cluster_cta && a.McL && tid == 0) {
-            constexpr uint32_t bytes = (uint32_t)NC * 128u * 8u;
-            mbar_expect_tx(&mbarM, bytes);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_u32(sm.st)), "l"(a.McL + (size_t)cta * 128 * 128), "r"(bytes), "r"(smem_u32(&mbarM)) : "memory");
+            constexpr uint32_t bytes = (uint32_t)NC * 128u * 8u, bytes2 = (uint32_t)CA * 128u * 8u;
+            mbar_expect_tx(&mbarM, ovl ? bytes + bytes2 : bytes);
+            if (a.mcl_evict_first) {
+                const uint64_t pol = l2_evict_first_policy();
+                tma_load_1d_pol(sm.st, a.McL + (size_t)cta * 128 * 128, bytes, &mbarM, pol);
+                if (ovl) tma_load_1d_pol(sm.st + (size_t)NC * 128, a.Mc2 + (size_t)cta * 128 * 128, bytes2, &mbarM, pol);
+            } else {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(sm.st)), "l"(a.McL + (size_t)cta * 128 * 128), "r"(bytes), "r"(smem_u32(&mbarM)) : "memory");
+                if (ovl)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(sm.st + (size_t)NC * 128)), "l"(a.Mc2 + (size_t)cta * 128 * 128), "r"(bytes2), "r"(smem_u32(&mbarM)) : "memory");
+            }
         }
         if (!producer) {
             const int gq = tid >> 5;                               // strip group 0..7
@@ -1573,6 +1682,23 @@ k_pcg_persistent(PcgPersistArgs a)
                 a.blkpart[(size_t)tid * nb + cta] = v;
             }
         }
+        double qh = 0.0, rh0 = 0.0, szh[kDefl];
+#pragma unroll
+        for (int d = 0; d < kDefl; d++) szh[d] = 0.0;
+        if (hrole) {
+            if (hact) { pv2[h] = __ldcg(a.p + gh); rh0 = __ldcg(a.r + gh); }
+            asm volatile("bar.sync 3, 128;" ::: "memory");
+            if (hact) {
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < NA; c++) v += a.Ud[(size_t)NA * NA * jh + rowh + NA * c] * pv2[lch * NA + c];
+                qh = v - __ldcg(a.wq + gh);
+                if (a.Z) {
+#pragma unroll
+                    for (int d = 0; d < kDefl; d++) szh[d] = a.SZ[d * N + gh];
+                }
+            }
+        }
         PCG_PROF(4);
         grid_barrier(a.barrier, bar_target, G);
         PCG_PROF(5);
@@ -1629,23 +1755,99 @@ k_pcg_persistent(PcgPersistArgs a)
         // ---- 4. x, r, z = M^-1 r
         double rzn = 0.0, rr = 0.0, zt = 0.0;
         double* bp2 = a.blkpart + (size_t)ND * nb;
-        if (cluster_cta && tid < 128) {
-            if (act) {
-                if (a.Z) {
+        if (cluster_cta && tid < 256) {
+            if (tid < 128) {
+                double rt = 0.0;
+                if (act) {
+                    if (a.Z) {
 #pragma unroll
-                    for (int d = 0; d < kDefl; d++) qt -= szv[d] * y[d];
+                        for (int d = 0; d < kDefl; d++) qt -= szv[d] * y[d];
+                    }
+                    a.x[t] = xt + alpha * pt;
+                    rt = rt0 - alpha * qt;
+                    a.r[t] = rt;
+                    rr = rt * rt;
                 }
-                a.x[t] = xt + alpha * pt;
-                const double rt = rt0 - alpha * qt;
-                a.r[t] = rt;
-                rv[tid] = rt;
-                rr = rt * rt;
-            } else {
-                rv[tid] = 0.0;
+                if (tid < NC) rv[tid] = rt;
+            } else if (hrole) {
+                double rh = 0.0;
+                if (hact) {
+                    if (a.Z) {
+#pragma unroll
+                        for (int d = 0; d < kDefl; d++) qh -= szh[d] * y[d];
+                    }
+                    rh = rh0 - alpha * qh;
+                }
+                if (h < NC) rx[eh] = rh;
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (ovl) consumer_sync();
+            else if (tid < 128) asm volatile("bar.sync 2, 128;" ::: "memory");
             PCG_PROF(10);
-            if (act) {
+            if (ovl) {
+                // z = M1^-1 r + M2^-1 r: threads 0..127 take the first term, threads 128..255 the second (composite rows)
+                if (tid < 128) {
+                    mbar_wait(&mbarM, (uint32_t)(it & 1));
+                    PCG_PROF(11);
+                    const double* M = sm.st + tid;
+                    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+                    if (tid < NC) {
+#pragma unroll 4
+                        for (int c = 0; c + 3 < CB; c += 4) {
+                            z0 += M[128 * c] * rv[c]; z1 += M[128 * (c + 1)] * rv[c + 1];
+                            z2 += M[128 * (c + 2)] * rv[c + 2]; z3 += M[128 * (c + 3)] * rv[c + 3];
+                        }
+#pragma unroll
+                        for (int c = CB - CB % 4; c < CB; c++) z0 += M[128 * c] * rv[c];
+                    }
+                    // M1's first CB columns are used up: the tail of M2 takes their place
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (tid == 0) {
+                        constexpr uint32_t bytes3 = (uint32_t)CB * 128u * 8u;
+                        mbar_expect_tx(&mbarM2, bytes3);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         smem_u32(sm.st)), "l"(a.Mc2 + ((size_t)cta * 128 + CA) * 128), "r"(bytes3), "r"(smem_u32(&mbarM2)) : "memory");
+                    }
+                    if (tid < NC) {
+#pragma unroll 4
+                        for (int c = CB; c + 3 < NC; c += 4) {
+                            z0 += M[128 * c] * rv[c]; z1 += M[128 * (c + 1)] * rv[c + 1];
+                            z2 += M[128 * (c + 2)] * rv[c + 2]; z3 += M[128 * (c + 3)] * rv[c + 3];
+                        }
+#pragma unroll
+                        for (int c = CB + (NC - CB) / 4 * 4; c < NC; c++) z0 += M[128 * c] * rv[c];
+                    }
+                    zt = (z0 + z1) + (z2 + z3);
+                } else {
+                    mbar_wait(&mbarM, (uint32_t)(it & 1));
+                    const double* rb = rx + (h < CL::kHalf * NA ? 0 : NC);
+                    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+                    if (h < NC) {
+                        const double* M = sm.st + (size_t)NC * 128 + h;
+#pragma unroll 4
+                        for (int c = 0; c + 3 < CA; c += 4) {
+                            z0 += M[128 * c] * rb[c]; z1 += M[128 * (c + 1)] * rb[c + 1];
+                            z2 += M[128 * (c + 2)] * rb[c + 2]; z3 += M[128 * (c + 3)] * rb[c + 3];
+                        }
+#pragma unroll
+                        for (int c = CA - CA % 4; c < CA; c++) z0 += M[128 * c] * rb[c];
+                    }
+                    mbar_wait(&mbarM2, (uint32_t)(it & 1));
+                    if (h < NC) {
+                        const double* M = sm.st + h;
+                        const double* rc = rb + CA;
+#pragma unroll 4
+                        for (int c = 0; c + 3 < CB; c += 4) {
+                            z0 += M[128 * c] * rc[c]; z1 += M[128 * (c + 1)] * rc[c + 1];
+                            z2 += M[128 * (c + 2)] * rc[c + 2]; z3 += M[128 * (c + 3)] * rc[c + 3];
+                        }
+#pragma unroll
+                        for (int c = CB - CB % 4; c < CB; c++) z0 += M[128 * c] * rc[c];
+                    }
+                    z2s[h] = (z0 + z1) + (z2 + z3);
+                }
+                consumer_sync();
+                if (act) { zt += z2s[tid]; rzn = rv[tid] * zt; }
+            } else if (act) {
                 if (a.McL) {
                     mbar_wait(&mbarM, (uint32_t)(it & 1));
                     PCG_PROF(11);
@@ -1666,14 +1868,16 @@ k_pcg_persistent(PcgPersistArgs a)
                 rzn = rv[tid] * zt;
             }
             PCG_PROF(12);
-            rzn = warp_sum(rzn);
-            rr = warp_sum(rr);
-            if (lane == 0) { shd[warp * 2] = rzn; shd[warp * 2 + 1] = rr; }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (tid < 2) {
-                double v = 0.0;
-                for (int w = 0; w < 4; w++) v += shd[w * 2 + tid];
-                bp2[2 * cta + tid] = v;
+            if (tid < 128) {
+                rzn = warp_sum(rzn);
+                rr = warp_sum(rr);
+                if (lane == 0) { shd[warp * 2] = rzn; shd[warp * 2 + 1] = rr; }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (tid < 2) {
+                    double v = 0.0;
+                    for (int w = 0; w < 4; w++) v += shd[w * 2 + tid];
+                    bp2[2 * cta + tid] = v;
+                }
             }
         }
         PCG_PROF(6);

@@ -105,6 +105,8 @@ struct vlg_ba_ctx {
     std::vector<int> s_bounds;             // strip boundaries of all ranks (nranks + 1), equal lower-triangle areas
     bool S_zeroed = false;                 // explicit-S PCG: structurally zero blocks of S cleared for this problem
     double *Cblk = nullptr, *McL = nullptr;   // cluster-Jacobi preconditioner: gathered diagonal blocks of S, their inverses [coop_grid][128 x 128]
+    double* Mc2 = nullptr;                    // overlapping variant: composite rows of the shifted partition's inverses [coop_grid][128 x 128]
+    bool overlap_ok = true;                   // VLG_BA_OVERLAP=0 switches the second partition off
     int Np = 0;               // padded order of S
     int64_t nblocks = 0, npairs = 0;
     // host copies
@@ -381,7 +383,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     free_problem(ctx);
     // optional buffers: which of them exist depends on the solver path of THIS problem
     ctx->init_part = nullptr; ctx->init_bar = nullptr; ctx->persist_bar = nullptr; ctx->init_coop_cap = -1; ctx->S_zeroed = false; ctx->s_split = false;
-    ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr;
+    ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr; ctx->Mc2 = nullptr;
     ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr; ctx->pt_pt = nullptr;
     ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
     ctx->symv_tiles = nullptr; ctx->symv_tile_ptr = nullptr; ctx->symv_rowpart = nullptr; ctx->symv_colpart = nullptr;
@@ -611,7 +613,15 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         CHK(dalloc(ctx, &ctx->blkpart, (size_t)11 * std::max(g, 1)));
         if (ctx->coop_grid > 0) { CHK(dalloc(ctx, &ctx->init_part, (size_t)17 * g)); CHK(dalloc(ctx, &ctx->init_bar, 1)); }
         if (cluster_pc && ctx->coop_grid > 0) {
-            CHK(dalloc(ctx, &ctx->Cblk, (size_t)g * 128 * 128)); CHK(dalloc(ctx, &ctx->McL, (size_t)g * 128 * 128));
+            // Cblk holds the g blocks of the cluster partition and, behind them, the g + 1 blocks of the shifted one
+            const bool ovl = ctx->use_explicit;
+            CHK(dalloc(ctx, &ctx->Cblk, (size_t)(ovl ? 2 * g + 1 : g) * 128 * 128)); CHK(dalloc(ctx, &ctx->McL, (size_t)g * 128 * 128));
+            if (ovl) {
+                CHK(dalloc(ctx, &ctx->Mc2, (size_t)g * 128 * 128));
+                CU(cudaMemsetAsync(ctx->Mc2, 0, sizeof(double) * (size_t)g * 128 * 128, ctx->stream));     // padding rows are staged, never used
+                const char* e = getenv("VLG_BA_OVERLAP");
+                ctx->overlap_ok = e ? atoi(e) != 0 : true;
+            }
         }
         CHK(dalloc(ctx, &ctx->Zd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->SZd, (size_t)kDefl * N)); CHK(dalloc(ctx, &ctx->defl_sc, 1));
         if (ctx->tiled_ok) {

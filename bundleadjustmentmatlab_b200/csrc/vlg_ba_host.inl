@@ -152,21 +152,39 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_update_coop<NA, true>, 128, mcl_in_smem ? upd_smem : 0));
             upd_batch = ctx->coop_grid <= per_sm * ctx->nsm;
         }
+        // assembled S on one GPU (or with the peer-memory exchange): the whole solve is one persistent kernel
+        const bool persistent = ctx->use_explicit && ctx->persist_ok && ctx->coop_grid > 0 && ctx->coop_grid <= ctx->symv_grid &&
+                                (ctx->nranks == 1 || ctx->p2p_ready) && ctx->opt.pcg_max_iter > 0;
+        // ... and only that kernel applies the second (shifted) cluster partition of the overlapping preconditioner
+        const bool overlap = persistent && ctx->McL && ctx->Mc2 && ctx->overlap_ok;
+        const double* Mc2 = nullptr;
         if (ctx->McL) {
             // cluster-Jacobi: diagonal blocks of S over the update kernel's CTAs, summed over ranks, inverted
             TimedScope ts(ctx, T_PRECOND);
+            const size_t nblk = (size_t)ctx->coop_grid * (overlap ? 2 : 1) + (overlap ? 1 : 0);
             if (ctx->use_explicit) {
-                k_cluster_gather<NA><<<ctx->coop_grid, 128, 0, ctx->stream>>>(m, ctx->Np, ctx->S, ctx->Cblk);
+                k_cluster_gather<NA><<<ctx->coop_grid, 128, 0, ctx->stream>>>(m, ctx->Np, ctx->S, ctx->Cblk, 0);
                 ctx->launches++;
+                if (overlap) {
+                    k_cluster_gather<NA><<<ctx->coop_grid + 1, 128, 0, ctx->stream>>>(m, ctx->Np, ctx->S, ctx->Cblk + (size_t)ctx->coop_grid * 128 * 128,
+                                                                                      Cluster<NA>::kShift);
+                    ctx->launches++;
+                }
             } else {
                 // implicit path: only the within-cluster blocks are assembled (pair lists restricted to them)
                 CU(cudaMemsetAsync(ctx->Cblk, 0, sizeof(double) * (size_t)ctx->coop_grid * 128 * 128, ctx->stream));
                 CHK(assemble_S<NA>(ctx, 0, ctx->Cblk, Cluster<NA>::kCams));
             }
-            CHK(allreduce(ctx, ctx->Cblk, (size_t)ctx->coop_grid * 128 * 128));
+            CHK(allreduce(ctx, ctx->Cblk, nblk * 128 * 128));
             CU(cudaFuncSetAttribute(k_cluster_inverse<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cluster<NA>::kSmem));
-            k_cluster_inverse<NA><<<ctx->coop_grid, 256, Cluster<NA>::kSmem, ctx->stream>>>(m, 1, ctx->Cblk, ctx->Ud, ctx->McL);
+            k_cluster_inverse<NA><<<ctx->coop_grid, 256, Cluster<NA>::kSmem, ctx->stream>>>(m, 1, 0, ctx->coop_grid, ctx->Cblk, ctx->Ud, ctx->McL);
             ctx->launches++;
+            if (overlap) {
+                k_cluster_inverse<NA><<<ctx->coop_grid + 1, 256, Cluster<NA>::kSmem, ctx->stream>>>(
+                    m, 1, Cluster<NA>::kShift, ctx->coop_grid, ctx->Cblk + (size_t)ctx->coop_grid * 128 * 128, ctx->Ud, ctx->Mc2);
+                ctx->launches++;
+                Mc2 = ctx->Mc2;
+            }
             CU(cudaGetLastError());
             McL = ctx->McL;
         }
@@ -280,44 +298,44 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             if (ctx->init_part && ctx->coop_grid <= ctx->init_coop_cap) {
                 // cooperative set-up on the update kernel's grid
                 int m_ = m;
-                const double *eb = ctx->ebar, *mi = ctx->Minv, *zz = ctx->Zd, *sz = ctx->SZd, *mcl = McL;
+                const double *eb = ctx->ebar, *mi = ctx->Minv, *zz = ctx->Zd, *sz = ctx->SZd, *mcl = McL, *mc2 = Mc2;
                 DeflScalars* dsc = ctx->defl_sc;
                 double *xx = ctx->da, *rr = ctx->pr, *pzv = ctx->pz, *ppv = ctx->pp, *ip = ctx->init_part;
                 PcgScalars* sc = ctx->pcg_sc;
                 unsigned int* ib = ctx->init_bar;
                 CU(cudaMemsetAsync(ctx->init_bar, 0, sizeof(unsigned int), ctx->stream));
-                void* args[] = {&m_, &eb, &mi, &zz, &sz, &dsc, &xx, &rr, &pzv, &ppv, &sc, &mcl, &ip, &ib};
+                void* args[] = {&m_, &eb, &mi, &zz, &sz, &dsc, &xx, &rr, &pzv, &ppv, &sc, &mcl, &ip, &ib, &mc2};
                 CU(cudaLaunchCooperativeKernel((void*)k_pcg_init_defl_coop<NA>, dim3(ctx->coop_grid), dim3(128), args, 0, ctx->stream));
             } else {
                 k_pcg_init_defl<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->Zd, ctx->SZd, ctx->defl_sc, ctx->da, ctx->pr,
-                                                               ctx->pz, ctx->pp, ctx->pcg_sc, McL);
+                                                               ctx->pz, ctx->pp, ctx->pcg_sc, McL, Mc2);
             }
         } else {
-            k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol, McL);
+            k_pcg_init<NA><<<1, 1024, 0, ctx->stream>>>(m, ctx->ebar, ctx->Minv, ctx->da, ctx->pr, ctx->pz, ctx->pp, ctx->pcg_sc, rtol, McL, Mc2);
         }
         ctx->launches++;
         int launched = 0;
         const int batch = 8;
-        // assembled S on one GPU (or with the peer-memory exchange): the whole solve is one persistent kernel
-        const bool persistent = ctx->use_explicit && ctx->persist_ok && ctx->coop_grid > 0 && ctx->coop_grid <= ctx->symv_grid &&
-                                (ctx->nranks == 1 || ctx->p2p_ready) && ctx->opt.pcg_max_iter > 0;
         if (persistent) {
             TimedScope ts(ctx, T_PCG_PERSIST);
             PcgPersistArgs pa;
             pa.Np = ctx->Np; pa.ld = ctx->Np; pa.N = N; pa.m = m; pa.max_iter = ctx->opt.pcg_max_iter; pa.nclusters = ctx->coop_grid;
             pa.rtol = rtol; pa.S = ctx->S; pa.tile_ptr = ctx->symv_tile_ptr; pa.tiles = ctx->symv_tiles;
             pa.rowpart = ctx->symv_rowpart; pa.colpart = ctx->symv_colpart; pa.wq = ctx->wq;
-            pa.Ud = ctx->Ud; pa.Minv = ctx->Minv; pa.McL = McL; pa.x = ctx->da; pa.r = ctx->pr; pa.p = ctx->pp;
+            pa.Ud = ctx->Ud; pa.Minv = ctx->Minv; pa.McL = McL; pa.Mc2 = Mc2; pa.x = ctx->da; pa.r = ctx->pr; pa.p = ctx->pp;
             pa.sc = ctx->pcg_sc; pa.blkpart = ctx->blkpart; pa.Z = defl ? ctx->Zd : nullptr; pa.SZ = defl ? ctx->SZd : nullptr;
             pa.ds = ctx->defl_sc; pa.barrier = ctx->persist_bar;
             pa.mb = ctx->nranks > 1 ? ctx->p2p_dev : nullptr; pa.epoch0 = ctx->p2p_epoch + 1;
             pa.J0 = ctx->s_split ? ctx->s_J0 : 0; pa.J1 = ctx->s_split ? ctx->s_J1 : 1 << 30;
             pa.prof = nullptr;
+            // staging the cluster inverses with an evict-first hint keeps them (22 MB with both partitions) from crowding the matvec's
+            // partials out of L2: measured -2.2 us (matvec phase) + 0.9 us (fold) per iteration at Venice shape
+            { const char* e = getenv("VLG_BA_MCL_EVICT"); pa.mcl_evict_first = e ? atoi(e) : (overlap ? 1 : 0); }
             static long long* d_prof = nullptr;
             const bool want_prof = getenv("VLG_BA_PERSIST_PROF") != nullptr;
             if (want_prof) {
-                if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
-                cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), ctx->stream);
+                if (!d_prof) cudaMalloc(&d_prof, (16 + 1024) * sizeof(long long));
+                cudaMemsetAsync(d_prof, 0, (16 + 1024) * sizeof(long long), ctx->stream);
                 pa.prof = d_prof;
             }
             CU(cudaMemsetAsync(ctx->persist_bar, 0, sizeof(unsigned int), ctx->stream));
@@ -339,6 +357,11 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                                       "p4:x,r", "p4:wait-McL", "p4:matvec", "p4:partials", "p4:sync"};
                 fprintf(stderr, "k_pcg_persistent, %d iterations, us per iteration (CTA 0):", ctx->h_pcg->iters);
                 for (int k = 0; k < 15; k++) fprintf(stderr, " %s %.1f", nm[k], hp[k] / (khz * 1e-3) / std::max(ctx->h_pcg->iters, 1));
+                fprintf(stderr, "\n");
+                std::vector<long long> hc((size_t)ctx->symv_grid);
+                cudaMemcpy(hc.data(), d_prof + 16, sizeof(long long) * hc.size(), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "  matvec us per iteration by CTA:");
+                for (size_t k = 0; k < hc.size(); k++) fprintf(stderr, " %.1f", hc[k] / (khz * 1e-3) / std::max(ctx->h_pcg->iters, 1));
                 fprintf(stderr, "\n");
             }
         }
