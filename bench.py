@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--model", default="euclid", choices=["euclid", "projective"],
                     help="euclid: bundle_euclid.m with 'fix_calibration' (num_a = 6, the headline); projective: bundle_projective.m (num_a = 12)")
+    ap.add_argument("--autotune", type=int, default=3,
+                    help="opts.pcg_autotune: re-weight the matvec cut by the measured per-SM rate over the first N solves (0 = off)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: all-reduce the PCG vector with NCCL instead of peer-memory mailboxes")
     return ap.parse_args()
 
@@ -227,7 +229,7 @@ def run_ours(args):
     proj = args.model == "projective"
     na = 12 if proj else 6
     ctx = capi.Context(num_variableK=0, solver=solver, pcg_rtol=args.pcg_rtol, rtable=rtable, device=local,
-                       model=capi.MODEL_PROJECTIVE if proj else capi.MODEL_EUCLID)
+                       model=capi.MODEL_PROJECTIVE if proj else capi.MODEL_EUCLID, pcg_autotune=args.autotune)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -392,8 +394,8 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, P, world), "num_a": na, "model": args.model,
                        "solver": {capi.SOLVER_CHOL: "cholesky", capi.SOLVER_PCG: "pcg (block-Jacobi, implicit Schur)",
-                                  capi.SOLVER_PCG_EXPLICIT: "pcg (block-Jacobi, assembled S, symmetric lower-triangle matvec)"}[infos[-1]["solver_used"]],
-                       "pcg_rtol": args.pcg_rtol, "rtable": args.rtable,
+                                  capi.SOLVER_PCG_EXPLICIT: "pcg (two-partition cluster preconditioner, assembled S, symmetric lower-triangle matvec, one persistent kernel)"}[infos[-1]["solver_used"]],
+                       "pcg_rtol": args.pcg_rtol, "rtable": args.rtable, "pcg_autotune": args.autotune,
                        "pcg_vector_allreduce": ("nvlink peer-memory mailboxes (k_p2p_allreduce)" if p2p else "nccl") if world > 1 else None,
                        "l2": "inputs larger than L2 (W alone is %.0f MB per rank)" % (P.nobs * 144 / 1e6)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),

@@ -30,7 +30,7 @@ class Opts(C.Structure):
         ("rel_tol", C.c_double), ("abs_tol", C.c_double), ("backsub_all_rows", C.c_int),
         ("solver", C.c_int), ("chol_max_cams", C.c_int), ("pcg_rtol", C.c_double), ("pcg_max_iter", C.c_int),
         ("rtable", C.c_int), ("order", C.c_int), ("device", C.c_int), ("verbose", C.c_int),
-        ("pcg_deflate", C.c_int), ("pcg_cluster", C.c_int), ("model", C.c_int),
+        ("pcg_deflate", C.c_int), ("pcg_cluster", C.c_int), ("model", C.c_int), ("pcg_autotune", C.c_int),
     ]
 
 

@@ -1218,10 +1218,13 @@ namespace vlgba {
 constexpr int kSymvCols = 32;
 constexpr int kSymvRows = 256;    // rows per tile == threads per CTA
 constexpr int kSymvStages = 3;
-constexpr int kSymvSegRows = 512;    // rows per work item (strip segment): granularity of the load balance
+constexpr int kSymvSlab = 8;         // strips per cell
+constexpr int kSymvBlkRows = 2048;   // rows per cell (absolute row grid); also the length of a fragment's row-sum vector
 
-// tile descriptor: x = strip, y = first row, z = rows | first-of-item << 16 | last-of-item << 17, w = segment
-struct SymvTile { int strip, r0, rows_flags, seg; };
+// tile descriptor: x = strip, y = first row, z = rows | flags << 16, w = fragment | strip-in-cell << 20.
+// Tiles are aligned to the absolute 256-row grid (the first tile of a strip starts at its diagonal, 32 J, and is
+// short): row r always belongs to thread r & 255.
+constexpr int kSymvFirstStrip = 1 << 16, kSymvLastStrip = 1 << 17, kSymvFirstFrag = 1 << 18, kSymvLastFrag = 1 << 19;
 
 // all 32 values of every lane summed over the warp; lane l ends up owning value l
 __device__ __forceinline__ double warp_reduce_32(double* v, int lane)
@@ -1252,16 +1255,27 @@ __device__ __forceinline__ void consumer_sync()      // named barrier 1: the 256
     asm volatile("bar.sync 1, %0;" ::"n"(kSymvRows) : "memory");
 }
 
-// warps 0..7 consume (thread t = row t of the tile), warp 8 produces: lane c issues the bulk copy of
-// column c, so a whole tile is requested by one warp instruction and the producer runs ahead of the
-// consumers by kSymvStages tiles (full/empty mbarrier pairs, no CTA-wide barrier per tile).
-// Both halves are device functions so that the persistent PCG kernel below runs the same code;
-// `kbase` is the number of tiles this CTA has already pushed through the ring (the mbarrier phases
-// go on across calls), `L2X` makes x a coherent L2 read (x written by other CTAs of the same kernel).
+// Work decomposition.  The lower triangle is cut into CELLS of kSymvSlab strips x kSymvBlkRows rows; the tiles
+// of a cell are ordered strip by strip, the cells slab by slab, and every CTA gets a contiguous piece of that
+// sequence (equal cost).  The piece of a cell that one CTA owns is a FRAGMENT, the unit of the partial results:
+//   * row sums: thread r & 255 adds the row sum of every tile into its own slot of a kSymvBlkRows-long vector in
+//     shared memory (no barrier: a slot has one owner) and the fragment leaves ONE vector of row partials;
+//   * column sums: the 32 accumulators of a thread live over a run of tiles of one strip, are reduced at its end
+//     (warp tree, then the 8 warps through shared memory) and leave as the fragment's partial for that strip.
+// A row is then the sum of <= Np / (32 kSymvSlab) + a few fragment partials and a column of <= Np / kSymvBlkRows + a
+// few (host-built lists; summed in list order => bit-reproducible, no atomics).  The first version wrote a row
+// partial per tile (one per 32 columns): 14 MB per product at Venice shape and 355 terms per row to fold.
+//
+// warps 0..7 consume, warp 8 produces: lane c issues the bulk copy of column c, so a whole tile is requested by
+// one warp instruction and the producer runs ahead of the consumers by kSymvStages tiles (full/empty mbarrier
+// pairs, no CTA-wide barrier per tile).  Both halves are device functions so that the persistent PCG kernel
+// below runs the same code; `kbase` is the number of tiles this CTA has already pushed through the ring (the
+// mbarrier phases go on across calls), `L2X` makes x a coherent L2 read (x written by other CTAs of the kernel).
 struct SymvSmem {
     double* st;        // kSymvStages x 32 x 256
     double* cred;      // 8 x 32
     double* xs;        // 32
+    double* yacc;      // kSymvBlkRows
     uint64_t* full;    // kSymvStages
     uint64_t* empty;   // kSymvStages
 };
@@ -1272,13 +1286,18 @@ __device__ __forceinline__ SymvSmem symv_smem(unsigned char* smraw)
     m.st = reinterpret_cast<double*>(smraw);
     m.cred = m.st + (size_t)kSymvStages * kSymvCols * kSymvRows;
     m.xs = m.cred + (kSymvRows / 32) * kSymvCols;
-    m.full = reinterpret_cast<uint64_t*>(m.xs + kSymvCols);
+    m.yacc = m.xs + kSymvCols;
+    m.full = reinterpret_cast<uint64_t*>(m.yacc + kSymvBlkRows);
     m.empty = m.full + kSymvStages;
     return m;
 }
 
 constexpr size_t kSymvSmemBytes =
-    sizeof(double) * ((size_t)kSymvStages * kSymvCols * kSymvRows + (kSymvRows / 32) * kSymvCols + kSymvCols) + 16 * kSymvStages + 16;
+    sizeof(double) * ((size_t)kSymvStages * kSymvCols * kSymvRows + (kSymvRows / 32) * kSymvCols + kSymvCols + kSymvBlkRows) + 16 * kSymvStages + 16;
+
+// fold lists: the fragments whose row vector covers row block b (of kSymvBlkRows rows), and for strip J the offsets
+// (fragment * 32 kSymvSlab + 32 strip-in-cell) of its column partials
+struct SymvFold { const int* row_ptr; const int* row_list; const int* col_ptr; const int* col_list; };
 
 __device__ __forceinline__ void symv_producer(const SymvSmem& sm, int ld, const double* __restrict__ S,
                                               const int4* __restrict__ tiles, int t0, int nt, int kbase, int lane)
@@ -1291,7 +1310,7 @@ __device__ __forceinline__ void symv_producer(const SymvSmem& sm, int ld, const 
         if (g >= kSymvStages) mbar_wait(sm.empty + slot, (uint32_t)((g / kSymvStages - 1) & 1));
         if (lane == 0) mbar_expect_tx(sm.full + slot, bytes * kSymvCols);
         __syncwarp();
-        tma_load_1d_pol(sm.st + ((size_t)slot * kSymvCols + lane) * kSymvRows,
+        tma_load_1d_pol(sm.st + ((size_t)slot * kSymvCols + lane) * kSymvRows + (d.y & (kSymvRows - 1)),
                         S + (size_t)ld * (kSymvCols * d.x + lane) + d.y, bytes, sm.full + slot, policy);
     }
 }
@@ -1300,7 +1319,7 @@ template <bool L2X>
 __device__ __forceinline__ double symv_ldx(const double* x) { return L2X ? __ldcg(x) : __ldg(x); }
 
 template <bool L2X>
-__device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int Np, int N, const double* __restrict__ x,
+__device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int N, const double* __restrict__ x,
                                               const int4* __restrict__ tiles, int t0, int nt, int kbase,
                                               double* __restrict__ rowpart, double* __restrict__ colpart)
 {
@@ -1311,24 +1330,32 @@ __device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int Np, int N,
     // x of this thread's row, requested one tile ahead
     int4 dn = __ldg(tiles + t0);
     double xr_next = 0.0;
-    { const int r = dn.y + tid; if (tid < (dn.z & 0xffff) && r < N) xr_next = symv_ldx<L2X>(x + r); }
+    {
+        const int r = (dn.y & ~(kSymvRows - 1)) + tid;
+        if (r >= dn.y && r < dn.y + (dn.z & 0xffff) && r < N) xr_next = symv_ldx<L2X>(x + r);
+    }
     for (int k = 0; k < nt; k++) {
         const int g = kbase + k, slot = g % kSymvStages;
         const int4 d = dn;
-        const int rows = d.z & 0xffff, c0 = kSymvCols * d.x, r = d.y + tid;
+        const int rows = d.z & 0xffff, c0 = kSymvCols * d.x, r = (d.y & ~(kSymvRows - 1)) + tid;
+        const bool live = r >= d.y && r < d.y + rows;
         double xr = xr_next;
         if (k + 1 < nt) {
             dn = __ldg(tiles + t0 + k + 1);
-            const int rn = dn.y + tid;
-            xr_next = (tid < (dn.z & 0xffff) && rn < N) ? symv_ldx<L2X>(x + rn) : 0.0;
+            const int rn = (dn.y & ~(kSymvRows - 1)) + tid;
+            xr_next = (rn >= dn.y && rn < dn.y + (dn.z & 0xffff) && rn < N) ? symv_ldx<L2X>(x + rn) : 0.0;
         }
-        if (d.z & (1 << 16)) {                      // first tile of a work item: this strip's x
+        if (d.z & kSymvFirstFrag) {                 // own slots only: no barrier
+#pragma unroll
+            for (int i = 0; i < kSymvBlkRows / kSymvRows; i++) sm.yacc[tid + kSymvRows * i] = 0.0;
+        }
+        if (d.z & kSymvFirstStrip) {                // first tile of a run in this strip: the strip's x
             if (tid < kSymvCols) sm.xs[tid] = (c0 + tid < N) ? symv_ldx<L2X>(x + c0 + tid) : 0.0;
             consumer_sync();
         }
         mbar_wait(sm.full + slot, (uint32_t)((g / kSymvStages) & 1));
         double ra = 0.0;
-        if (tid < rows) {
+        if (live) {
             // the diagonal 32 x 32 block is stored in full: whole-row dot product there, no mirrored part
             if (r < c0 + kSymvCols) xr = 0.0;
             const double* a = sm.st + (size_t)slot * kSymvCols * kSymvRows + tid;
@@ -1341,8 +1368,9 @@ __device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int Np, int N,
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.empty + slot);   // this warp is done with the slot
-        if (tid < rows) rowpart[(size_t)d.x * Np + r] = ra;
-        if (d.z & (1 << 17)) {                      // last tile of the work item: column sums out
+        if (live) sm.yacc[r & (kSymvBlkRows - 1)] += ra;
+        const int frag = d.w & 0xfffff;
+        if (d.z & kSymvLastStrip) {                 // last tile of the run: column sums out
             const double tot = warp_reduce_32(colacc, lane);
             sm.cred[warp * kSymvCols + lane] = tot;
             consumer_sync();
@@ -1350,19 +1378,24 @@ __device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int Np, int N,
                 double s = 0.0;
 #pragma unroll
                 for (int w = 0; w < kSymvRows / 32; w++) s += sm.cred[w * kSymvCols + tid];
-                colpart[(size_t)d.w * Np + c0 + tid] = s;
+                colpart[(size_t)frag * (kSymvCols * kSymvSlab) + kSymvCols * (d.w >> 20) + tid] = s;
             }
 #pragma unroll
             for (int c = 0; c < kSymvCols; c++) colacc[c] = 0.0;
+        }
+        if (d.z & kSymvLastFrag) {                  // the fragment's row sums out (own slots only)
+#pragma unroll
+            for (int i = 0; i < kSymvBlkRows / kSymvRows; i++)
+                rowpart[(size_t)frag * kSymvBlkRows + tid + kSymvRows * i] = sm.yacc[tid + kSymvRows * i];
         }
     }
 }
 
 __global__ void __launch_bounds__(kSymvRows + 32, 1)
-k_symv_lower(int Np, int ld, int N, const double* __restrict__ S, const double* __restrict__ x,
+k_symv_lower(int ld, int N, const double* __restrict__ S, const double* __restrict__ x,
              const int* __restrict__ tile_ptr /* [gridDim.x + 1] */, const int4* __restrict__ tiles,
-             const int* __restrict__ done, double* __restrict__ rowpart /* [Np/32][Np] */,
-             double* __restrict__ colpart /* [nseg][Np] */)
+             const int* __restrict__ done, double* __restrict__ rowpart /* [nfrag][kSymvBlkRows] */,
+             double* __restrict__ colpart /* [nfrag][32 kSymvSlab] */)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
     const SymvSmem sm = symv_smem(smraw);
@@ -1374,7 +1407,15 @@ k_symv_lower(int Np, int ld, int N, const double* __restrict__ S, const double* 
         for (int s = 0; s < kSymvStages; s++) { mbar_init(sm.full + s, 1); mbar_init(sm.empty + s, kSymvRows / 32); }
     __syncthreads();
     if (warp == kSymvRows / 32) symv_producer(sm, ld, S, tiles, t0, nt, 0, lane);
-    else symv_consumer<false>(sm, Np, N, x, tiles, t0, nt, 0, rowpart, colpart);
+    else symv_consumer<false>(sm, N, x, tiles, t0, nt, 0, rowpart, colpart);
+}
+
+// term q of the 32-row block rb (lane = row in the block): the fragments' row partials first, then the column partials
+__device__ __forceinline__ const double* symv_term(const SymvFold& f, const double* rowpart, const double* colpart, int rb, int lane,
+                                                   int rbeg, int nrow, int cbeg, int q)
+{
+    return q < nrow ? rowpart + (size_t)__ldg(f.row_list + rbeg + q) * kSymvBlkRows + ((rb & (kSymvBlkRows / 32 - 1)) << 5) + lane
+                    : colpart + __ldg(f.col_list + cbeg + q - nrow) + lane;
 }
 
 struct P2PMail;
@@ -1383,24 +1424,22 @@ __device__ __forceinline__ double p2p_allreduce_elem(const P2PMail& mb, unsigned
 // With `mb` (multi-GPU) the row's value is exchanged with the peers right here: it is stored into every
 // rank's mailbox and the sum over ranks comes back, see the P2PMail section at the end of this file.
 __global__ void __launch_bounds__(1024)
-k_symv_finish(int Np, int N, double sign, const double* __restrict__ rowpart, const double* __restrict__ colpart,
+k_symv_finish(int N, double sign, SymvFold f, const double* __restrict__ rowpart, const double* __restrict__ colpart,
               const int* __restrict__ done, double* __restrict__ out, const P2PMail* __restrict__ mb = nullptr,
-              unsigned int epoch = 0, int J0 = 0, int J1 = 1 << 30 /* strips [J0, J1) are this rank's (multi-GPU split of S) */)
+              unsigned int epoch = 0)
 {
     __shared__ double red[32][33];
     if (done && *done) return;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int r = blockIdx.x * 32 + lane;
-    const int jb = blockIdx.x;                       // r / 32: strips 0..jb have this row
+    const int rb = blockIdx.x, r = rb * 32 + lane;
+    const int b = rb / (kSymvBlkRows / 32);
+    const int rbeg = f.row_ptr[b], nrow = f.row_ptr[b + 1] - rbeg, cbeg = f.col_ptr[rb], nterm = nrow + f.col_ptr[rb + 1] - cbeg;
     double s = 0.0;
-    const int jend = min(jb, J1 - 1);
-    for (int J = J0 + g; J <= jend; J += 32) s += __ldcs(rowpart + (size_t)J * Np + r);
+    for (int q = g; q < nterm; q += 32) s += __ldcs(symv_term(f, rowpart, colpart, rb, lane, rbeg, nrow, cbeg, q));
     red[g][lane] = s;
     __syncthreads();
     if (g == 0 && r < N) {
         double y = 0.0;
-        const int nseg = (jb >= J0 && jb < J1) ? (Np - kSymvCols * jb + kSymvSegRows - 1) / kSymvSegRows : 0;
-        for (int sg = 0; sg < nseg; sg++) y += __ldcs(colpart + (size_t)sg * Np + r);
 #pragma unroll
         for (int q = 0; q < 32; q++) y += red[q][lane];
         y *= sign;
@@ -1505,7 +1544,8 @@ struct PcgPersistArgs {
     const P2PMail* mb;               // multi-GPU exchange or NULL
     unsigned int epoch0;             // mailbox epoch of the first matvec of this launch
     long long* prof;                 // optional: clock64 totals per phase seen by CTA 0 / thread 0 (VLG_BA_PERSIST_PROF), or NULL
-    int J0, J1;                      // strips of S this rank multiplies (all of them on one GPU)
+    SymvFold fold;                   // fragment lists of the row / column partials
+    long long* stat;                 // optional [2 G]: matvec clocks (accumulated) and SM id per CTA (opts.pcg_autotune) or NULL
     int mcl_evict_first;             // stage the cluster inverses with an L2 evict-first hint (VLG_BA_MCL_EVICT overrides)
 };
 
@@ -1532,7 +1572,7 @@ k_pcg_persistent(PcgPersistArgs a)
     static_assert(CA > 0 && CB > 0 && CB <= NC && 2 * NC <= 256, "ring window of the overlapping preconditioner");
     extern __shared__ __align__(128) unsigned char smraw[];
     const SymvSmem sm = symv_smem(smraw);
-    __shared__ double shd[4 * ND], pv[128], pv2[128], rx[256], z2s[128], fold[1][8][33], bcast[ND + 2];
+    __shared__ double shd[4 * ND], pv[128], pv2[128], rx[256], z2s[128], fold[3][8][33], bcast[ND + 2];
     double* const rv = rx + kOwn0;
     __shared__ uint64_t mbarM, mbarM2;
     __shared__ double einv[kDefl * kDefl];
@@ -1547,6 +1587,11 @@ k_pcg_persistent(PcgPersistArgs a)
         mbar_init(&mbarM, 1); mbar_init(&mbarM2, 1);
     }
     if (a.Z && tid < kDefl * kDefl) einv[tid] = a.ds->Einv[tid];     // constant over the solve
+    if (a.stat && tid == 0) {
+        unsigned int smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.stat[2 * blockIdx.x + 1] = (long long)smid;
+    }
     __syncthreads();
     unsigned int bar_target = 0;
     int kbase = 0;
@@ -1570,13 +1615,17 @@ k_pcg_persistent(PcgPersistArgs a)
     long long prof_t = a.prof ? clock64() : 0;
     for (int it = 0; it < a.max_iter; it++) {
         // ---- 1. matvec tiles
-        const long long mv_t0 = a.prof ? clock64() : 0;
+        const long long mv_t0 = (a.prof || a.stat) ? clock64() : 0;
         if (nt > 0) {
             if (producer) symv_producer(sm, a.ld, a.S, a.tiles, t0, nt, kbase, lane);
-            else symv_consumer<true>(sm, a.Np, a.N, a.p, a.tiles, t0, nt, kbase, a.rowpart, a.colpart);
+            else symv_consumer<true>(sm, a.N, a.p, a.tiles, t0, nt, kbase, a.rowpart, a.colpart);
             kbase += nt;
         }
-        if (a.prof && tid == 0) a.prof[16 + cta] += clock64() - mv_t0;      // per-CTA matvec time (load balance of the tile list)
+        if (tid == 0 && (a.prof || a.stat)) {                               // per-CTA matvec time (load balance of the cut)
+            const long long dt = clock64() - mv_t0;
+            if (a.prof) a.prof[32 + cta] += dt;
+            if (a.stat) a.stat[2 * cta] += dt;
+        }
         PCG_PROF(0);
         grid_barrier(a.barrier, bar_target, G);
         PCG_PROF(1);
@@ -1596,46 +1645,62 @@ k_pcg_persistent(PcgPersistArgs a)
                                      smem_u32(sm.st + (size_t)NC * 128)), "l"(a.Mc2 + (size_t)cta * 128 * 128), "r"(bytes2), "r"(smem_u32(&mbarM)) : "memory");
             }
         }
+        PCG_PROF(16);
         if (!producer) {
-            const int gq = tid >> 5;                               // strip group 0..7
-            // row blocks are dealt to the CTAs like a snake draft (block b costs ~b terms): round q gives CTA c the
-            // block q G + c (q even) or q G + G - 1 - c (q odd), counted from the LAST block down; per block the
-            // 256 threads are 32 rows x 8 groups, group gq takes terms gq, gq + 8, ... 16 loads in flight each
-            for (int q = 0; q * G < nrb; q++) {
-                const int idx = q * G + ((q & 1) ? G - 1 - cta : cta);
-                const int rb = nrb - 1 - idx;
-                const bool have = idx < nrb;                        // uniform over the CTA
-                const int r = rb * 32 + lane;
-                double acc = 0.0;
-                if (have) {
-                    // terms 0..rb: row partials of strips 0..rb; then the column partials of this block's segments
-                    // (multi-GPU split of S: only this rank's strips [J0, J1) have partials)
-                    const int nseg = (rb >= a.J0 && rb < a.J1) ? (a.Np - kSymvCols * rb + kSymvSegRows - 1) / kSymvSegRows : 0;
-                    const int nrow = max(0, min(rb, a.J1 - 1) - a.J0 + 1);
-                    const int nterm = nrow + nseg;
-                    for (int q0 = gq; q0 < nterm; q0 += 128) {
-                        double v[16];
+            const int gq = tid >> 5;                               // term group 0..7
+            // 32-row blocks are dealt round-robin to the CTAs, three rounds folded TOGETHER: per block the 256 threads
+            // are 32 rows x 8 groups, group gq takes terms gq, gq + 8, ... of the block's fragment lists; the loads of
+            // all three blocks are issued before the first add and three different warps finish the three blocks.
+            for (int qb = 0; qb * G < nrb; qb += 3) {
+                int rbv[3], rbeg[3], nrowv[3], cbeg[3], ntermv[3];
+                int maxterm = 0;
 #pragma unroll
-                        for (int u = 0; u < 16; u++) {
+                for (int u3 = 0; u3 < 3; u3++) {
+                    const int rb = (qb + u3) * G + cta;
+                    rbv[u3] = rb;
+                    ntermv[u3] = 0; rbeg[u3] = 0; nrowv[u3] = 0; cbeg[u3] = 0;
+                    if (rb < nrb) {                                 // uniform over the CTA
+                        const int b = rb / (kSymvBlkRows / 32);
+                        rbeg[u3] = __ldg(a.fold.row_ptr + b); nrowv[u3] = __ldg(a.fold.row_ptr + b + 1) - rbeg[u3];
+                        cbeg[u3] = __ldg(a.fold.col_ptr + rb); ntermv[u3] = nrowv[u3] + __ldg(a.fold.col_ptr + rb + 1) - cbeg[u3];
+                    }
+                    maxterm = max(maxterm, ntermv[u3]);
+                }
+                double acc[3] = {0.0, 0.0, 0.0};
+                PCG_PROF(17);
+                for (int q0 = gq; q0 < maxterm + gq; q0 += 64) {    // bound uniform over the CTA
+                    double v[3][8];
+#pragma unroll
+                    for (int u3 = 0; u3 < 3; u3++)
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
                             const int tq = q0 + 8 * u;
-                            const double* src = tq < nrow ? a.rowpart + (size_t)(a.J0 + tq) * a.Np + r : a.colpart + (size_t)(tq - nrow) * a.Np + r;
-                            v[u] = tq < nterm ? __ldcg(src) : 0.0;
+                            v[u3][u] = tq < ntermv[u3]
+                                           ? __ldcg(symv_term(a.fold, a.rowpart, a.colpart, rbv[u3], lane, rbeg[u3], nrowv[u3], cbeg[u3], tq))
+                                           : 0.0;
                         }
 #pragma unroll
-                        for (int u = 0; u < 16; u++) acc += v[u];
+                    for (int u3 = 0; u3 < 3; u3++)
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc[u3] += v[u3][u];
+                }
+                PCG_PROF(15);
+                if (qb > 0) consumer_sync();                        // the previous group's sums have been read
+#pragma unroll
+                for (int u3 = 0; u3 < 3; u3++) fold[u3][gq][lane] = acc[u3];
+                consumer_sync();
+                if (gq < 3) {
+                    const int rb = gq == 0 ? rbv[0] : gq == 1 ? rbv[1] : rbv[2];
+                    const int r = rb * 32 + lane;
+                    if (rb < nrb && r < a.N) {
+                        double y = 0.0;
+#pragma unroll
+                        for (int g8 = 0; g8 < 8; g8++) y += fold[gq][g8][lane];
+                        y = -y;
+                        if (a.mb) y = p2p_allreduce_elem(*a.mb, a.epoch0 + (unsigned int)it, r, y);
+                        a.wq[r] = y;
                     }
                 }
-                fold[0][gq][lane] = acc;
-                consumer_sync();
-                if (have && gq == 0 && r < a.N) {
-                    double y = 0.0;
-#pragma unroll
-                    for (int g8 = 0; g8 < 8; g8++) y += fold[0][g8][lane];
-                    y = -y;
-                    if (a.mb) y = p2p_allreduce_elem(*a.mb, a.epoch0 + (unsigned int)it, r, y);
-                    a.wq[r] = y;
-                }
-                consumer_sync();
             }
         }
         PCG_PROF(2);

@@ -93,8 +93,16 @@ struct vlg_ba_ctx {
     bool use_explicit = false;        // PCG on the assembled dense S (k_symv_lower) instead of the two W sweeps
     int4* symv_tiles = nullptr;       // tile list of k_symv_lower, grouped per CTA
     int* symv_tile_ptr = nullptr;
-    int symv_grid = 0, nsymv_seg = 0;
-    double *symv_rowpart = nullptr, *symv_colpart = nullptr;
+    int symv_grid = 0, symv_nfrag = 0;
+    double *symv_rowpart = nullptr, *symv_colpart = nullptr;   // [nfrag][kSymvBlkRows], [nfrag][32 kSymvSlab]
+    int *symv_row_ptr = nullptr, *symv_row_list = nullptr, *symv_col_ptr = nullptr, *symv_col_list = nullptr;   // fold lists (SymvFold)
+    // the tile sequence and its cost prefix (host), the per-CTA speed weights the cut uses, and their measurement
+    struct SymvTileH { int strip, r0, rows, cell, sl; };
+    std::vector<SymvTileH> h_symv_seq;
+    std::vector<double> h_symv_cum, symv_speed;
+    std::vector<int> h_symv_tptr, symv_smid;
+    int symv_ncell = 0, symv_learn_left = 0;
+    long long* symv_stat = nullptr;           // device [2 G]: matvec clocks of the last solve, SM id, per CTA
     unsigned int* persist_bar = nullptr;   // grid barrier counter of k_pcg_persistent
     unsigned int* init_bar = nullptr;      // ... of k_pcg_init_defl_coop
     double* init_part = nullptr;           // its block partials [17 x coop_grid]
@@ -360,6 +368,91 @@ int reduce_to(vlg_ba_ctx* ctx, const double* in, size_t n, double* out)
 }
 
 // ---- problem set-up ----------------------------------------------------------------------------
+// Cuts the tile sequence of the explicit-S matvec into one contiguous piece per persistent CTA -- cost proportional to
+// the CTA's speed weight (1 at first; re-measured over the first solves: the SMs of a B200 do not all stream at the
+// same rate, +-4 % by position) -- and rebuilds what depends on the cut: tile flags, fragments, fold lists.  The
+// partial results are indexed by fragment and folded in list order, so the product does not depend on the cut's bits
+// only through the order of summation inside a row (covered by the PCG tolerance, identical on every rank).
+int symv_partition(vlg_ba_ctx* ctx)
+{
+    const std::vector<vlg_ba_ctx::SymvTileH>& seq = ctx->h_symv_seq;
+    const std::vector<double>& cum = ctx->h_symv_cum;
+    const int G = ctx->symv_grid, Np = ctx->Np, nstrips = Np / kSymvCols;
+    std::vector<int>& tptr = ctx->h_symv_tptr;
+    tptr.assign((size_t)G + 1, 0);
+    double wsum = 0.0, wacc = 0.0;
+    for (int g = 0; g < G; g++) wsum += ctx->symv_speed[(size_t)g];
+    for (int g = 1; g < G; g++) {
+        wacc += ctx->symv_speed[(size_t)g - 1];
+        const double target = cum.back() * wacc / wsum;
+        tptr[g] = std::max(tptr[g - 1], (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin()));
+        tptr[g] = std::min(tptr[g], (int)seq.size());
+    }
+    tptr[G] = (int)seq.size();
+    // fragments: maximal runs of one cell inside one CTA's piece; flags and fold lists
+    std::vector<int4> tiles(seq.size());
+    const int nrowblk = (Np + kSymvBlkRows - 1) / kSymvBlkRows;
+    std::vector<std::vector<int>> rowl((size_t)nrowblk), coll((size_t)nstrips);
+    int nfrag = 0;
+    for (int g = 0; g < G; g++)
+        for (int t = tptr[g]; t < tptr[g + 1]; t++) {
+            const vlg_ba_ctx::SymvTileH& c = seq[(size_t)t];
+            const bool ffrag = t == tptr[g] || seq[(size_t)t - 1].cell != c.cell;
+            const bool lfrag = t + 1 == tptr[g + 1] || seq[(size_t)t + 1].cell != c.cell;
+            const bool fstrip = ffrag || seq[(size_t)t - 1].strip != c.strip;
+            const bool lstrip = lfrag || seq[(size_t)t + 1].strip != c.strip;
+            if (ffrag) { nfrag++; rowl[(size_t)(c.r0 / kSymvBlkRows)].push_back(nfrag - 1); }
+            if (fstrip) coll[(size_t)c.strip].push_back((nfrag - 1) * kSymvCols * kSymvSlab + kSymvCols * c.sl);
+            const int flags = (fstrip ? kSymvFirstStrip : 0) | (lstrip ? kSymvLastStrip : 0) | (ffrag ? kSymvFirstFrag : 0) | (lfrag ? kSymvLastFrag : 0);
+            tiles[(size_t)t] = make_int4(c.strip, c.r0, c.rows | flags, (nfrag - 1) | (c.sl << 20));
+        }
+    std::vector<int> rptr(1, 0), rlist, cptr(1, 0), clist;
+    for (auto& v : rowl) { rlist.insert(rlist.end(), v.begin(), v.end()); rptr.push_back((int)rlist.size()); }
+    for (auto& v : coll) { clist.insert(clist.end(), v.begin(), v.end()); cptr.push_back((int)clist.size()); }
+    ctx->symv_nfrag = nfrag;
+    CHK(upload(ctx, ctx->symv_tiles, tiles.data(), tiles.size()));
+    CHK(upload(ctx, ctx->symv_tile_ptr, tptr.data(), tptr.size()));
+    CHK(upload(ctx, ctx->symv_row_ptr, rptr.data(), rptr.size())); CHK(upload(ctx, ctx->symv_row_list, rlist.data(), rlist.size()));
+    CHK(upload(ctx, ctx->symv_col_ptr, cptr.data(), cptr.size())); CHK(upload(ctx, ctx->symv_col_list, clist.data(), clist.size()));
+    CU(cudaStreamSynchronize(ctx->stream));      // the host vectors go out of scope
+    return VLG_BA_OK;
+}
+
+// After a solve by the persistent kernel: per-CTA matvec clocks -> speed weights -> new cut (first solves of a problem only).
+int symv_learn(vlg_ba_ctx* ctx)
+{
+    if (ctx->symv_learn_left <= 0 || !ctx->symv_stat) return VLG_BA_OK;
+    const int G = ctx->symv_grid;
+    std::vector<long long> st((size_t)2 * G);
+    CU(cudaMemcpyAsync(st.data(), ctx->symv_stat, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemsetAsync(ctx->symv_stat, 0, sizeof(long long) * st.size(), ctx->stream));
+    std::vector<int> smid((size_t)G);
+    for (int g = 0; g < G; g++) smid[(size_t)g] = (int)st[(size_t)2 * g + 1];
+    if (!ctx->symv_smid.empty() && smid != ctx->symv_smid) {
+        // the CTAs landed on other SMs than the weights were measured on: start over
+        ctx->symv_speed.assign((size_t)G, 1.0);
+        ctx->symv_smid = smid;
+        return symv_partition(ctx);
+    }
+    ctx->symv_smid = smid;
+    double mean = 0.0;
+    std::vector<double> sp((size_t)G, 0.0);
+    for (int g = 0; g < G; g++) {
+        const double cost = ctx->h_symv_cum[(size_t)ctx->h_symv_tptr[(size_t)g + 1]] - ctx->h_symv_cum[(size_t)ctx->h_symv_tptr[(size_t)g]];
+        const double clk = (double)st[(size_t)2 * g];
+        if (!(cost > 0.0) || !(clk > 0.0)) return VLG_BA_OK;       // a CTA without work or without a measurement: keep the cut
+        sp[(size_t)g] = cost / clk;
+        mean += sp[(size_t)g] / G;
+    }
+    for (int g = 0; g < G; g++) {
+        const double rel = std::min(1.25, std::max(0.8, sp[(size_t)g] / mean));
+        ctx->symv_speed[(size_t)g] = rel;
+    }
+    ctx->symv_learn_left--;
+    return symv_partition(ctx);
+}
+
 int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* a, const double* b, int64_t nobs,
                   const double* obs_xy, const int32_t* obs_pt, const int32_t* obs_cam, const double* pivot)
 {
@@ -637,15 +730,12 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         }
     }
     if (ctx->use_explicit) {
-        // work items = strip segments of <= kSymvSegRows rows, spread over one persistent CTA per SM by
-        // longest-processing-time-first; each CTA's items are flattened into 256-row tiles
+        // tiles of the lower triangle in cell order (cells = kSymvSlab strips x kSymvBlkRows rows, strip by strip inside a
+        // cell), cut into one contiguous, equally expensive piece per persistent CTA; see ba_pcg.cuh (SymvSmem)
         const int Np = ctx->Np, nstrips = Np / kSymvCols;
-        struct Item { int strip, seg, r0, rows; };
-        std::vector<Item> items;
-        // multi-GPU (set_comm before set_problem): every rank assembles its share of S in full, one grouped
-        // ncclReduce per LM step leaves rank r with the SUM of its column block (strips [J_r, J_r+1), chosen so
-        // that every rank gets the same lower-triangle area), and the matvec of rank r only walks those strips;
-        // the partial products meet in the same vector exchange as before
+        // multi-GPU (set_comm before set_problem): every rank assembles its share of S in full, rank r then holds the SUM
+        // of its column block (strips [J_r, J_r+1), chosen so that every rank gets the same lower-triangle area), and the
+        // matvec of rank r only walks those strips; the partial products meet in the same vector exchange as before
         ctx->s_split = ctx->nranks > 1 && g_nccl.Reduce && g_nccl.GroupStart && g_nccl.GroupEnd;
         ctx->s_bounds.assign((size_t)ctx->nranks + 1, nstrips);
         ctx->s_bounds[0] = 0;
@@ -657,42 +747,54 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         }
         ctx->s_J0 = ctx->s_split ? ctx->s_bounds[(size_t)ctx->rank] : 0;
         ctx->s_J1 = ctx->s_split ? ctx->s_bounds[(size_t)ctx->rank + 1] : nstrips;
-        for (int J = ctx->s_J0; J < ctx->s_J1; J++)
-            for (int sg = 0, r0 = kSymvCols * J; r0 < Np; sg++, r0 += kSymvSegRows)
-                items.push_back({J, sg, r0, std::min(kSymvSegRows, Np - r0)});
-        std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.rows > b.rows; });
-        const int G = std::max(1, std::min(ctx->nsm, (int)items.size()));
-        std::vector<std::vector<Item>> mine((size_t)G);
-        std::vector<int64_t> load((size_t)G, 0);
-        for (const Item& it : items) {
-            int best = 0;
-            for (int g = 1; g < G; g++) if (load[g] < load[best]) best = g;
-            mine[best].push_back(it); load[best] += it.rows + 24 * ((it.rows + kSymvRows - 1) / kSymvRows) + 40;   // rows + per-tile and per-item overheads
-        }
-        std::vector<int4> tiles;
-        std::vector<int> tptr((size_t)G + 1, 0);
-        for (int g = 0; g < G; g++) {
-            for (const Item& it : mine[g])
-                for (int r = 0; r < it.rows; r += kSymvRows) {
-                    const int rows = std::min(kSymvRows, it.rows - r);
-                    const int flags = (r == 0 ? 1 << 16 : 0) | (r + kSymvRows >= it.rows ? 1 << 17 : 0);
-                    tiles.push_back(make_int4(it.strip, it.r0 + r, rows | flags, it.seg));
+        std::vector<vlg_ba_ctx::SymvTileH>& seq = ctx->h_symv_seq;
+        seq.clear();
+        int ncell = 0;
+        for (int Js = ctx->s_J0; Js < ctx->s_J1; Js += kSymvSlab) {
+            const int Je = std::min(ctx->s_J1, Js + kSymvSlab);
+            for (int b0 = (kSymvCols * Js) / kSymvBlkRows * kSymvBlkRows; b0 < Np; b0 += kSymvBlkRows, ncell++)
+                for (int J = Js; J < Je; J++) {
+                    int lo = std::max(kSymvCols * J, b0);
+                    const int hi = std::min(Np, b0 + kSymvBlkRows);
+                    while (lo < hi) {
+                        const int nx = std::min(hi, (lo / kSymvRows + 1) * kSymvRows);
+                        seq.push_back({J, lo, nx - lo, ncell, J - Js});
+                        lo = nx;
+                    }
                 }
-            tptr[g + 1] = (int)tiles.size();
+        }
+        const int G = std::max(1, std::min(ctx->nsm, (int)seq.size()));
+        // cost of a tile in row units (a 256-row tile streams in ~1.4 us): its rows, but never less than the ring's latency
+        // floor, plus a fixed part (barrier waits, descriptor, x prefetch); the first tile of a run in a strip also pays the
+        // strip's x (an exposed L2 round trip) and the column reduction at the run's end
+        ctx->h_symv_cum.assign(seq.size() + 1, 0.0);
+        for (size_t t = 0; t < seq.size(); t++) {
+            const bool newrun = t == 0 || seq[t - 1].strip != seq[t].strip || seq[t - 1].cell != seq[t].cell;
+            ctx->h_symv_cum[t + 1] = ctx->h_symv_cum[t] + std::max(seq[t].rows, 64) + 40 + (newrun ? 150 : 0);
         }
         ctx->symv_grid = G;
-        ctx->nsymv_seg = (Np + kSymvSegRows - 1) / kSymvSegRows;
-        CHK(dalloc(ctx, &ctx->symv_tiles, tiles.size())); CHK(dalloc(ctx, &ctx->symv_tile_ptr, tptr.size()));
-        CHK(upload(ctx, ctx->symv_tiles, tiles.data(), tiles.size()));
-        CHK(upload(ctx, ctx->symv_tile_ptr, tptr.data(), tptr.size()));
-        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->symv_ncell = ncell;
+        ctx->symv_speed.assign((size_t)G, 1.0);
+        ctx->symv_smid.clear();
+        {
+            const char* e = getenv("VLG_BA_SYMV_LEARN");     // overrides opts.pcg_autotune
+            ctx->symv_learn_left = e ? atoi(e) : o.pcg_autotune;
+        }
+        const size_t nfrag_max = (size_t)ncell + G, nrun_max = (size_t)ncell * kSymvSlab + G;
+        CHK(dalloc(ctx, &ctx->symv_tiles, seq.size())); CHK(dalloc(ctx, &ctx->symv_tile_ptr, (size_t)G + 1));
+        CHK(dalloc(ctx, &ctx->symv_row_ptr, (size_t)(Np + kSymvBlkRows - 1) / kSymvBlkRows + 1)); CHK(dalloc(ctx, &ctx->symv_row_list, nfrag_max));
+        CHK(dalloc(ctx, &ctx->symv_col_ptr, (size_t)nstrips + 1)); CHK(dalloc(ctx, &ctx->symv_col_list, nrun_max));
+        CHK(dalloc(ctx, &ctx->symv_rowpart, nfrag_max * kSymvBlkRows));
+        CHK(dalloc(ctx, &ctx->symv_colpart, nfrag_max * kSymvCols * kSymvSlab));
+        CHK(dalloc(ctx, &ctx->symv_stat, (size_t)2 * G));
+        CU(cudaMemsetAsync(ctx->symv_stat, 0, sizeof(long long) * 2 * G, ctx->stream));
+        CHK(symv_partition(ctx));
         CHK(dalloc(ctx, &ctx->persist_bar, 1));
         {
             const char* e = getenv("VLG_BA_PERSIST");      // 0: one launch per PCG phase instead of the persistent kernel
             ctx->persist_ok = e ? atoi(e) != 0 : true;
         }
-        CHK(dalloc(ctx, &ctx->symv_rowpart, (size_t)nstrips * Np));
-        CHK(dalloc(ctx, &ctx->symv_colpart, (size_t)ctx->nsymv_seg * Np));
+
     }
     if (ctx->use_chol) {
         const int nb = ctx->Np / kNB;

@@ -232,13 +232,13 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             if (ctx->use_explicit) {
                 // wq = (sum Y W') v = -(S - U*) v from the lower triangle of the assembled S
                 TimedScope ts(ctx, T_SYMV);
-                k_symv_lower<<<ctx->symv_grid, kSymvRows + 32, kSymvSmem, ctx->stream>>>(ctx->Np, ctx->Np, N, ctx->S, v, ctx->symv_tile_ptr,
+                k_symv_lower<<<ctx->symv_grid, kSymvRows + 32, kSymvSmem, ctx->stream>>>(ctx->Np, N, ctx->S, v, ctx->symv_tile_ptr,
                                                                                    ctx->symv_tiles, dn, ctx->symv_rowpart, ctx->symv_colpart);
+                const SymvFold fl{ctx->symv_row_ptr, ctx->symv_row_list, ctx->symv_col_ptr, ctx->symv_col_list};
                 const bool fused = ctx->nranks > 1 && ctx->p2p_ready;     // the exchange with the peers happens inside the finish kernel
                 if (fused) ctx->p2p_epoch++;
-                k_symv_finish<<<ctx->Np / 32, 1024, 0, ctx->stream>>>(ctx->Np, N, -1.0, ctx->symv_rowpart, ctx->symv_colpart, dn, ctx->wq,
-                                                                      fused ? ctx->p2p_dev : nullptr, ctx->p2p_epoch,
-                                                                      ctx->s_split ? ctx->s_J0 : 0, ctx->s_split ? ctx->s_J1 : 1 << 30);
+                k_symv_finish<<<ctx->Np / 32, 1024, 0, ctx->stream>>>(N, -1.0, fl, ctx->symv_rowpart, ctx->symv_colpart, dn, ctx->wq,
+                                                                      fused ? ctx->p2p_dev : nullptr, ctx->p2p_epoch);
                 ctx->launches += 2;
                 CU(cudaGetLastError());
                 if (!fused) CHK(allreduce_pcg_vector(ctx, ctx->wq, N, dn));
@@ -326,16 +326,17 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             pa.sc = ctx->pcg_sc; pa.blkpart = ctx->blkpart; pa.Z = defl ? ctx->Zd : nullptr; pa.SZ = defl ? ctx->SZd : nullptr;
             pa.ds = ctx->defl_sc; pa.barrier = ctx->persist_bar;
             pa.mb = ctx->nranks > 1 ? ctx->p2p_dev : nullptr; pa.epoch0 = ctx->p2p_epoch + 1;
-            pa.J0 = ctx->s_split ? ctx->s_J0 : 0; pa.J1 = ctx->s_split ? ctx->s_J1 : 1 << 30;
+            pa.fold = SymvFold{ctx->symv_row_ptr, ctx->symv_row_list, ctx->symv_col_ptr, ctx->symv_col_list};
             pa.prof = nullptr;
+            pa.stat = ctx->symv_learn_left > 0 ? ctx->symv_stat : nullptr;
             // staging the cluster inverses with an evict-first hint keeps them (22 MB with both partitions) from crowding the matvec's
             // partials out of L2: measured -2.2 us (matvec phase) + 0.9 us (fold) per iteration at Venice shape
             { const char* e = getenv("VLG_BA_MCL_EVICT"); pa.mcl_evict_first = e ? atoi(e) : (overlap ? 1 : 0); }
             static long long* d_prof = nullptr;
             const bool want_prof = getenv("VLG_BA_PERSIST_PROF") != nullptr;
             if (want_prof) {
-                if (!d_prof) cudaMalloc(&d_prof, (16 + 1024) * sizeof(long long));
-                cudaMemsetAsync(d_prof, 0, (16 + 1024) * sizeof(long long), ctx->stream);
+                if (!d_prof) cudaMalloc(&d_prof, (32 + 1024) * sizeof(long long));
+                cudaMemsetAsync(d_prof, 0, (32 + 1024) * sizeof(long long), ctx->stream);
                 pa.prof = d_prof;
             }
             CU(cudaMemsetAsync(ctx->persist_bar, 0, sizeof(unsigned int), ctx->stream));
@@ -348,18 +349,19 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             if (ctx->nranks > 1) ctx->p2p_epoch += (unsigned int)ctx->h_pcg->iters;       // one mailbox epoch per matvec, on every rank
+            if (pa.stat && ctx->h_pcg->iters > 0) CHK(symv_learn(ctx));
             if (want_prof) {
-                long long hp[16];
+                long long hp[18];
                 cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
                 int khz = 0;
                 cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
-                const char* nm[15] = {"matvec", "barrier", "fold", "barrier", "phase3", "barrier", "phase4-rest", "barrier", "phase5", "barrier",
-                                      "p4:x,r", "p4:wait-McL", "p4:matvec", "p4:partials", "p4:sync"};
+                const char* nm[18] = {"matvec", "barrier", "fold-rest", "barrier", "phase3", "barrier", "phase4-rest", "barrier", "phase5", "barrier",
+                                      "p4:x,r", "p4:wait-McL", "p4:matvec", "p4:partials", "p4:sync", "fold:loads", "fold:tma-issue", "fold:list-ptrs"};
                 fprintf(stderr, "k_pcg_persistent, %d iterations, us per iteration (CTA 0):", ctx->h_pcg->iters);
-                for (int k = 0; k < 15; k++) fprintf(stderr, " %s %.1f", nm[k], hp[k] / (khz * 1e-3) / std::max(ctx->h_pcg->iters, 1));
+                for (int k = 0; k < 18; k++) fprintf(stderr, " %s %.1f", nm[k], hp[k] / (khz * 1e-3) / std::max(ctx->h_pcg->iters, 1));
                 fprintf(stderr, "\n");
                 std::vector<long long> hc((size_t)ctx->symv_grid);
-                cudaMemcpy(hc.data(), d_prof + 16, sizeof(long long) * hc.size(), cudaMemcpyDeviceToHost);
+                cudaMemcpy(hc.data(), d_prof + 32, sizeof(long long) * hc.size(), cudaMemcpyDeviceToHost);
                 fprintf(stderr, "  matvec us per iteration by CTA:");
                 for (size_t k = 0; k < hc.size(); k++) fprintf(stderr, " %.1f", hc[k] / (khz * 1e-3) / std::max(ctx->h_pcg->iters, 1));
                 fprintf(stderr, "\n");
@@ -588,6 +590,7 @@ void vlg_ba_opts_default(vlg_ba_opts* o)
     o->pcg_deflate = 1;
     o->pcg_cluster = 1;
     o->model = VLG_BA_MODEL_EUCLID;
+    o->pcg_autotune = 0;
 }
 
 const char* vlg_ba_version(void) { return "vlgba 0.1 (sm_100a, fp64)"; }

@@ -77,6 +77,10 @@ typedef struct vlg_ba_opts {
     int    pcg_cluster;       /* 1 (default): PCG preconditions with the inverses of 128/num_a-camera diagonal blocks of S
                                  (cluster-Jacobi) instead of per-camera blocks */
     int    model;             /* VLG_BA_MODEL_* (default EUCLID) */
+    int    pcg_autotune;      /* 0 (default): the assembled-S matvec is cut into equal pieces per SM -- results are bit-reproducible
+                                 from run to run.  n > 0: over the first n solves of a problem the cut is re-weighted by the measured
+                                 per-SM streaming rate (SMs differ by +-4 % with position): ~4 % faster PCG iterations, results
+                                 still deterministic for a given cut but the cut depends on the measurement */
 } vlg_ba_opts;
 
 typedef struct vlg_ba_ctx vlg_ba_ctx;
