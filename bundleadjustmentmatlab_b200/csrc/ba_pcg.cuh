@@ -1315,13 +1315,21 @@ __device__ __forceinline__ void symv_producer(const SymvSmem& sm, int ld, const 
     }
 }
 
+// x_r: plain, or x_r + beta xp_r when xp is given (the persistent PCG kernel multiplies by p = z + beta p_old without
+// waiting for anyone to store p)
 template <bool L2X>
-__device__ __forceinline__ double symv_ldx(const double* x) { return L2X ? __ldcg(x) : __ldg(x); }
+__device__ __forceinline__ double symv_ldx(const double* x, const double* xp, double beta, int r)
+{
+    if (!L2X) return __ldg(x + r);
+    const double v = __ldcg(x + r);
+    return xp ? fma(beta, __ldcg(xp + r), v) : v;
+}
 
 template <bool L2X>
 __device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int N, const double* __restrict__ x,
                                               const int4* __restrict__ tiles, int t0, int nt, int kbase,
-                                              double* __restrict__ rowpart, double* __restrict__ colpart)
+                                              double* __restrict__ rowpart, double* __restrict__ colpart,
+                                              const double* __restrict__ xp = nullptr, double beta = 0.0)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double colacc[kSymvCols];
@@ -1332,7 +1340,7 @@ __device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int N, const d
     double xr_next = 0.0;
     {
         const int r = (dn.y & ~(kSymvRows - 1)) + tid;
-        if (r >= dn.y && r < dn.y + (dn.z & 0xffff) && r < N) xr_next = symv_ldx<L2X>(x + r);
+        if (r >= dn.y && r < dn.y + (dn.z & 0xffff) && r < N) xr_next = symv_ldx<L2X>(x, xp, beta, r);
     }
     for (int k = 0; k < nt; k++) {
         const int g = kbase + k, slot = g % kSymvStages;
@@ -1343,14 +1351,14 @@ __device__ __forceinline__ void symv_consumer(const SymvSmem& sm, int N, const d
         if (k + 1 < nt) {
             dn = __ldg(tiles + t0 + k + 1);
             const int rn = (dn.y & ~(kSymvRows - 1)) + tid;
-            xr_next = (rn >= dn.y && rn < dn.y + (dn.z & 0xffff) && rn < N) ? symv_ldx<L2X>(x + rn) : 0.0;
+            xr_next = (rn >= dn.y && rn < dn.y + (dn.z & 0xffff) && rn < N) ? symv_ldx<L2X>(x, xp, beta, rn) : 0.0;
         }
         if (d.z & kSymvFirstFrag) {                 // own slots only: no barrier
 #pragma unroll
             for (int i = 0; i < kSymvBlkRows / kSymvRows; i++) sm.yacc[tid + kSymvRows * i] = 0.0;
         }
         if (d.z & kSymvFirstStrip) {                // first tile of a run in this strip: the strip's x
-            if (tid < kSymvCols) sm.xs[tid] = (c0 + tid < N) ? symv_ldx<L2X>(x + c0 + tid) : 0.0;
+            if (tid < kSymvCols) sm.xs[tid] = (c0 + tid < N) ? symv_ldx<L2X>(x, xp, beta, c0 + tid) : 0.0;
             consumer_sync();
         }
         mbar_wait(sm.full + slot, (uint32_t)((g / kSymvStages) & 1));
@@ -1536,6 +1544,7 @@ struct PcgPersistArgs {
     const double *Ud, *Minv, *McL;
     const double* Mc2;               // composite rows of the shifted partition's inverses (overlapping preconditioner) or NULL
     double *x, *r, *p;
+    double *p2, *zbuf;               // second p buffer and z: iteration k multiplies by z + beta p_old read from these (no barrier for p)
     PcgScalars* sc;
     double* blkpart;                 // 11 * nclusters
     const double *Z, *SZ;            // deflation vectors or NULL
@@ -1563,6 +1572,7 @@ __global__ void __launch_bounds__(kSymvRows + 32, 1)
 k_pcg_persistent(PcgPersistArgs a)
 {
     constexpr int ND = 1 + 2 * kDefl;
+    static_assert(ND <= (kSymvRows + 32) / 32, "one warp per scalar partial");
     using CL = Cluster<NA>;
     constexpr int kCams = 128 / NA, NC = kCams * NA;
     // overlapping preconditioner: the ring memory holds 192 columns of 128 doubles -- M1 (NC columns) and the first CA
@@ -1575,6 +1585,7 @@ k_pcg_persistent(PcgPersistArgs a)
     __shared__ double shd[4 * ND], pv[128], pv2[128], rx[256], z2s[128], fold[3][8][33], bcast[ND + 2];
     double* const rv = rx + kOwn0;
     __shared__ uint64_t mbarM, mbarM2;
+    __shared__ int fterm[3][64], fmeta[3][4];      // fold terms of this CTA's first three row blocks (constant over the solve)
     __shared__ double einv[kDefl * kDefl];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, G = gridDim.x, nb = a.nclusters;
@@ -1592,11 +1603,30 @@ k_pcg_persistent(PcgPersistArgs a)
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         a.stat[2 * blockIdx.x + 1] = (long long)smid;
     }
+    // the fold lists of the CTA's first three 32-row blocks, resolved to offsets once: row partials as offsets into rowpart,
+    // column partials as offsets into colpart with the sign bit set (an acquire at every grid barrier empties L1, so reading
+    // pointer -> list -> data from global was three dependent L2 round trips per iteration)
+    for (int u3 = 0; u3 < 3; u3++) {
+        const int rb = u3 * (int)gridDim.x + (int)blockIdx.x;
+        int rbeg = 0, nrow = 0, cbeg = 0, nterm = 0;
+        if (rb < a.Np / 32) {
+            const int b = rb / (kSymvBlkRows / 32);
+            rbeg = a.fold.row_ptr[b]; nrow = a.fold.row_ptr[b + 1] - rbeg;
+            cbeg = a.fold.col_ptr[rb]; nterm = nrow + a.fold.col_ptr[rb + 1] - cbeg;
+        }
+        if (tid < 64 && tid < nterm)
+            fterm[u3][tid] = tid < nrow ? a.fold.row_list[rbeg + tid] * kSymvBlkRows + ((rb & (kSymvBlkRows / 32 - 1)) << 5)
+                                        : (int)(0x80000000u | (unsigned int)a.fold.col_list[cbeg + tid - nrow]);
+        if (tid == 0) { fmeta[u3][0] = rbeg; fmeta[u3][1] = nrow; fmeta[u3][2] = cbeg; fmeta[u3][3] = nterm; }
+    }
     __syncthreads();
     unsigned int bar_target = 0;
     int kbase = 0;
     const double r0n2 = a.sc->r0n2;
     double rz = a.sc->rz;
+    // p of iteration k lives in buffer k & 1 (a.p, a.p2), stored by its owner once beta is known and read by the halo
+    // threads two barriers later; the matvec does not wait for it: it forms z + beta p_old itself
+    double beta_prev = 0.0, pt_next = 0.0;
     const int lc = tid / NA, row = tid - lc * NA;             // update role: local camera, row (threads < 128)
     const int j = cta * kCams + lc;
     const bool act = cluster_cta && tid < 128 && lc < kCams && j < a.m;
@@ -1618,7 +1648,8 @@ k_pcg_persistent(PcgPersistArgs a)
         const long long mv_t0 = (a.prof || a.stat) ? clock64() : 0;
         if (nt > 0) {
             if (producer) symv_producer(sm, a.ld, a.S, a.tiles, t0, nt, kbase, lane);
-            else symv_consumer<true>(sm, a.N, a.p, a.tiles, t0, nt, kbase, a.rowpart, a.colpart);
+            else if (it == 0) symv_consumer<true>(sm, a.N, a.p, a.tiles, t0, nt, kbase, a.rowpart, a.colpart);
+            else symv_consumer<true>(sm, a.N, a.zbuf, a.tiles, t0, nt, kbase, a.rowpart, a.colpart, (it & 1) ? a.p : a.p2, beta_prev);
             kbase += nt;
         }
         if (tid == 0 && (a.prof || a.stat)) {                               // per-CTA matvec time (load balance of the cut)
@@ -1660,9 +1691,13 @@ k_pcg_persistent(PcgPersistArgs a)
                     rbv[u3] = rb;
                     ntermv[u3] = 0; rbeg[u3] = 0; nrowv[u3] = 0; cbeg[u3] = 0;
                     if (rb < nrb) {                                 // uniform over the CTA
-                        const int b = rb / (kSymvBlkRows / 32);
-                        rbeg[u3] = __ldg(a.fold.row_ptr + b); nrowv[u3] = __ldg(a.fold.row_ptr + b + 1) - rbeg[u3];
-                        cbeg[u3] = __ldg(a.fold.col_ptr + rb); ntermv[u3] = nrowv[u3] + __ldg(a.fold.col_ptr + rb + 1) - cbeg[u3];
+                        if (qb == 0) {
+                            rbeg[u3] = fmeta[u3][0]; nrowv[u3] = fmeta[u3][1]; cbeg[u3] = fmeta[u3][2]; ntermv[u3] = fmeta[u3][3];
+                        } else {
+                            const int b = rb / (kSymvBlkRows / 32);
+                            rbeg[u3] = __ldg(a.fold.row_ptr + b); nrowv[u3] = __ldg(a.fold.row_ptr + b + 1) - rbeg[u3];
+                            cbeg[u3] = __ldg(a.fold.col_ptr + rb); ntermv[u3] = nrowv[u3] + __ldg(a.fold.col_ptr + rb + 1) - cbeg[u3];
+                        }
                     }
                     maxterm = max(maxterm, ntermv[u3]);
                 }
@@ -1670,15 +1705,28 @@ k_pcg_persistent(PcgPersistArgs a)
                 PCG_PROF(17);
                 for (int q0 = gq; q0 < maxterm + gq; q0 += 64) {    // bound uniform over the CTA
                     double v[3][8];
+                    if (qb == 0 && q0 < 64) {
+                        // the common case: offsets from shared memory, one L2 round trip for all the partials
 #pragma unroll
-                    for (int u3 = 0; u3 < 3; u3++)
+                        for (int u3 = 0; u3 < 3; u3++)
 #pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            const int tq = q0 + 8 * u;
-                            v[u3][u] = tq < ntermv[u3]
-                                           ? __ldcg(symv_term(a.fold, a.rowpart, a.colpart, rbv[u3], lane, rbeg[u3], nrowv[u3], cbeg[u3], tq))
-                                           : 0.0;
-                        }
+                            for (int u = 0; u < 8; u++) {
+                                const int tq = q0 + 8 * u;
+                                const int off = fterm[u3][tq];
+                                const double* src = off >= 0 ? a.rowpart + off + lane : a.colpart + (off & 0x7fffffff) + lane;
+                                v[u3][u] = tq < ntermv[u3] ? __ldcg(src) : 0.0;
+                            }
+                    } else {
+#pragma unroll
+                        for (int u3 = 0; u3 < 3; u3++)
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const int tq = q0 + 8 * u;
+                                v[u3][u] = tq < ntermv[u3]
+                                               ? __ldcg(symv_term(a.fold, a.rowpart, a.colpart, rbv[u3], lane, rbeg[u3], nrowv[u3], cbeg[u3], tq))
+                                               : 0.0;
+                            }
+                    }
 #pragma unroll
                     for (int u3 = 0; u3 < 3; u3++)
 #pragma unroll
@@ -1717,7 +1765,7 @@ k_pcg_persistent(PcgPersistArgs a)
         const int nd = a.Z ? ND : 1;
         if (cluster_cta && tid < 128) {
             if (act) {
-                pt = __ldcg(a.p + t); pv[tid] = pt;
+                pt = it == 0 ? __ldcg(a.p + t) : pt_next; pv[tid] = pt;
                 xt = __ldcg(a.x + t); rt0 = __ldcg(a.r + t);
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -1751,7 +1799,7 @@ k_pcg_persistent(PcgPersistArgs a)
 #pragma unroll
         for (int d = 0; d < kDefl; d++) szh[d] = 0.0;
         if (hrole) {
-            if (hact) { pv2[h] = __ldcg(a.p + gh); rh0 = __ldcg(a.r + gh); }
+            if (hact) { pv2[h] = __ldcg(((it & 1) ? a.p2 : a.p) + gh); rh0 = __ldcg(a.r + gh); }
             asm volatile("bar.sync 3, 128;" ::: "memory");
             if (hact) {
                 double v = 0.0;
@@ -1772,28 +1820,25 @@ k_pcg_persistent(PcgPersistArgs a)
         // serialises one L2 round trip per scalar: measured 10 us of an iteration)
         // ONE warp per CTA reads the partials (148 x 9 warps hammering the same 6 KB of L2 cost 9 us per
         // iteration) and publishes the sums through shared memory
-        if (warp == 0) {
-            // every load is issued before the first add: an add placed right behind its load stalls the
-            // in-order issue for a whole L2 round trip (27 of them cost 6.7 us here)
+        // every warp of every CTA would read the same 6 KB of L2 (148 x 9 warps: 9 us per iteration, measured); instead
+        // warp k folds scalar k (ND = 9 scalars, 9 warps) -- all its loads before the first add -- and publishes the sum
+        // through shared memory
+        if (warp < nd) {
             constexpr int KB = 5;                      // nb <= 160 clusters covered in one pass
-            double ldv[ND][KB];
+            double ldv[KB];
 #pragma unroll
-            for (int k = 0; k < ND; k++)
-#pragma unroll
-                for (int u = 0; u < KB; u++) {
-                    const int b = lane + 32 * u;
-                    ldv[k][u] = (k < nd && b < nb) ? __ldcg(a.blkpart + (size_t)k * nb + b) : 0.0;
-                }
-#pragma unroll
-            for (int k = 0; k < ND; k++) {
-                double v = 0.0;
-#pragma unroll
-                for (int u = 0; u < KB; u++) v += ldv[k][u];
-                if (k < nd)
-                    for (int b = lane + 32 * KB; b < nb; b += 32) v += __ldcg(a.blkpart + (size_t)k * nb + b);
-                v = k < nd ? warp_sum(v) : 0.0;
-                if (lane == 0) bcast[k] = v;
+            for (int u = 0; u < KB; u++) {
+                const int b = lane + 32 * u;
+                ldv[u] = b < nb ? __ldcg(a.blkpart + (size_t)warp * nb + b) : 0.0;
             }
+            double v = 0.0;
+#pragma unroll
+            for (int u = 0; u < KB; u++) v += ldv[u];
+            for (int b = lane + 32 * KB; b < nb; b += 32) v += __ldcg(a.blkpart + (size_t)warp * nb + b);
+            v = warp_sum(v);
+            if (lane == 0) bcast[warp] = v;
+        } else if (warp < ND && lane == 0) {
+            bcast[warp] = 0.0;
         }
         PCG_PROF(13);
         __syncthreads();
@@ -1911,7 +1956,7 @@ k_pcg_persistent(PcgPersistArgs a)
                     z2s[h] = (z0 + z1) + (z2 + z3);
                 }
                 consumer_sync();
-                if (act) { zt += z2s[tid]; rzn = rv[tid] * zt; }
+                if (act) { zt += z2s[tid]; rzn = rv[tid] * zt; a.zbuf[t] = zt; }
             } else if (act) {
                 if (a.McL) {
                     mbar_wait(&mbarM, (uint32_t)(it & 1));
@@ -1931,6 +1976,7 @@ k_pcg_persistent(PcgPersistArgs a)
                     for (int c = 0; c < NA; c++) zt += a.Minv[(size_t)NA * NA * j + row + NA * c] * rv[lc * NA + c];
                 }
                 rzn = rv[tid] * zt;
+                a.zbuf[t] = zt;
             }
             PCG_PROF(12);
             if (tid < 128) {
@@ -1968,8 +2014,8 @@ k_pcg_persistent(PcgPersistArgs a)
         rzn = bcast[ND]; rr = bcast[ND + 1];
         // ---- 5. p = z + beta p, stop test
         const double beta = rzn / rz;
-        if (act) a.p[t] = zt + beta * pt;
-        rz = rzn;
+        if (act) { pt_next = fma(beta, pt, zt); (((it + 1) & 1) ? a.p2 : a.p)[t] = pt_next; }
+        rz = rzn; beta_prev = beta;
         const bool stop = rr <= a.rtol * a.rtol * r0n2 || it + 1 == a.max_iter;
         if (stop) {
             if (cta == 0 && tid == 0) {
@@ -1979,8 +2025,6 @@ k_pcg_persistent(PcgPersistArgs a)
             return;
         }
         PCG_PROF(8);
-        grid_barrier(a.barrier, bar_target, G);       // p complete before the next matvec reads it
-        PCG_PROF(9);
     }
 }
 

@@ -159,7 +159,7 @@ struct vlg_ba_ctx {
     int chol_grid = 0;
     double *red2 = nullptr, *Sjj = nullptr, *ebar = nullptr;   // red2 = per-camera sums [m][NU], all-reduced
     double *Minv = nullptr, *da = nullptr;
-    double *pr = nullptr, *pz = nullptr, *pp = nullptr, *pq = nullptr, *wq = nullptr, *tvec = nullptr, *qpart = nullptr;
+    double *pr = nullptr, *pz = nullptr, *pp = nullptr, *pp2 = nullptr, *pq = nullptr, *wq = nullptr, *tvec = nullptr, *qpart = nullptr;
     PcgScalars* pcg_sc = nullptr;
     // device: stage 3 (scal3 = new_cost | denom_pt_sum | denom_cam)
     double *db = nullptr, *denom_pt = nullptr, *cost_obs = nullptr, *scal3 = nullptr;
@@ -690,7 +690,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(dalloc(ctx, &ctx->red2, (size_t)NU * m));
     CHK(dalloc(ctx, &ctx->Sjj, (size_t)na * N)); CHK(dalloc(ctx, &ctx->ebar, N));
     CHK(dalloc(ctx, &ctx->Minv, (size_t)na * N)); CHK(dalloc(ctx, &ctx->da, N));
-    CHK(dalloc(ctx, &ctx->pr, N)); CHK(dalloc(ctx, &ctx->pz, N)); CHK(dalloc(ctx, &ctx->pp, N)); CHK(dalloc(ctx, &ctx->pq, N));
+    CHK(dalloc(ctx, &ctx->pr, N)); CHK(dalloc(ctx, &ctx->pz, N)); CHK(dalloc(ctx, &ctx->pp, N)); CHK(dalloc(ctx, &ctx->pp2, N)); CHK(dalloc(ctx, &ctx->pq, N));
     CHK(dalloc(ctx, &ctx->wq, N)); CHK(dalloc(ctx, &ctx->tvec, (size_t)4 * n)); CHK(dalloc(ctx, &ctx->qpart, (size_t)na * ctx->nchunks));
     CHK(dalloc(ctx, &ctx->pcg_sc, 1));
     CHK(dalloc(ctx, &ctx->db, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->denom_pt, (size_t)n));

@@ -322,7 +322,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             pa.Np = ctx->Np; pa.ld = ctx->Np; pa.N = N; pa.m = m; pa.max_iter = ctx->opt.pcg_max_iter; pa.nclusters = ctx->coop_grid;
             pa.rtol = rtol; pa.S = ctx->S; pa.tile_ptr = ctx->symv_tile_ptr; pa.tiles = ctx->symv_tiles;
             pa.rowpart = ctx->symv_rowpart; pa.colpart = ctx->symv_colpart; pa.wq = ctx->wq;
-            pa.Ud = ctx->Ud; pa.Minv = ctx->Minv; pa.McL = McL; pa.Mc2 = Mc2; pa.x = ctx->da; pa.r = ctx->pr; pa.p = ctx->pp;
+            pa.Ud = ctx->Ud; pa.Minv = ctx->Minv; pa.McL = McL; pa.Mc2 = Mc2; pa.x = ctx->da; pa.r = ctx->pr; pa.p = ctx->pp; pa.p2 = ctx->pp2; pa.zbuf = ctx->pz;
             pa.sc = ctx->pcg_sc; pa.blkpart = ctx->blkpart; pa.Z = defl ? ctx->Zd : nullptr; pa.SZ = defl ? ctx->SZd : nullptr;
             pa.ds = ctx->defl_sc; pa.barrier = ctx->persist_bar;
             pa.mb = ctx->nranks > 1 ? ctx->p2p_dev : nullptr; pa.epoch0 = ctx->p2p_epoch + 1;
