@@ -118,7 +118,14 @@ struct vlg_ba_ctx {
     int Np = 0;               // padded order of S
     int64_t nblocks = 0, npairs = 0;
     // host copies
-    std::vector<double> h_K, h_a, h_a_new, h_rtab, h_rtab_new, h_da;
+    std::vector<double> h_K, h_a, h_a_new, h_rtab, h_rtab_new, h_rtab_next, h_da;
+    // host-libm rotation tables: `rtab` is valid for the current a (skip the recomputation), `rtab_next` holds the 4-matrix
+    // table of the candidate a_new, computed on the host while the back-substitution runs and swapped in on accept
+    bool rtab_valid = false, rtab_next_valid = false;
+    double* rtab_next = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_da = nullptr, ev_bnew = nullptr;
+    double* d2h_bnew = nullptr;        // pinned host destination of b_new for this step (vlg_ba_trial_step_host), fetched while the cost is computed
     std::vector<int32_t> h_obs_pt, h_obs_cam;
     std::vector<double> h_obs_xy;
     std::vector<int32_t> h_blk_j, h_blk_k;
@@ -175,6 +182,8 @@ struct vlg_ba_ctx {
     double old_cost = 0.0;
     double s2_lambda = 0.0;
     int last_solver = 0, last_pcg_iters = 0;
+    bool cost_pending = false;         // stage 1's cost and visible count are still on their way to h_pin[4..5]
+    bool pcg_pending = false;          // the solve's scalars are still on their way to h_pcg (no host sync after the persistent kernel)
     double last_pcg_relres = 0.0;
     // multi-GPU
     nccl_comm comm = nullptr;
@@ -493,6 +502,8 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     ctx->h_da.assign(N, 0.0);
     ctx->h_rtab.assign((size_t)36 * m, 0.0);
     ctx->h_rtab_new.assign((size_t)9 * m, 0.0);
+    ctx->h_rtab_next.assign((size_t)36 * m, 0.0);
+    ctx->rtab_valid = ctx->rtab_next_valid = false;
     ctx->h_obs_pt.assign(obs_pt, obs_pt + nobs);
     ctx->h_obs_cam.assign(obs_cam, obs_cam + nobs);
     ctx->h_obs_xy.assign(obs_xy, obs_xy + 2 * nobs);
@@ -679,7 +690,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(dalloc(ctx, &ctx->cam_fixed, (size_t)m));
     CHK(dalloc(ctx, &ctx->K4, (size_t)4 * m)); CHK(dalloc(ctx, &ctx->a, N)); CHK(dalloc(ctx, &ctx->a_new, N));
     CHK(dalloc(ctx, &ctx->b, (size_t)3 * n)); CHK(dalloc(ctx, &ctx->b_new, (size_t)3 * n));
-    CHK(dalloc(ctx, &ctx->rtab, (size_t)36 * m)); CHK(dalloc(ctx, &ctx->rtab_new, (size_t)9 * m));
+    CHK(dalloc(ctx, &ctx->rtab, (size_t)36 * m)); CHK(dalloc(ctx, &ctx->rtab_new, (size_t)9 * m)); CHK(dalloc(ctx, &ctx->rtab_next, (size_t)36 * m));
     CHK(dalloc(ctx, &ctx->red1, (size_t)na * N + N + 2));
     ctx->U = ctx->red1; ctx->eA = ctx->red1 + (size_t)na * N; ctx->scal1 = ctx->eA + N;
     CHK(dalloc(ctx, &ctx->W, (size_t)3 * na * nobs)); CHK(dalloc(ctx, &ctx->Upart, (size_t)NU * ctx->nchunks));
@@ -889,7 +900,8 @@ int run_stage1(vlg_ba_ctx* ctx, double* diag_X, double* diag_A, double* diag_B, 
 {
     constexpr int NU = nu_of(NA);
     const bool diag = diag_X || diag_A || diag_B || diag_e;
-    CHK(run_rtab<NA>(ctx, ctx->h_a, ctx->a, 4, ctx->h_rtab, ctx->rtab));
+    if (!ctx->rtab_valid) CHK(run_rtab<NA>(ctx, ctx->h_a, ctx->a, 4, ctx->h_rtab, ctx->rtab));
+    ctx->rtab_valid = true;
     Stage1Args p;
     p.m = ctx->m; p.n = ctx->n; p.nchunks = ctx->nchunks;
     p.obs_xy = ctx->obs_xy; p.obs_pt = ctx->obs_pt;

@@ -48,7 +48,8 @@ int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S, int ccams = 0)
 template <int NA>
 int run_reproj_errors(vlg_ba_ctx* ctx, double depth_max, double* d_err, double* d_depth, double* d_bad)
 {
-    CHK(run_rtab<NA>(ctx, ctx->h_a, ctx->a, 4, ctx->h_rtab, ctx->rtab));
+    if (!ctx->rtab_valid) CHK(run_rtab<NA>(ctx, ctx->h_a, ctx->a, 4, ctx->h_rtab, ctx->rtab));
+    ctx->rtab_valid = true;
     if (ctx->nobs > 0) {
         k_reproj_errors<NA><<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->obs_xy, ctx->obs_pt, ctx->obs_cam, ctx->K4, ctx->a,
                                                                           ctx->b, ctx->rtab, depth_max, d_err, d_depth, d_bad);
@@ -315,6 +316,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         }
         ctx->launches++;
         int launched = 0;
+        bool deferred = false;
         const int batch = 8;
         if (persistent) {
             TimedScope ts(ctx, T_PCG_PERSIST);
@@ -347,7 +349,10 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             ctx->launches++;
             launched = ctx->opt.pcg_max_iter;
             CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+            // the host only has to wait here when it needs the iteration count now (mailbox epochs of the next exchange,
+            // autotuning, profile); otherwise the scalars are picked up at the step's final synchronisation
+            deferred = !(ctx->nranks > 1 || pa.stat || want_prof);
+            if (!deferred) CU(cudaStreamSynchronize(ctx->stream));
             if (ctx->nranks > 1) ctx->p2p_epoch += (unsigned int)ctx->h_pcg->iters;       // one mailbox epoch per matvec, on every rank
             if (pa.stat && ctx->h_pcg->iters > 0) CHK(symv_learn(ctx));
             if (want_prof) {
@@ -401,7 +406,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CU(cudaStreamSynchronize(ctx->stream));
             if (ctx->h_pcg->done) break;
         }
-        if (!ctx->h_pcg->done) {
+        if (!deferred && !ctx->h_pcg->done) {
             CU(cudaMemcpyAsync(ctx->h_pcg, ctx->pcg_sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
@@ -411,9 +416,23 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             CU(cudaGetLastError());
         }
         ctx->last_solver = ctx->use_explicit ? VLG_BA_SOLVER_PCG_EXPLICIT : VLG_BA_SOLVER_PCG;
-        ctx->last_pcg_iters = ctx->h_pcg->iters;
-        ctx->last_pcg_relres = ctx->h_pcg->r0n2 > 0.0 ? sqrt(ctx->h_pcg->rn2 / ctx->h_pcg->r0n2) : 0.0;
+        ctx->pcg_pending = deferred;
+        if (!deferred) {
+            ctx->last_pcg_iters = ctx->h_pcg->iters;
+            ctx->last_pcg_relres = ctx->h_pcg->r0n2 > 0.0 ? sqrt(ctx->h_pcg->rn2 / ctx->h_pcg->r0n2) : 0.0;
+        }
     }
+    return VLG_BA_OK;
+}
+
+// iteration count / residual of the last solve, once the host has synchronised with the stream
+static int resolve_pcg_info(vlg_ba_ctx* ctx)
+{
+    if (!ctx->pcg_pending) return VLG_BA_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->last_pcg_iters = ctx->h_pcg->iters;
+    ctx->last_pcg_relres = ctx->h_pcg->r0n2 > 0.0 ? sqrt(ctx->h_pcg->rn2 / ctx->h_pcg->r0n2) : 0.0;
+    ctx->pcg_pending = false;
     return VLG_BA_OK;
 }
 
@@ -422,18 +441,14 @@ template <int NA>
 int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
 {
     const int m = ctx->m, n = ctx->n, N = NA * m;
-    if (ctx->opt.rtable == VLG_BA_RTABLE_HOST_LIBM) {
-        // a_new = a + da on the host (same IEEE add as mex_bundle_3_db_new.c:137-140) so that the
-        // rotation matrices of the candidate come from the host libm
-        CHK(download(ctx, ctx->h_da.data(), ctx->da, (size_t)N));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (int t = 0; t < N; t++) ctx->h_a_new[t] = ctx->h_a[t] + ctx->h_da[t];
-        CHK(upload(ctx, ctx->a_new, ctx->h_a_new.data(), (size_t)N));
-    } else {
+    const bool host_tab = ctx->opt.rtable == VLG_BA_RTABLE_HOST_LIBM;
+    ctx->rtab_next_valid = false;
+    if (host_tab) CU(cudaEventRecord(ctx->ev_da, ctx->stream));       // da is final here
+    else {
         k_axpy1<<<cdiv(N, 256), 256, 0, ctx->stream>>>(N, ctx->a, ctx->da, ctx->a_new);
         ctx->launches++;
+        CHK(run_rtab<NA>(ctx, ctx->h_a_new, ctx->a_new, 1, ctx->h_rtab_new, ctx->rtab_new));
     }
-    CHK(run_rtab<NA>(ctx, ctx->h_a_new, ctx->a_new, 1, ctx->h_rtab_new, ctx->rtab_new));
     {
         TimedScope ts(ctx, T_STAGE3);
         if (n > 0) {
@@ -446,6 +461,31 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
                                                                     ctx->da, ctx->b, lambda, ctx->opt.backsub_all_rows, ctx->db,
                                                                     ctx->b_new, ctx->denom_pt);
             ctx->launches++;
+            if (ctx->d2h_bnew) {
+                // the caller's (pinned) buffer gets b_new over the copy stream while the new cost is still being computed
+                CU(cudaEventRecord(ctx->ev_bnew, ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_bnew, 0));
+                CU(cudaMemcpyAsync(ctx->d2h_bnew, ctx->b_new, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
+        }
+        if (host_tab) {
+            // a_new = a + da on the host (same IEEE add as mex_bundle_3_db_new.c:137-140) so that the rotation matrices of the
+            // candidate come from the host libm.  da is fetched on a second stream and the table is computed WHILE the
+            // back-substitution runs (it only needs da): all four matrices per camera, so that the next stage 1 finds its
+            // table ready when the step is accepted
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_da, 0));
+            CU(cudaMemcpyAsync(ctx->h_da.data(), ctx->da, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CU(cudaStreamSynchronize(ctx->copy_stream));
+            for (int t = 0; t < N; t++) ctx->h_a_new[t] = ctx->h_a[t] + ctx->h_da[t];
+            CHK(upload(ctx, ctx->a_new, ctx->h_a_new.data(), (size_t)N));
+            if (NA != kNaProjective) {
+                rtab_host(m, NA, ctx->h_a_new.data(), 4, ctx->h_rtab_next.data());
+                for (int j = 0; j < m; j++)
+                    for (int q = 0; q < 9; q++) ctx->h_rtab_new[(size_t)9 * j + q] = ctx->h_rtab_next[(size_t)36 * j + q];
+                CHK(upload(ctx, ctx->rtab_new, ctx->h_rtab_new.data(), (size_t)9 * m));
+                CHK(upload(ctx, ctx->rtab_next, ctx->h_rtab_next.data(), (size_t)36 * m));
+                ctx->rtab_next_valid = true;
+            }
         }
         if (ctx->nobs > 0) {
             k_new_cost<NA><<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->obs_xy, ctx->obs_pt, ctx->obs_cam, ctx->K4,
@@ -472,10 +512,21 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
     return VLG_BA_OK;
 }
 
+static int resolve_cost(vlg_ba_ctx* ctx)
+{
+    if (!ctx->cost_pending) return VLG_BA_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->old_cost = ctx->h_pin[4];
+    ctx->num_vis = ctx->h_pin[5];
+    ctx->cost_pending = false;
+    return VLG_BA_OK;
+}
+
 #define DISPATCH_NA(ctx, call)                                                   \
     ((ctx)->na == 6 ? call<6> : (ctx)->na == 7 ? call<7> : (ctx)->na == 10 ? call<10> : call<12>)
 
-int do_stage1(vlg_ba_ctx* ctx)
+// `defer`: do not wait for the cost on the host (the LM step only needs it for the accept test after stage 3)
+int do_stage1(vlg_ba_ctx* ctx, bool defer = false)
 {
     if (!ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
     CU(cudaSetDevice(ctx->device));
@@ -487,9 +538,8 @@ int do_stage1(vlg_ba_ctx* ctx)
     CHK(allreduce(ctx, ctx->red1, (size_t)ctx->na * ctx->na * ctx->m + (size_t)ctx->na * ctx->m + 2));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaMemcpyAsync(ctx->h_pin + 4, ctx->scal1, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->old_cost = ctx->h_pin[4];
-    ctx->num_vis = ctx->h_pin[5];
+    ctx->cost_pending = true;
+    if (!defer) CHK(resolve_cost(ctx));
     ctx->s1_valid = true; ctx->s2_valid = false; ctx->s3_valid = false;
     return VLG_BA_OK;
 }
@@ -521,18 +571,20 @@ int do_trial(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
 {
     const double lambda = ctx->lambda;
     bool fresh1 = false;
-    if (!ctx->s1_valid) { CHK(do_stage1(ctx)); fresh1 = true; }   // a rejected step left (a,b) unchanged: mex1 would give the same bits
+    if (!ctx->s1_valid) { CHK(do_stage1(ctx, true)); fresh1 = true; }   // a rejected step left (a,b) unchanged: mex1 would give the same bits
     else CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    const double old_cost = ctx->old_cost;
     CHK(do_stage2(ctx, lambda));
     double new_cost = 0.0, denom = 0.0;
     CHK(do_stage3(ctx, lambda, &new_cost, &denom));
+    CHK(resolve_cost(ctx));
+    const double old_cost = ctx->old_cost;
     const double rho = (old_cost - new_cost) / denom;                       // :217
     const bool accept = (old_cost - new_cost) > 0;                          // :218
     if (info) {
         memset(info, 0, sizeof(*info));
         info->old_cost = old_cost; info->new_cost = new_cost; info->denom = denom; info->rho = rho;
         info->lambda_used = lambda; info->accepted = accept ? 1 : 0;
+        CHK(resolve_pcg_info(ctx));
         info->solver_used = ctx->last_solver; info->pcg_iters = ctx->last_pcg_iters; info->pcg_relres = ctx->last_pcg_relres;
         float ms = 0.f;
         if (fresh1 && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) info->ms_stage1 = ms;
@@ -545,6 +597,10 @@ int do_trial(vlg_ba_ctx* ctx, vlg_ba_trial_info* info)
         std::swap(ctx->a, ctx->a_new);
         std::swap(ctx->b, ctx->b_new);
         ctx->h_a.swap(ctx->h_a_new);
+        std::swap(ctx->rtab, ctx->rtab_next);                               // the candidate's table, if stage 3 left one
+        ctx->h_rtab.swap(ctx->h_rtab_next);
+        ctx->rtab_valid = ctx->rtab_next_valid;
+        ctx->rtab_next_valid = false;
         if (ctx->opt.model == VLG_BA_MODEL_PROJECTIVE) {
             ctx->lambda = lambda / 10;                                      // bundle_projective.m:194
         } else {
@@ -622,6 +678,9 @@ int vlg_ba_create(const vlg_ba_opts* opts, vlg_ba_ctx** out)
     }
     for (int k = 0; k < 5; k++) cudaEventCreate(&c->ev[k]);
     for (int k = 0; k < 2; k++) cudaEventCreate(&c->ev_sw[k]);
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_da, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_bnew, cudaEventDisableTiming);
     memset(c->h_pcg, 0, sizeof(PcgScalars));
     (void)ctx;
     *out = c;
@@ -645,6 +704,9 @@ void vlg_ba_destroy(vlg_ba_ctx* ctx)
     for (int k = 0; k < 2; k++) if (ctx->ev_sw[k]) cudaEventDestroy(ctx->ev_sw[k]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_pcg) cudaFreeHost(ctx->h_pcg);
+    if (ctx->ev_da) cudaEventDestroy(ctx->ev_da);
+    if (ctx->ev_bnew) cudaEventDestroy(ctx->ev_bnew);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -819,7 +881,7 @@ int vlg_ba_set_state(vlg_ba_ctx* ctx, const double* a, const double* b, double l
     if (!ctx || !ctx->have_problem) return fail(ctx, VLG_BA_ESTATE, "no problem set");
     CU(cudaSetDevice(ctx->device));
     const size_t N = (size_t)ctx->na * ctx->m;
-    if (a) { ctx->h_a.assign(a, a + N); CHK(upload(ctx, ctx->a, a, N)); }
+    if (a) { ctx->h_a.assign(a, a + N); CHK(upload(ctx, ctx->a, a, N)); ctx->rtab_valid = false; }
     if (b) CHK(upload(ctx, ctx->b, b, (size_t)3 * ctx->n));
     CU(cudaStreamSynchronize(ctx->stream));
     if (lambda > 0) ctx->lambda = lambda;
@@ -1067,21 +1129,45 @@ int vlg_ba_trial_step_host(vlg_ba_ctx* ctx, const double* a, const double* b, co
         k_gather_xy<<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->pt_obs, ctx->obs_xy, ctx->pt_xy);
         ctx->launches++;
     }
-    CHK(vlg_ba_set_state(ctx, a, b, lambda, -1.0));
-    ctx->s1_valid = false;
-    // the candidate always lands in (a_new, b_new) on the device; fetch before do_trial swaps on accept
+    // new state without a host synchronisation: the caller's buffers stay untouched until this call returns, and the
+    // rotation table is computed from the host copy of a while the observations are still on their way to the device
+    {
+        const size_t N = (size_t)ctx->na * ctx->m;
+        if (a) { ctx->h_a.assign(a, a + N); CHK(upload(ctx, ctx->a, a, N)); ctx->rtab_valid = false; }
+        if (b) CHK(upload(ctx, ctx->b, b, (size_t)3 * ctx->n));
+        if (lambda > 0) ctx->lambda = lambda;
+        ctx->s1_valid = ctx->s2_valid = ctx->s3_valid = false;
+        if (!ctx->rtab_valid && ctx->opt.rtable == VLG_BA_RTABLE_HOST_LIBM) {
+            CHK(DISPATCH_NA(ctx, run_rtab)(ctx, ctx->h_a, ctx->a, 4, ctx->h_rtab, ctx->rtab));
+            ctx->rtab_valid = true;
+        }
+    }
+    // the candidate always lands in (a_new, b_new) on the device; b_new (the big one) leaves over the copy stream as soon as
+    // the back-substitution has produced it, when the destination is pinned memory
     const double lam = ctx->lambda;
-    CHK(do_stage1(ctx));
+    {
+        cudaPointerAttributes at;
+        const bool pinned = b_new && cudaPointerGetAttributes(&at, b_new) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        ctx->d2h_bnew = pinned ? b_new : nullptr;
+    }
+    CHK(do_stage1(ctx, true));
     CHK(do_stage2(ctx, lam));
     double nc = 0, dn = 0;
-    CHK(do_stage3(ctx, lam, &nc, &dn));
+    const bool overlapped = ctx->d2h_bnew != nullptr;
+    const int r3 = do_stage3(ctx, lam, &nc, &dn);
+    ctx->d2h_bnew = nullptr;
+    CHK(r3);
+    CHK(resolve_cost(ctx));
     CHK(download(ctx, a_new, ctx->a_new, (size_t)ctx->na * ctx->m));
-    CHK(download(ctx, b_new, ctx->b_new, (size_t)3 * ctx->n));
+    if (!overlapped) CHK(download(ctx, b_new, ctx->b_new, (size_t)3 * ctx->n));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (overlapped) CU(cudaStreamSynchronize(ctx->copy_stream));
     if (info) {
         memset(info, 0, sizeof(*info));
         info->old_cost = ctx->old_cost; info->new_cost = nc; info->denom = dn; info->rho = (ctx->old_cost - nc) / dn;
         info->lambda_used = lam; info->accepted = (ctx->old_cost - nc) > 0;
+        CHK(resolve_pcg_info(ctx));
         info->solver_used = ctx->last_solver; info->pcg_iters = ctx->last_pcg_iters; info->pcg_relres = ctx->last_pcg_relres;
     }
     return VLG_BA_OK;
