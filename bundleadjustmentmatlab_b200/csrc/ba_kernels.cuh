@@ -606,16 +606,19 @@ __device__ __forceinline__ SchurDest schur_dest(double* __restrict__ S, int ld, 
     return d;
 }
 
-// v[row + NA col] -> S block (j,k) and its mirror (k,j); 16-byte stores when NA is even
+// v[row + NA col] -> S block (j,k), j <= k (the upper one; skipped when `upper` is false), and its mirror (k,j);
+// 16-byte stores when NA is even
 template <int NA>
-__device__ __forceinline__ void schur_store_block(const SchurDest& t, bool offdiag, const double* __restrict__ v)
+__device__ __forceinline__ void schur_store_block(const SchurDest& t, bool offdiag, const double* __restrict__ v, bool upper = true)
 {
     if constexpr (NA % 2 == 0) {
+        if (upper || !offdiag) {
 #pragma unroll
-        for (int col = 0; col < NA; col++) {
-            double2* d = reinterpret_cast<double2*>(t.base + (size_t)t.jr + t.ld * (t.kr + col));
+            for (int col = 0; col < NA; col++) {
+                double2* d = reinterpret_cast<double2*>(t.base + (size_t)t.jr + t.ld * (t.kr + col));
 #pragma unroll
-            for (int h = 0; h < NA / 2; h++) d[h] = make_double2(v[2 * h + NA * col], v[2 * h + 1 + NA * col]);
+                for (int h = 0; h < NA / 2; h++) d[h] = make_double2(v[2 * h + NA * col], v[2 * h + 1 + NA * col]);
+            }
         }
         if (offdiag) {
 #pragma unroll
@@ -630,7 +633,7 @@ __device__ __forceinline__ void schur_store_block(const SchurDest& t, bool offdi
         for (int col = 0; col < NA; col++)
 #pragma unroll
             for (int row = 0; row < NA; row++) {
-                t.base[(size_t)(t.jr + row) + t.ld * (t.kr + col)] = v[row + NA * col];
+                if (upper || !offdiag) t.base[(size_t)(t.jr + row) + t.ld * (t.kr + col)] = v[row + NA * col];
                 if (offdiag) t.base[(size_t)(t.kr + col) + t.ld * (t.jr + row)] = v[row + NA * col];
             }
     }
@@ -657,7 +660,7 @@ __global__ void k_schur_diag_fill(int m, int ld, int ccams, int add_U, const dou
 // summation, mex_bundle_2_Se_.c:103-118)
 template <int NA>
 __global__ void __launch_bounds__(128)
-k_schur_blocks_light(int nlist, const int* __restrict__ list, int ld, int ccams, int add_U, const int* __restrict__ blk_j,
+k_schur_blocks_light(int nlist, const int* __restrict__ list, int ld, int ccams, int add_U, int upper_band, const int* __restrict__ blk_j,
                      const int* __restrict__ blk_k, const int64_t* __restrict__ blk_ptr, const int2* __restrict__ pairs,
                      const double* __restrict__ Y, const double* __restrict__ W, const double* __restrict__ Ud,
                      double* __restrict__ S)
@@ -676,7 +679,9 @@ k_schur_blocks_light(int nlist, const int* __restrict__ list, int ld, int ccams,
         if (j == k && add_U) v += Ud[(size_t)NA * NA * j + u];
         acc[u] = v;
     }
-    schur_store_block<NA>(schur_dest<NA>(S, ld, ccams, j, k), j != k, acc);
+    // far from the diagonal only the lower block is stored when the consumer reads the lower triangle (assembled-S PCG:
+    // the symmetric matvec, the peer pull; the cluster gathers stay within upper_band cameras of the diagonal)
+    schur_store_block<NA>(schur_dest<NA>(S, ld, ccams, j, k), j != k, acc, k - j <= upper_band);
 }
 
 // heavy blocks: one warp per block, lanes stride over the pairs, values folded by recursive halving

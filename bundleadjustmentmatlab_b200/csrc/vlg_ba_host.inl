@@ -37,7 +37,9 @@ int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S, int ccams = 0)
     }
     if (ctx->nlight > 0) {
         k_schur_blocks_light<NA><<<cdiv(ctx->nlight, 128), 128, 0, ctx->stream>>>(
-            ctx->nlight, ctx->blk_light, ctx->Np, ccams, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
+            ctx->nlight, ctx->blk_light, ctx->Np, ccams, add_U,
+            (ctx->use_explicit && ccams == 0) ? 2 * (128 / NA) + 8 : 1 << 30,      // PCG on S: upper blocks only near the diagonal
+            ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
         ctx->launches++;
     }
     CU(cudaGetLastError());
