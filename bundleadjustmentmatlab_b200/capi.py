@@ -61,7 +61,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan",
 ]
 
 
@@ -321,3 +321,29 @@ class Context:
         ms, cnt = C.c_double(), C.c_int64()
         self._ck(self._L.vlg_ba_kernel_time(self._h, name.encode(), C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
+
+
+def symv_plan(Np: int, G: int, J0: int = 0, J1: int | None = None, speed=None) -> dict:
+    """Host-side plan of the assembled-S matvec (vlg_ba_symv_plan): tiles, per-CTA pieces and fold lists.  No GPU needed."""
+    L = lib()
+    if J1 is None:
+        J1 = Np // 32
+    sizes = (C.c_int64 * 8)()
+    sp = None if speed is None else np.ascontiguousarray(speed, dtype=np.float64)
+    spp = None if sp is None else sp.ctypes.data_as(C.POINTER(C.c_double))
+
+    def call(*arrs):
+        r = L.vlg_ba_symv_plan(C.c_int(Np), C.c_int(G), C.c_int(J0), C.c_int(J1), spp, *arrs, sizes)
+        if r != 0:
+            raise VlgBaError(f"vlg_ba_symv_plan: {L.vlg_ba_last_error(None).decode()}")
+
+    call(None, None, None, None, None, None)
+    nt, nfrag, nrl, ncl, nrb = (int(sizes[k]) for k in range(5))
+    out = dict(tiles=np.zeros((nt, 4), np.int32), tile_ptr=np.zeros(G + 1, np.int32), row_ptr=np.zeros(nrb + 1, np.int32),
+               row_list=np.zeros(max(nrl, 1), np.int32), col_ptr=np.zeros(Np // 32 + 1, np.int32), col_list=np.zeros(max(ncl, 1), np.int32))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    call(ip(out["tiles"]), ip(out["tile_ptr"]), ip(out["row_ptr"]), ip(out["row_list"]), ip(out["col_ptr"]), ip(out["col_list"]))
+    out.update(nfrag=nfrag, blk_rows=int(sizes[5]), slab=int(sizes[6]), ncell=int(sizes[7]))
+    out["row_list"] = out["row_list"][:nrl]; out["col_list"] = out["col_list"][:ncl]
+    return out
+

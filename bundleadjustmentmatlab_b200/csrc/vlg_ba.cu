@@ -377,29 +377,60 @@ int reduce_to(vlg_ba_ctx* ctx, const double* in, size_t n, double* out)
 }
 
 // ---- problem set-up ----------------------------------------------------------------------------
-// Cuts the tile sequence of the explicit-S matvec into one contiguous piece per persistent CTA -- cost proportional to
-// the CTA's speed weight (1 at first; re-measured over the first solves: the SMs of a B200 do not all stream at the
-// same rate, +-4 % by position) -- and rebuilds what depends on the cut: tile flags, fragments, fold lists.  The
-// partial results are indexed by fragment and folded in list order, so the product does not depend on the cut's bits
-// only through the order of summation inside a row (covered by the PCG tolerance, identical on every rank).
-int symv_partition(vlg_ba_ctx* ctx)
+// Host-side plan of the explicit-S matvec (pure functions: also reachable without a GPU through vlg_ba_symv_plan, which the
+// CPU tests use to replay the decomposition).  symv_sequence: the tiles of the strips [J0, J1) of the lower triangle in
+// cell order with their cost prefix.  symv_cut: one contiguous piece per CTA, cost proportional to the CTA's speed weight,
+// and what depends on the cut -- tile flags, fragments, fold lists (ba_pcg.cuh, SymvSmem).
+struct SymvPlan {
+    std::vector<int4> tiles;
+    std::vector<int> tptr, rptr, rlist, cptr, clist;
+    int nfrag = 0;
+};
+
+void symv_sequence(int Np, int J0, int J1, std::vector<vlg_ba_ctx::SymvTileH>& seq, std::vector<double>& cum, int& ncell)
 {
-    const std::vector<vlg_ba_ctx::SymvTileH>& seq = ctx->h_symv_seq;
-    const std::vector<double>& cum = ctx->h_symv_cum;
-    const int G = ctx->symv_grid, Np = ctx->Np, nstrips = Np / kSymvCols;
-    std::vector<int>& tptr = ctx->h_symv_tptr;
+    seq.clear();
+    ncell = 0;
+    for (int Js = J0; Js < J1; Js += kSymvSlab) {
+        const int Je = std::min(J1, Js + kSymvSlab);
+        for (int b0 = (kSymvCols * Js) / kSymvBlkRows * kSymvBlkRows; b0 < Np; b0 += kSymvBlkRows, ncell++)
+            for (int J = Js; J < Je; J++) {
+                int lo = std::max(kSymvCols * J, b0);
+                const int hi = std::min(Np, b0 + kSymvBlkRows);
+                while (lo < hi) {
+                    const int nx = std::min(hi, (lo / kSymvRows + 1) * kSymvRows);
+                    seq.push_back({J, lo, nx - lo, ncell, J - Js});
+                    lo = nx;
+                }
+            }
+    }
+    // cost of a tile in row units (a 256-row tile streams in ~1.4 us): its rows, but never less than the ring's latency
+    // floor, plus a fixed part (barrier waits, descriptor, x prefetch); the first tile of a run in a strip also pays the
+    // strip's x (an exposed L2 round trip) and the column reduction at the run's end
+    cum.assign(seq.size() + 1, 0.0);
+    for (size_t t = 0; t < seq.size(); t++) {
+        const bool newrun = t == 0 || seq[t - 1].strip != seq[t].strip || seq[t - 1].cell != seq[t].cell;
+        cum[t + 1] = cum[t] + std::max(seq[t].rows, 64) + 40 + (newrun ? 150 : 0);
+    }
+}
+
+void symv_cut(int Np, int G, const std::vector<vlg_ba_ctx::SymvTileH>& seq, const std::vector<double>& cum,
+              const std::vector<double>& speed, SymvPlan& pl)
+{
+    const int nstrips = Np / kSymvCols;
+    std::vector<int>& tptr = pl.tptr;
     tptr.assign((size_t)G + 1, 0);
     double wsum = 0.0, wacc = 0.0;
-    for (int g = 0; g < G; g++) wsum += ctx->symv_speed[(size_t)g];
+    for (int g = 0; g < G; g++) wsum += speed[(size_t)g];
     for (int g = 1; g < G; g++) {
-        wacc += ctx->symv_speed[(size_t)g - 1];
+        wacc += speed[(size_t)g - 1];
         const double target = cum.back() * wacc / wsum;
         tptr[g] = std::max(tptr[g - 1], (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin()));
         tptr[g] = std::min(tptr[g], (int)seq.size());
     }
     tptr[G] = (int)seq.size();
     // fragments: maximal runs of one cell inside one CTA's piece; flags and fold lists
-    std::vector<int4> tiles(seq.size());
+    pl.tiles.resize(seq.size());
     const int nrowblk = (Np + kSymvBlkRows - 1) / kSymvBlkRows;
     std::vector<std::vector<int>> rowl((size_t)nrowblk), coll((size_t)nstrips);
     int nfrag = 0;
@@ -413,11 +444,26 @@ int symv_partition(vlg_ba_ctx* ctx)
             if (ffrag) { nfrag++; rowl[(size_t)(c.r0 / kSymvBlkRows)].push_back(nfrag - 1); }
             if (fstrip) coll[(size_t)c.strip].push_back((nfrag - 1) * kSymvCols * kSymvSlab + kSymvCols * c.sl);
             const int flags = (fstrip ? kSymvFirstStrip : 0) | (lstrip ? kSymvLastStrip : 0) | (ffrag ? kSymvFirstFrag : 0) | (lfrag ? kSymvLastFrag : 0);
-            tiles[(size_t)t] = make_int4(c.strip, c.r0, c.rows | flags, (nfrag - 1) | (c.sl << 20));
+            pl.tiles[(size_t)t] = make_int4(c.strip, c.r0, c.rows | flags, (nfrag - 1) | (c.sl << 20));
         }
-    std::vector<int> rptr(1, 0), rlist, cptr(1, 0), clist;
-    for (auto& v : rowl) { rlist.insert(rlist.end(), v.begin(), v.end()); rptr.push_back((int)rlist.size()); }
-    for (auto& v : coll) { clist.insert(clist.end(), v.begin(), v.end()); cptr.push_back((int)clist.size()); }
+    pl.rptr.assign(1, 0); pl.rlist.clear(); pl.cptr.assign(1, 0); pl.clist.clear();
+    for (auto& v : rowl) { pl.rlist.insert(pl.rlist.end(), v.begin(), v.end()); pl.rptr.push_back((int)pl.rlist.size()); }
+    for (auto& v : coll) { pl.clist.insert(pl.clist.end(), v.begin(), v.end()); pl.cptr.push_back((int)pl.clist.size()); }
+    pl.nfrag = nfrag;
+}
+
+// The context's cut: weights 1 at first; with opts.pcg_autotune re-measured over the first solves (the SMs of a B200 do not
+// all stream at the same rate, +-4 % by position).  The partial results are indexed by fragment and folded in list order, so
+// the product depends on the cut only through the order of summation inside a row (covered by the PCG tolerance,
+// identical on every rank).
+int symv_partition(vlg_ba_ctx* ctx)
+{
+    SymvPlan pl;
+    symv_cut(ctx->Np, ctx->symv_grid, ctx->h_symv_seq, ctx->h_symv_cum, ctx->symv_speed, pl);
+    ctx->h_symv_tptr = pl.tptr;
+    const std::vector<int4>& tiles = pl.tiles;
+    const std::vector<int>&tptr = pl.tptr, &rptr = pl.rptr, &rlist = pl.rlist, &cptr = pl.cptr, &clist = pl.clist;
+    const int nfrag = pl.nfrag;
     ctx->symv_nfrag = nfrag;
     CHK(upload(ctx, ctx->symv_tiles, tiles.data(), tiles.size()));
     CHK(upload(ctx, ctx->symv_tile_ptr, tptr.data(), tptr.size()));
@@ -759,30 +805,9 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         ctx->s_J0 = ctx->s_split ? ctx->s_bounds[(size_t)ctx->rank] : 0;
         ctx->s_J1 = ctx->s_split ? ctx->s_bounds[(size_t)ctx->rank + 1] : nstrips;
         std::vector<vlg_ba_ctx::SymvTileH>& seq = ctx->h_symv_seq;
-        seq.clear();
         int ncell = 0;
-        for (int Js = ctx->s_J0; Js < ctx->s_J1; Js += kSymvSlab) {
-            const int Je = std::min(ctx->s_J1, Js + kSymvSlab);
-            for (int b0 = (kSymvCols * Js) / kSymvBlkRows * kSymvBlkRows; b0 < Np; b0 += kSymvBlkRows, ncell++)
-                for (int J = Js; J < Je; J++) {
-                    int lo = std::max(kSymvCols * J, b0);
-                    const int hi = std::min(Np, b0 + kSymvBlkRows);
-                    while (lo < hi) {
-                        const int nx = std::min(hi, (lo / kSymvRows + 1) * kSymvRows);
-                        seq.push_back({J, lo, nx - lo, ncell, J - Js});
-                        lo = nx;
-                    }
-                }
-        }
+        symv_sequence(Np, ctx->s_J0, ctx->s_J1, seq, ctx->h_symv_cum, ncell);
         const int G = std::max(1, std::min(ctx->nsm, (int)seq.size()));
-        // cost of a tile in row units (a 256-row tile streams in ~1.4 us): its rows, but never less than the ring's latency
-        // floor, plus a fixed part (barrier waits, descriptor, x prefetch); the first tile of a run in a strip also pays the
-        // strip's x (an exposed L2 round trip) and the column reduction at the run's end
-        ctx->h_symv_cum.assign(seq.size() + 1, 0.0);
-        for (size_t t = 0; t < seq.size(); t++) {
-            const bool newrun = t == 0 || seq[t - 1].strip != seq[t].strip || seq[t - 1].cell != seq[t].cell;
-            ctx->h_symv_cum[t + 1] = ctx->h_symv_cum[t] + std::max(seq[t].rows, 64) + 40 + (newrun ? 150 : 0);
-        }
         ctx->symv_grid = G;
         ctx->symv_ncell = ncell;
         ctx->symv_speed.assign((size_t)G, 1.0);

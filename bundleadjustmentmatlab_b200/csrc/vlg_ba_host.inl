@@ -986,6 +986,29 @@ int vlg_ba_get_reduced(vlg_ba_ctx* ctx, double* Vinv, double* S, double* e_, dou
     return VLG_BA_OK;
 }
 
+int vlg_ba_symv_plan(int Np, int G, int J0, int J1, const double* speed, int32_t* tiles4, int32_t* tile_ptr, int32_t* row_ptr,
+                     int32_t* row_list, int32_t* col_ptr, int32_t* col_list, int64_t* sizes)
+{
+    if (Np <= 0 || Np % kSymvCols != 0 || G <= 0 || J0 < 0 || J1 > Np / kSymvCols || J0 > J1 || !sizes)
+        return fail(nullptr, VLG_BA_EINVAL, "symv_plan: Np must be a positive multiple of 32, 0 <= J0 <= J1 <= Np/32, G > 0");
+    std::vector<vlg_ba_ctx::SymvTileH> seq;
+    std::vector<double> cum, sp((size_t)G, 1.0);
+    int ncell = 0;
+    symv_sequence(Np, J0, J1, seq, cum, ncell);
+    if (speed) sp.assign(speed, speed + G);
+    SymvPlan pl;
+    symv_cut(Np, G, seq, cum, sp, pl);
+    sizes[0] = (int64_t)pl.tiles.size(); sizes[1] = pl.nfrag; sizes[2] = (int64_t)pl.rlist.size(); sizes[3] = (int64_t)pl.clist.size();
+    sizes[4] = (int64_t)pl.rptr.size() - 1; sizes[5] = kSymvBlkRows; sizes[6] = kSymvSlab; sizes[7] = ncell;
+    if (tiles4) for (size_t t = 0; t < pl.tiles.size(); t++) { tiles4[4 * t] = pl.tiles[t].x; tiles4[4 * t + 1] = pl.tiles[t].y; tiles4[4 * t + 2] = pl.tiles[t].z; tiles4[4 * t + 3] = pl.tiles[t].w; }
+    if (tile_ptr) std::copy(pl.tptr.begin(), pl.tptr.end(), tile_ptr);
+    if (row_ptr) std::copy(pl.rptr.begin(), pl.rptr.end(), row_ptr);
+    if (row_list) std::copy(pl.rlist.begin(), pl.rlist.end(), row_list);
+    if (col_ptr) std::copy(pl.cptr.begin(), pl.cptr.end(), col_ptr);
+    if (col_list) std::copy(pl.clist.begin(), pl.clist.end(), col_list);
+    return VLG_BA_OK;
+}
+
 int vlg_ba_reproj_errors(vlg_ba_ctx* ctx, double depth_max, double* err, double* depth, double* mean_err, double* max_sq_err,
                          int64_t* argmax, int64_t* n_bad_depth)
 {

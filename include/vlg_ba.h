@@ -260,6 +260,15 @@ int  vlg_ba_reset_timers(vlg_ba_ctx *ctx, int enable);
 int  vlg_ba_timer_start(vlg_ba_ctx *ctx);
 int  vlg_ba_timer_stop(vlg_ba_ctx *ctx, float *elapsed_ms);
 
+/* Diagnostic, no GPU needed: the host-side plan of the assembled-S symmetric matvec (csrc/ba_pcg.cuh, "Work decomposition")
+ * for an Np x Np system (Np a multiple of 32) on G persistent CTAs over the strips [J0, J1) of 32 columns, with optional
+ * per-CTA speed weights (NULL = equal).  sizes[8] <- {tiles, fragments, row-list entries, column-list entries, row blocks,
+ * rows per cell, strips per cell, cells}; the arrays may be NULL (call once for the sizes).  tiles4: 4 ints per tile
+ * {strip, first row, rows | flags << 16, fragment | strip-in-cell << 20}, flags: 1 first / 2 last tile of a run in a strip,
+ * 4 first / 8 last tile of a fragment.  CPU tests replay the plan against a dense product. */
+int  vlg_ba_symv_plan(int Np, int G, int J0, int J1, const double *speed, int32_t *tiles4, int32_t *tile_ptr,
+                      int32_t *row_ptr, int32_t *row_list, int32_t *col_ptr, int32_t *col_list, int64_t *sizes);
+
 #ifdef __cplusplus
 }
 #endif

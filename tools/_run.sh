@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r01J.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch.log 2>&1; echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on --kernel-name regex:'k_pcg_persistent|k_symv_lower|k_cluster_inverse' --launch-skip 20 --launch-count 4 -o gpurun_out/prof_r01J python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "full rc=$?"
-ls -la gpurun_out/prof_r01J.ncu-rep
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/bench_4gpu_J.json 2> gpurun_out/bench_4gpu_J.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_4gpu_J.json").read().strip().splitlines()[-1])
+print(d["ms_per_step"], d["value"], d["e2e"]["value"], d["pcg_iters"], d.get("accepted_steps"), {k:v["avg_ms"] for k,v in d["kernels"].items()})
+PY
