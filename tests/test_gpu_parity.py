@@ -421,6 +421,30 @@ def test_many_clusters_implicit_path():
     assert rel(out[0]["new_cost"], out[1]["new_cost"]) <= COST_RTOL
 
 
+def test_autotuned_matvec_cut_same_steps():
+    """opts.pcg_autotune re-cuts the assembled-S matvec by the measured per-SM rate after each of the first solves: the
+    steps must not change beyond the PCG tolerance (teacher-forced from the equal-cut trajectory), and the overlapping
+    preconditioner switched off (VLG_BA_OVERLAP=0 semantics are covered by the solver-variant tests) is not needed here."""
+    P = synth.make_problem(700, 60000, 330000, seed=31)
+    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T); b = np.ascontiguousarray(P.Xe[:3].T)
+    ref = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG_EXPLICIT, pcg_rtol=1e-11)
+    ref.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
+    tun = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG_EXPLICIT, pcg_rtol=1e-11, pcg_autotune=3)
+    tun.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
+    worst = 0.0
+    for _ in range(5):
+        st = ref.get_state()
+        i0 = ref.trial_step()
+        tun.set_state(a=st["a"], b=st["b"], lam=st["lam"], nu=st["nu"])
+        i1 = tun.trial_step()
+        assert i1["solver_used"] == capi.SOLVER_PCG_EXPLICIT
+        assert i0["old_cost"] == i1["old_cost"]
+        worst = max(worst, rel(i0["new_cost"], i1["new_cost"]))
+    print(f"autotuned cut: worst relative cost deviation over 5 steps {worst:.2e}")
+    assert worst <= COST_RTOL
+    ref.close(); tun.close()
+
+
 def test_long_tracks_fall_back_to_untiled_kernels():
     """Points seen by more than 512 cameras do not fit a point tile: the stage-1 point pass, the back-substitution
     and the implicit PCG point sweep fall back to their thread-per-point forms.  All three solvers must still agree
