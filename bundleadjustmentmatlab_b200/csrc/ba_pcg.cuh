@@ -1206,12 +1206,12 @@ k_sweep_pt_ring(int ntiles, const int4* __restrict__ ptile_meta /* (q0, nob, p0,
 // LOWER TRIANGLE ONLY: every element a = S[r][c] read once feeds both y_r += a x_c and
 // y_c += a x_r.
 //   * a tile is 256 rows x 32 columns of S (column-major => 32 contiguous 2-KB runs), pulled
-//     into shared memory by 32 TMA bulk copies on one mbarrier; a persistent CTA per SM walks a
-//     host-built tile list (LPT-balanced) with a 3-stage ring, i.e. up to 192 KB in flight per SM;
-//   * thread t owns row t of the tile: row sums leave as per-strip partials, the 32 column
-//     sums stay in registers over a work item (strip segment) and leave as per-segment partials;
-//   * k_symv_finish adds the partials in a fixed order (ascending strip, then ascending segment)
-//     -> bit-reproducible, no atomics.
+//     into shared memory by 32 TMA bulk copies on one mbarrier; a persistent CTA per SM walks its
+//     contiguous piece of a host-built tile sequence with a 3-stage ring, i.e. up to 192 KB in
+//     flight per SM;
+//   * thread r & 255 owns row r: row sums are accumulated per fragment in shared memory, the 32
+//     column sums stay in registers over a run of tiles of one strip ("Work decomposition" below);
+//   * the partials are added in the order of host-built lists -> bit-reproducible, no atomics.
 // =========================================================================================
 namespace vlgba {
 
@@ -1521,14 +1521,19 @@ k_p2p_allreduce(P2PMail mb, int n, unsigned int epoch, const int* __restrict__ d
 // Launched per iteration, the loop is three kernels (matvec 75 us, fold of its partials 10 us,
 // vector update 22 us with two grid syncs) plus their launch gaps and a host check of the stop
 // flag every 8 iterations.  Here one CTA per SM stays resident for the whole solve and an
-// iteration is five phases separated by the light grid barrier of ba_chol.cuh:
-//   1. matvec tiles through the TMA ring (symv_producer / symv_consumer, same code as k_symv_lower);
-//   2. fold of the row/column partials into wq (each CTA folds the row blocks b = cta, cta + G, ...;
-//      the NVLink mailbox exchange of multi-GPU runs happens here, per element); meanwhile the TMA
-//      engine pulls this CTA's cluster inverse into the (now idle) ring memory;
-//   3. q = U* p - wq and the dot products p'q, Z'q, SZ'p (block partials);
-//   4. alpha, x, r, z = M^-1 r from shared memory, r'z and r'r (block partials);
-//   5. beta, p, stop flag.
+// iteration is four phases, each closed by the light grid barrier of ba_chol.cuh:
+//   1. matvec tiles through the TMA ring (symv_producer / symv_consumer, same code as k_symv_lower),
+//      multiplying by p = z + beta p_old formed on the fly from the two vectors of the previous
+//      iteration (the owners store p for the later phases, nobody waits for it);
+//   2. fold of the fragment partials into wq (CTA c folds the 32-row blocks c, c + G, c + 2G at once,
+//      term offsets staged in shared memory once per solve; the NVLink mailbox exchange of multi-GPU
+//      runs happens here, per element); meanwhile the TMA engine pulls this CTA's cluster inverse M1
+//      and the head of the composite M2 into the (now idle) ring memory;
+//   3. q = U* p - wq and the dot products p'q, Z'q, SZ'p (block partials; halo threads fetch the
+//      operands of the neighbouring cameras' residual);
+//   4. alpha (scalar partials folded by one warp per scalar), x, r -- own and halo --,
+//      z = (M1^-1 + M2^-1) r from shared memory, r'z and r'r (block partials); after the barrier
+//      beta, the owners' p, the stop flag.
 // Clusters (update CTAs) are the first `nclusters` CTAs; every CTA folds the scalar partials so
 // that alpha, beta and the stop decision are uniform without a broadcast.
 // =========================================================================================
