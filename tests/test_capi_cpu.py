@@ -32,6 +32,18 @@ def test_defaults_are_the_reference_constants():
     assert o.num_variableK == 4 and o.lambda0 == 1e-3 and o.nu0 == 2.0
     assert o.max_iter == 20 and o.max_iter2 == 10 and o.rel_tol == 1e-3 and o.abs_tol == 1e-20
     assert o.backsub_all_rows == 0 and o.rtable == capi.RTABLE_HOST_LIBM
+    # solver-side defaults: everything that changes bits from run to run is opt-in
+    assert o.solver == capi.SOLVER_AUTO and o.pcg_deflate == 1 and o.pcg_cluster == 1 and o.model == capi.MODEL_EUCLID
+    assert o.pcg_autotune == 0 and o.pcg_rtol == 1e-8
+
+
+def test_opts_struct_matches_the_header():
+    """The ctypes mirror lists the fields of vlg_ba_opts in the header's order (the last one is written by
+    vlg_ba_opts_default through the C struct, so a layout slip shows up as a wrong default above too)."""
+    hdr = open(os.path.join(ROOT, "include", "vlg_ba.h")).read()
+    body = hdr[hdr.index("typedef struct vlg_ba_opts {"):hdr.index("} vlg_ba_opts;")]
+    fields = re.findall(r"^\s*(int|double)\s+([a-zA-Z0-9_]+);", body, flags=re.M)
+    assert [(n, {"int": C.c_int, "double": C.c_double}[t]) for t, n in fields] == list(capi.Opts._fields_)
 
 
 def test_option_parsing_mirrors_reference():
