@@ -1864,6 +1864,10 @@ k_pcg_persistent(PcgPersistArgs a)
         }
         if (!(pq > 0.0)) {                            // breakdown: uniform over the grid
             if (cta == 0 && tid == 0) { a.sc->done = 2; a.sc->pq = pq; a.sc->rz = rz; a.sc->iters += it; }
+            // the bulk copy of this iteration's cluster inverse is still on its way into this CTA's shared memory:
+            // let it land before the CTA (and its shared memory) goes away
+            if (cluster_cta && a.McL && tid == 0) mbar_wait(&mbarM, (uint32_t)(it & 1));
+            __syncthreads();
             return;
         }
         const double alpha = rz / pq;
