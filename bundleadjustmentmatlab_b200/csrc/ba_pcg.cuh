@@ -665,6 +665,8 @@ k_pcg_update_coop(int m, const int* __restrict__ cam_chunk_ptr, const double* __
     }
     if (!(pq > 0.0)) {                            // breakdown: every thread sees the same pq
         if (blockIdx.x == 0 && threadIdx.x == 0) { sc->done = 2; sc->pq = pq; }
+        if (McL && mcl_in_smem && threadIdx.x == 0) mbar_wait(&mbar, 0);      // the staged inverse must land before the CTA exits
+        __syncthreads();
         return;
     }
     const double alpha = rz / pq;
