@@ -30,3 +30,15 @@ def shard_points(obs_xy, obs_pt, obs_cam, b, rank: int, world: int):
     sel = (obs_pt >= lo) & (obs_pt < hi)
     return (np.ascontiguousarray(obs_xy[sel]), (obs_pt[sel] - lo).astype(np.int32), np.ascontiguousarray(obs_cam[sel]),
             np.ascontiguousarray(b[lo:hi]), (lo, hi))
+
+
+def strip_bounds(nstrips: int, nranks: int) -> np.ndarray:
+    """Column blocks of the assembled S for `nranks` ranks: strips [J_r, J_r+1) of 32 columns with equal lower-triangle
+    area, J_r = round(nstrips (1 - sqrt(1 - r / nranks))) -- the rule build_problem applies when set_comm preceded
+    set_problem (csrc/vlg_ba.cu, s_bounds); rank r multiplies only its block."""
+    J = [0]
+    for r in range(1, nranks):
+        J.append(min(nstrips, max(J[-1], int(round(nstrips * (1.0 - np.sqrt(1.0 - r / nranks)))))))
+    J.append(nstrips)
+    return np.asarray(J, dtype=np.int64)
+

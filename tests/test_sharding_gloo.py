@@ -9,6 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from bundleadjustmentmatlab_b200 import shard, synth
+from test_symv_plan import replay
 from oracle import lm
 
 
@@ -77,3 +78,31 @@ def test_point_ranges_balance_and_cover():
             assert np.all(np.diff(key) > 0)                      # still the reference's traversal order
             seen += pt.shape[0]
         assert seen == P.nobs
+
+
+def _matvec_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Np = 3200
+    J = shard.strip_bounds(Np // 32, world)
+    # this rank's column block through the library's own plan (vlg_ba_symv_plan), replayed with the kernel's semantics
+    y, ref, full, _ = replay(Np, 19, int(J[rank]), int(J[rank + 1]))
+    buf = torch.from_numpy(y.copy())
+    dist.all_reduce(buf)                                         # the per-iteration vector exchange
+    if rank == 0:
+        np.save(out, np.stack([buf.numpy(), full]))
+    dist.destroy_process_group()
+
+
+def test_symmetric_matvec_split_over_two_gloo_ranks(tmp_path):
+    """Multi-GPU assembled-S path on the host side: the ranks multiply equal-area column blocks of the lower triangle and
+    their partial products meet in one all-reduce."""
+    world = 2
+    out = str(tmp_path / "matvec.npy")
+    mp.spawn(_matvec_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got, full = np.load(out)
+    assert np.abs(got - full).max() <= 1e-10 * np.abs(full).max()
+    J = shard.strip_bounds(100, 4)
+    area = [sum(100 - j for j in range(J[r], J[r + 1])) for r in range(4)]
+    assert J[0] == 0 and J[-1] == 100 and max(area) - min(area) <= 2 * 100      # equal areas up to a strip
+
