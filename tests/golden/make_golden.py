@@ -27,9 +27,33 @@ CASES = {
 }
 
 
+# BASELINE.json config 1: the 4-view UCLA fixture (tests/golden/ucla4_tracks.npz, made by make_ucla4.py from the
+# reference's data/UCLA_0[1-4].jpg), with the options of mview_reconstruction.m:196 ('fix_calibration') and with
+# bundle_euclid's default (free intrinsics, bundle_euclid.m:49)
+UCLA_CASES = {
+    "euclid_ucla4_fixcal": ("fix_calibration",),
+    "euclid_ucla4_fullK": (),
+}
+
+
+class _Fixture:
+    def __init__(self, path):
+        f = np.load(path)
+        self.K, self.Te, self.w, self.Xe = f["K"], f["Te"], f["w"], f["Xe"]
+        self._x, self._vis = f["x"], f["visible"]
+        self.m, self.n = self.w.shape[1], self.Xe.shape[1]
+
+    def dense(self):
+        return np.asfortranarray(self._x), np.asfortranarray(self._vis)
+
+
 def main():
-    for name, (m, n, nobs, seed, opts) in CASES.items():
-        P = synth.make_problem(m, n, nobs, seed=seed)
+    cases = [(name, synth.make_problem(m, n, nobs, seed=seed), opts) for name, (m, n, nobs, seed, opts) in CASES.items()]
+    fx = os.path.join(HERE, "ucla4_tracks.npz")
+    if os.path.exists(fx):
+        cases += [(name, _Fixture(fx), opts) for name, opts in UCLA_CASES.items()]
+    for name, P, opts in cases:
+        m, n = P.m, P.n
         x, vis = P.dense()
         res = lm.bundle_euclid(P.K, P.Te, P.w, P.Xe, x, *opts, "visibility", vis, backend="ref")
         o = lm.parse_options(m, n, x, list(opts) + ["visibility", vis])
