@@ -839,7 +839,9 @@ k_sweep_cam(int nchunks, const int* __restrict__ chunk_begin, const int* __restr
 }
 
 // PCG scalars kept on the device: [0] rz, [1] r0norm2, [2] rnorm2, [3] iterations, [4] pq
-struct PcgScalars { double rz, r0n2, rn2, pq; int iters; int done; };
+// `exchanges`: matvec vector exchanges (mailbox epochs) the last launch of the persistent kernel consumed -- one more than
+// its completed iterations when it left through the breakdown exit
+struct PcgScalars { double rz, r0n2, rn2, pq; int iters; int done; int exchanges; int pad_; };
 
 // one-CTA vector kernels over the N = NA*m reduced unknowns (replicated on every rank)
 __device__ __forceinline__ double block_sum_1024(double v, double* sh)

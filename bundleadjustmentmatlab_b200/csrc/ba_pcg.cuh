@@ -1865,7 +1865,7 @@ k_pcg_persistent(PcgPersistArgs a)
             }
         }
         if (!(pq > 0.0)) {                            // breakdown: uniform over the grid
-            if (cta == 0 && tid == 0) { a.sc->done = 2; a.sc->pq = pq; a.sc->rz = rz; a.sc->iters += it; }
+            if (cta == 0 && tid == 0) { a.sc->done = 2; a.sc->pq = pq; a.sc->rz = rz; a.sc->iters += it; a.sc->exchanges = it + 1; }
             // the bulk copy of this iteration's cluster inverse is still on its way into this CTA's shared memory:
             // let it land before the CTA (and its shared memory) goes away
             if (cluster_cta && a.McL && tid == 0) mbar_wait(&mbarM, (uint32_t)(it & 1));
@@ -2030,7 +2030,7 @@ k_pcg_persistent(PcgPersistArgs a)
         const bool stop = rr <= a.rtol * a.rtol * r0n2 || it + 1 == a.max_iter;
         if (stop) {
             if (cta == 0 && tid == 0) {
-                a.sc->rz = rzn; a.sc->rn2 = rr; a.sc->pq = pq; a.sc->iters += it + 1;
+                a.sc->rz = rzn; a.sc->rn2 = rr; a.sc->pq = pq; a.sc->iters += it + 1; a.sc->exchanges = it + 1;
                 if (rr <= a.rtol * a.rtol * r0n2) a.sc->done = 1;
             }
             return;

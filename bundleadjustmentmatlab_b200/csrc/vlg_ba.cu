@@ -64,7 +64,7 @@ bool nccl_load()
     return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
 }
 
-char g_create_error[512] = "";
+thread_local char g_create_error[512] = "";     // failures without a context (create, stateless entries): per host thread
 
 enum TimerId { T_STAGE1_CAM = 0, T_STAGE1_PT, T_VINV, T_SCHUR, T_SCHUR_BLK, T_CHOL, T_SWEEP_PT, T_SWEEP_CAM, T_STAGE3, T_PCG_UPDATE, T_W_COPY, T_SYMV, T_PRECOND, T_PCG_PERSIST, T_COUNT };
 const char* kTimerNames[T_COUNT] = {"stage1_cam", "stage1_pt", "vinv", "schur", "schur_blocks", "chol", "pcg_sweep_pt",
@@ -199,6 +199,8 @@ struct vlg_ba_ctx {
     std::vector<void*> p2p_peer_S;        // opened peer S mappings
     bool p2p_ready = false;
     unsigned int p2p_epoch = 0;
+    long long* persist_prof = nullptr;    // VLG_BA_PERSIST_PROF: in-kernel clock64 profile of k_pcg_persistent (per context)
+    bool num_vis_user = false;            // vlg_ba_set_num_vis: the caller's num_vis (bundle_euclid.m:82) overrides the all-reduced count
     // accounting
     int64_t launches = 0;
     bool timers_on = false;
@@ -246,8 +248,36 @@ int dalloc(vlg_ba_ctx* ctx, T** p, size_t count)
     return VLG_BA_OK;
 }
 
+int allreduce(vlg_ba_ctx* ctx, double* buf, size_t count);
+
+// closes every peer mapping (mailboxes, shares of S) and frees this rank's mailbox
+void p2p_close(vlg_ba_ctx* ctx)
+{
+    for (void* q : ctx->p2p_peer_S)
+        if (q) cudaIpcCloseMemHandle(q);
+    ctx->p2p_peer_S.clear();
+    ctx->peer_S_ready = false;
+    for (size_t r = 0; r < ctx->p2p_peer_base.size(); r++)
+        if (ctx->p2p_peer_base[r] && ctx->p2p_peer_base[r] != ctx->p2p_base) cudaIpcCloseMemHandle(ctx->p2p_peer_base[r]);
+    ctx->p2p_peer_base.clear();
+    if (ctx->p2p_base) cudaFree(ctx->p2p_base);
+    if (ctx->p2p_dev) cudaFree(ctx->p2p_dev);
+    ctx->p2p_base = nullptr; ctx->p2p_dev = nullptr; ctx->p2p_ready = false; ctx->p2p_epoch = 0;
+}
+
+
 void free_problem(vlg_ba_ctx* ctx)
 {
+    // peer-memory state is sized by (and, for S, points into) the problem: close the peers' mappings first; on a live
+    // multi-rank context (set_problem_* is collective there) nobody may free an exported allocation before every importer
+    // has closed it, so the ranks meet in a 1-element all-reduce in between
+    const bool had_p2p = ctx->p2p_ready || ctx->peer_S_ready || ctx->p2p_base;
+    p2p_close(ctx);
+    if (had_p2p && ctx->nranks > 1 && ctx->comm && ctx->scal3) {
+        allreduce(ctx, ctx->scal3 + 3, 1);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    ctx->scal3 = nullptr;
     for (void* p : ctx->allocs) cudaFree(p);
     ctx->allocs.clear();
     ctx->have_problem = false;
@@ -539,6 +569,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CU(cudaSetDevice(ctx->device));
     ctx->m = m; ctx->n = n; ctx->na = na; ctx->nobs = nobs;
     ctx->num_vis = (double)nobs;
+    ctx->num_vis_user = false;
     const size_t N = (size_t)na * m;
 
     if (K) ctx->h_K.assign(K, K + 4 * (size_t)m);

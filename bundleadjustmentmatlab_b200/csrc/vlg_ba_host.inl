@@ -208,7 +208,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             // S <- sum over ranks, column block r on rank r (in place, one grouped ncclReduce per block); the cluster blocks
             // above were taken from the local shares and all-reduced on their own
             TimedScope ts(ctx, T_SCHUR_BLK);
-            if (ctx->peer_S_ready) {
+            if (ctx->p2p_ready && ctx->peer_S_ready) {
                 // every rank's share must be complete before anyone pulls: a 1-element all-reduce is the barrier (the solve
                 // itself keeps the ranks in lockstep afterwards, so nobody rewrites its share while it is being read)
                 CHK(allreduce(ctx, ctx->scal3 + 3, 1));
@@ -336,10 +336,10 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             // staging the cluster inverses with an evict-first hint keeps them (22 MB with both partitions) from crowding the matvec's
             // partials out of L2: measured -2.2 us (matvec phase) + 0.9 us (fold) per iteration at Venice shape
             { const char* e = getenv("VLG_BA_MCL_EVICT"); pa.mcl_evict_first = e ? atoi(e) : (overlap ? 1 : 0); }
-            static long long* d_prof = nullptr;
+            long long*& d_prof = ctx->persist_prof;
             const bool want_prof = getenv("VLG_BA_PERSIST_PROF") != nullptr;
             if (want_prof) {
-                if (!d_prof) cudaMalloc(&d_prof, (32 + 1024) * sizeof(long long));
+                if (!d_prof) CU(cudaMalloc(&d_prof, (32 + 1024) * sizeof(long long)));
                 cudaMemsetAsync(d_prof, 0, (32 + 1024) * sizeof(long long), ctx->stream);
                 pa.prof = d_prof;
             }
@@ -355,7 +355,7 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
             // autotuning, profile); otherwise the scalars are picked up at the step's final synchronisation
             deferred = !(ctx->nranks > 1 || pa.stat || want_prof);
             if (!deferred) CU(cudaStreamSynchronize(ctx->stream));
-            if (ctx->nranks > 1) ctx->p2p_epoch += (unsigned int)ctx->h_pcg->iters;       // one mailbox epoch per matvec, on every rank
+            if (ctx->nranks > 1) ctx->p2p_epoch += (unsigned int)ctx->h_pcg->exchanges;   // one mailbox epoch per matvec exchange, on every rank (the breakdown exit has used one more than it completed iterations)
             if (pa.stat && ctx->h_pcg->iters > 0) CHK(symv_learn(ctx));
             if (want_prof) {
                 long long hp[18];
@@ -519,7 +519,7 @@ static int resolve_cost(vlg_ba_ctx* ctx)
     if (!ctx->cost_pending) return VLG_BA_OK;
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->old_cost = ctx->h_pin[4];
-    ctx->num_vis = ctx->h_pin[5];
+    if (!ctx->num_vis_user) ctx->num_vis = ctx->h_pin[5];
     ctx->cost_pending = false;
     return VLG_BA_OK;
 }
@@ -653,7 +653,7 @@ void vlg_ba_opts_default(vlg_ba_opts* o)
 
 const char* vlg_ba_version(void) { return "vlgba 0.1 (sm_100a, fp64)"; }
 
-const char* vlg_ba_last_error(const vlg_ba_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+const char* vlg_ba_last_error(const vlg_ba_ctx* ctx) { return ctx ? ctx->err : g_create_error; }   // NULL: this thread's last context-less failure
 
 int vlg_ba_create(const vlg_ba_opts* opts, vlg_ba_ctx** out)
 {
@@ -689,8 +689,6 @@ int vlg_ba_create(const vlg_ba_opts* opts, vlg_ba_ctx** out)
     return VLG_BA_OK;
 }
 
-static void p2p_close(vlg_ba_ctx* ctx);
-
 void vlg_ba_destroy(vlg_ba_ctx* ctx)
 {
     if (!ctx) return;
@@ -704,6 +702,7 @@ void vlg_ba_destroy(vlg_ba_ctx* ctx)
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (int k = 0; k < 5; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 2; k++) if (ctx->ev_sw[k]) cudaEventDestroy(ctx->ev_sw[k]);
+    if (ctx->persist_prof) cudaFree(ctx->persist_prof);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_pcg) cudaFreeHost(ctx->h_pcg);
     if (ctx->ev_da) cudaEventDestroy(ctx->ev_da);
@@ -735,20 +734,6 @@ int vlg_ba_set_comm(vlg_ba_ctx* ctx, int rank, int nranks, const void* unique_id
     if (r != 0) return fail(ctx, VLG_BA_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     ctx->rank = rank; ctx->nranks = nranks;
     return VLG_BA_OK;
-}
-
-static void p2p_close(vlg_ba_ctx* ctx)
-{
-    for (void* q : ctx->p2p_peer_S)
-        if (q) cudaIpcCloseMemHandle(q);
-    ctx->p2p_peer_S.clear();
-    ctx->peer_S_ready = false;
-    for (size_t r = 0; r < ctx->p2p_peer_base.size(); r++)
-        if (ctx->p2p_peer_base[r] && ctx->p2p_peer_base[r] != ctx->p2p_base) cudaIpcCloseMemHandle(ctx->p2p_peer_base[r]);
-    ctx->p2p_peer_base.clear();
-    if (ctx->p2p_base) cudaFree(ctx->p2p_base);
-    if (ctx->p2p_dev) cudaFree(ctx->p2p_dev);
-    ctx->p2p_base = nullptr; ctx->p2p_dev = nullptr; ctx->p2p_ready = false; ctx->p2p_epoch = 0;
 }
 
 int vlg_ba_p2p_export(vlg_ba_ctx* ctx, void* ipc_handle_64)
@@ -863,7 +848,9 @@ int vlg_ba_set_problem_dense(vlg_ba_ctx* ctx, int m, int n, const double* K, con
 int vlg_ba_set_num_vis(vlg_ba_ctx* ctx, double num_vis)
 {
     if (!ctx) return VLG_BA_EINVAL;
+    if (!(num_vis > 0.0)) { ctx->num_vis_user = false; return VLG_BA_OK; }     // back to the all-reduced observation count
     ctx->num_vis = num_vis;
+    ctx->num_vis_user = true;
     return VLG_BA_OK;
 }
 
@@ -934,11 +921,15 @@ int vlg_ba_get_jacobians(vlg_ba_ctx* ctx, double* X_hat, double* A, double* B, d
     CU(cudaSetDevice(ctx->device));
     const size_t no = (size_t)ctx->nobs, na = (size_t)ctx->na;
     double *dX = nullptr, *dA = nullptr, *dB = nullptr, *de = nullptr;
-    CU(cudaMalloc(&dX, sizeof(double) * std::max<size_t>(2 * no, 1)));
-    CU(cudaMalloc(&dA, sizeof(double) * std::max<size_t>(2 * na * no, 1)));
-    CU(cudaMalloc(&dB, sizeof(double) * std::max<size_t>(6 * no, 1)));
-    CU(cudaMalloc(&de, sizeof(double) * std::max<size_t>(2 * no, 1)));
-    int r = DISPATCH_NA(ctx, run_stage1)(ctx, dX, dA, dB, de);
+    int r = VLG_BA_OK;
+    {
+        cudaError_t e = cudaMalloc(&dX, sizeof(double) * std::max<size_t>(2 * no, 1));
+        if (e == cudaSuccess) e = cudaMalloc(&dA, sizeof(double) * std::max<size_t>(2 * na * no, 1));
+        if (e == cudaSuccess) e = cudaMalloc(&dB, sizeof(double) * std::max<size_t>(6 * no, 1));
+        if (e == cudaSuccess) e = cudaMalloc(&de, sizeof(double) * std::max<size_t>(2 * no, 1));
+        if (e != cudaSuccess) r = fail(ctx, VLG_BA_ENOMEM, "get_jacobians: cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    if (r == VLG_BA_OK) r = DISPATCH_NA(ctx, run_stage1)(ctx, dX, dA, dB, de);
     if (r == VLG_BA_OK) r = download(ctx, X_hat, dX, 2 * no);
     if (r == VLG_BA_OK) r = download(ctx, A, dA, 2 * na * no);
     if (r == VLG_BA_OK) r = download(ctx, B, dB, 6 * no);
@@ -1017,12 +1008,12 @@ int vlg_ba_reproj_errors(vlg_ba_ctx* ctx, double depth_max, double* err, double*
     const size_t no = (size_t)ctx->nobs;
     double *d_err = nullptr, *d_depth = nullptr, *d_bad = nullptr, *d_sc = nullptr;
     long long* d_idx = nullptr;
-    CU(cudaMalloc(&d_err, sizeof(double) * std::max<size_t>(no, 1)));
-    CU(cudaMalloc(&d_depth, sizeof(double) * std::max<size_t>(no, 1)));
-    CU(cudaMalloc(&d_bad, sizeof(double) * std::max<size_t>(no, 1)));
-    CU(cudaMalloc(&d_sc, sizeof(double) * 4));
-    CU(cudaMalloc(&d_idx, sizeof(long long)));
     auto body = [&]() -> int {
+        CU(cudaMalloc(&d_err, sizeof(double) * std::max<size_t>(no, 1)));
+        CU(cudaMalloc(&d_depth, sizeof(double) * std::max<size_t>(no, 1)));
+        CU(cudaMalloc(&d_bad, sizeof(double) * std::max<size_t>(no, 1)));
+        CU(cudaMalloc(&d_sc, sizeof(double) * 4));
+        CU(cudaMalloc(&d_idx, sizeof(long long)));
         CHK(DISPATCH_NA(ctx, run_reproj_errors)(ctx, depth_max, d_err, d_depth, d_bad));
         CHK(reduce_to(ctx, d_err, no, d_sc));
         CHK(reduce_to(ctx, d_bad, no, d_sc + 1));

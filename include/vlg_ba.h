@@ -110,7 +110,7 @@ const char *vlg_ba_version(void);
 /* Context: one per host thread / GPU. */
 int  vlg_ba_create(const vlg_ba_opts *opts, vlg_ba_ctx **out);
 void vlg_ba_destroy(vlg_ba_ctx *ctx);
-const char *vlg_ba_last_error(const vlg_ba_ctx *ctx);      /* ctx may be NULL: error of a failed create */
+const char *vlg_ba_last_error(const vlg_ba_ctx *ctx);      /* ctx may be NULL: this host thread's last failure without a context (create, stateless entries) */
 
 /* Multi-GPU: one context per rank holding a point shard.  `unique_id` is the
  * 128-byte ncclUniqueId obtained from vlg_ba_nccl_unique_id() on rank 0 and broadcast by
@@ -146,7 +146,9 @@ int  vlg_ba_set_problem_dense(vlg_ba_ctx *ctx, int m, int n, const double *K, co
 int  vlg_ba_set_problem_sparse(vlg_ba_ctx *ctx, int m, int n, const double *K, const double *a,
                                const double *b, int64_t nobs, const double *obs_xy,
                                const int32_t *obs_pt, const int32_t *obs_cam, const double *pivot);
-/* n_total_obs: num_vis over ALL ranks (bundle_euclid.m:82); defaults to the local count. */
+/* num_vis of bundle_euclid.m:82 (the divisor of error_, :229-231).  Default: the number of list entries summed over all
+ * ranks -- `visible` is treated as a 0/1 mask (the reference's sum(visible(:)) differs only for a non-binary array).
+ * A positive value overrides that count until the next set_problem_*; <= 0 restores the default. */
 int  vlg_ba_set_num_vis(vlg_ba_ctx *ctx, double num_vis);
 
 int64_t vlg_ba_nobs(const vlg_ba_ctx *ctx);

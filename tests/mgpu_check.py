@@ -69,6 +69,26 @@ def main():
             assert info["solver_used"] == solver
         dist.barrier()
         ctx.close()
+    # context re-use on a live multi-rank context (the incremental cadence): set_problem_* again with
+    # another problem must drop every peer mapping of the old one (mailbox, shares of S) and work after a fresh
+    # export / import -- the first problem's S is freed, a stale pull would read freed peer memory
+    P2 = synth.make_problem(40, 9000, 41000, seed=5)
+    a2 = np.ascontiguousarray(np.vstack([P2.w, P2.Te]).T); b2 = np.ascontiguousarray(P2.Xe[:3].T)
+    c1 = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG_EXPLICIT, pcg_rtol=1e-12, device=local)
+    c1.set_problem_sparse(P2.K.T, a2, b2, P2.obs_xy, P2.obs_pt, P2.obs_cam)
+    ref2 = c1.trial_step()
+    c1.close()
+    ctx = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG_EXPLICIT, pcg_rtol=1e-12, device=local)
+    ctx.set_comm(rank, world, fresh_uid())
+    for (PP, aa, bb, want) in ((P, a, b, ref[capi.SOLVER_PCG_EXPLICIT][0][1]), (P2, a2, b2, ref2)):
+        xy, pt, cam, bl, _ = shard.shard_points(PP.obs_xy, PP.obs_pt, PP.obs_cam, bb, rank, world)
+        ctx.set_problem_sparse(PP.K.T, aa, bl, xy, pt, cam)
+        exchange_mailboxes(ctx)
+        info = ctx.trial_step()
+        for key in ("old_cost", "new_cost"):
+            worst = max(worst, abs(info[key] - want[key]) / want[key])
+        dist.barrier()
+    ctx.close()
     w = torch.tensor([worst], dtype=torch.float64, device="cuda")
     dist.all_reduce(w, op=dist.ReduceOp.MAX)
     if rank == 0:
