@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvlgba.so")
+LIB_PATH = os.environ.get("VLG_BA_LIB") or os.path.join(_HERE, "libvlgba.so")      # VLG_BA_LIB: an experimental build of the same library
 
 SOLVER_AUTO, SOLVER_CHOL, SOLVER_PCG, SOLVER_PCG_EXPLICIT = 0, 1, 2, 3
 MODEL_EUCLID, MODEL_PROJECTIVE = 0, 1
@@ -61,7 +61,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan", "vlg_ba_selftest_quotients",
 ]
 
 
@@ -321,6 +321,16 @@ class Context:
         ms, cnt = C.c_double(), C.c_int64()
         self._ck(self._L.vlg_ba_kernel_time(self._h, name.encode(), C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
+
+
+def selftest_quotients(nsamples: int = 10**9, seed: int = 1, device: int = -1) -> int:
+    """Bitwise mismatches between stage 1's shared-reciprocal quotients and __ddiv_rn over random operands (must be 0)."""
+    L = lib()
+    bad = C.c_int64()
+    r = L.vlg_ba_selftest_quotients(C.c_int(device), C.c_int64(nsamples), C.c_uint64(seed), C.byref(bad))
+    if r != 0:
+        raise VlgBaError(f"vlg_ba_selftest_quotients: {L.vlg_ba_last_error(None).decode()}")
+    return int(bad.value)
 
 
 def symv_plan(Np: int, G: int, J0: int = 0, J1: int | None = None, speed=None) -> dict:

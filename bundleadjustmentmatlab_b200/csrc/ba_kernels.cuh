@@ -32,7 +32,10 @@ struct Stage1Args {
     const double* rtab;
     const unsigned char* cam_fixed;
     int fix_structure;
+    int ref_order;              // VLG_BA_ORDER_REFERENCE: U/eA accumulated in one chain, ascending observation order
+    const int* obs_slot;        // C-order -> P-order slot of each observation
     double* W;
+    double* BeP;                // [nobs][8], P-order: B (2 x 3) and e of each observation, for the point pass
     double* Upart;              // [nchunks][NU]
     // diagnostics (NULL in production)
     double* dX_hat; double* dA; double* dB; double* de;
@@ -40,16 +43,32 @@ struct Stage1Args {
 
 // ---------------------------------------------------------------------------------------
 // stage 1, camera pass ("resid_jac_normal"): one warp per chunk of one camera's segment.
-// Per observation: X_hat, A, B, e (bit-exact, ba_math.cuh), W_ij = A'B written through a
-// shared-memory tile so that the global stores are contiguous, and the NU = NA(NA+1)/2 + NA
+// Per observation: X_hat, A, B, e ONCE (bit-exact, ba_math.cuh), W_ij = A'B written through a
+// shared-memory tile so that the global stores are contiguous, B and e left as one 64-byte record (two
+// whole 32-byte sectors) at the observation's P-order slot for the point pass, and the NU = NA(NA+1)/2 + NA
 // distinct entries of A'A and A'e staged in shared memory and accumulated by lane r in
 // ascending observation order -- the reference's order (mex_bundle_1_XABeUVWeAeB.c:281-290,
 // :317-323).  One partial per chunk; k_stage1_cam_finalize adds the chunks of a camera in
 // order.  With one chunk per camera (VLG_BA_ORDER_REFERENCE) U and eA are bit-identical to
 // the reference.
 // ---------------------------------------------------------------------------------------
+// the same observation with one __ddiv_rn per quotient: taken when a depth is so small or so large that the shared
+// reciprocals of the fast path could over/underflow (never on a sane scene)
+template <int NA>
+__device__ __noinline__ void obs_jacobian_exact(const double* __restrict__ R4, const double* __restrict__ a, double fx, double fy,
+                                                double cx, double cy, double b0, double b1, double b2, double ox, double oy,
+                                                double* __restrict__ X0, double* __restrict__ A, double* __restrict__ B,
+                                                double* __restrict__ e)
+{
+    if constexpr (NA == kNaProjective) obs_jacobian_proj<false>(a, b0, b1, b2, ox, oy, X0, A, B, e);
+    else obs_jacobian<NA, false>(R4, a, fx, fy, cx, cy, b0, b1, b2, ox, oy, X0, A, B, e);
+}
+
 template <int NA, bool DIAG>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, NA == 6 ? 4 : 1)      // NA = 6: <= 128 registers, 4 CTAs (16 warps) per SM
+#ifndef VLG_S1_MINB
+#define VLG_S1_MINB 3
+#endif
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NA == 6 ? VLG_S1_MINB : 1)      // NA = 6: <= 168 registers, 3 CTAs (12 warps) per SM -- with the two-deep prefetch 128 registers spill (measured 0.48 vs 0.39 ms at Venice shape)
 k_stage1_cam(Stage1Args p)
 {
     constexpr int NU = nu_of(NA);
@@ -77,21 +96,61 @@ k_stage1_cam(Stage1Args p)
     if (!kProj) effective_K<NA>(camK, cama, fx, fy, cx, cy);
     const bool zeroW = p.fix_structure || p.cam_fixed[j];
 
+    // U/eA partial of the chunk: lane r owns entry r (and r+32, r+64 for NA = 10).  Reference order: one chain in ascending
+    // observation order; chunked order (default): four interleaved chains (observation k -> chain k & 3), combined as
+    // (c0 + c1) + (c2 + c3) at the end -- a fixed shape as well, and a quarter of the dependent-add latency.
     constexpr int NACC = (NU + 31) / 32;
-    double acc[NACC];
+    double acc[NACC][4];
 #pragma unroll
-    for (int t = 0; t < NACC; t++) acc[t] = 0.0;
+    for (int t = 0; t < NACC; t++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[t][u] = 0.0;
+    const bool ref_order = p.ref_order != 0;
+
+    // software pipeline over the batches of 32 observations: the observation records (image point, point id, P-order
+    // slot) are fetched two batches ahead and the point coordinates one batch ahead, so that a batch never waits for the
+    // two dependent memory round trips id -> b (ncu, round 2: long-scoreboard stalls were 60 % of this kernel's issue slots)
+    struct Rec { double2 xy; int i, slot; };
+    auto load_rec = [&](int o) {
+        Rec r;
+        r.xy = make_double2(0.0, 0.0); r.i = 0; r.slot = 0;
+        if (o < end) { r.xy = __ldg(p.obs_xy + o); r.i = __ldg(p.obs_pt + o); r.slot = __ldg(p.obs_slot + o); }
+        return r;
+    };
+    Rec cur = load_rec(beg + lane), nxt = load_rec(beg + 32 + lane);
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    if (beg + lane < end) { b0 = __ldg(p.b + (size_t)3 * cur.i); b1 = __ldg(p.b + (size_t)3 * cur.i + 1); b2 = __ldg(p.b + (size_t)3 * cur.i + 2); }
 
     for (int base = beg; base < end; base += 32) {
         const int o = base + lane;
         const int cnt = min(32, end - base);
+        // next batch's point, the batch after's record
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+        if (o + 32 < end) { n0 = __ldg(p.b + (size_t)3 * nxt.i); n1 = __ldg(p.b + (size_t)3 * nxt.i + 1); n2 = __ldg(p.b + (size_t)3 * nxt.i + 2); }
+        const Rec nn = load_rec(o + 64);
         if (o < end) {
-            const double2 xy = p.obs_xy[o];
-            const int i = p.obs_pt[o];
-            const double b0 = p.b[(size_t)3 * i], b1 = p.b[(size_t)3 * i + 1], b2 = p.b[(size_t)3 * i + 2];
+            const double2 xy = cur.xy;
             double X0[2], A[2 * NA], B[6], e[2];
-            if constexpr (kProj) obs_jacobian_proj<true>(cama, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
-            else obs_jacobian<NA>(camR, cama, fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
+            bool ok;
+            if constexpr (kProj) ok = obs_jacobian_proj<true>(cama, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
+            else ok = obs_jacobian<NA, true>(camR, cama, fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, X0, A, B, e);
+            if (!ok) {
+                // a depth outside the reciprocals' safe window: one __ddiv_rn per quotient (own buffers, so that the
+                // arrays of the fast path never have their address taken and stay in registers)
+                double Xs[2], As[2 * NA], Bs[6], es[2];
+                obs_jacobian_exact<NA>(camR, cama, fx, fy, cx, cy, b0, b1, b2, xy.x, xy.y, Xs, As, Bs, es);
+                X0[0] = Xs[0]; X0[1] = Xs[1]; e[0] = es[0]; e[1] = es[1];
+#pragma unroll
+                for (int k = 0; k < 2 * NA; k++) A[k] = As[k];
+#pragma unroll
+                for (int k = 0; k < 6; k++) B[k] = Bs[k];
+            }
+            {
+                // B | e -> the observation's P-order slot: 64 bytes, 64-byte aligned
+                double2* rec = reinterpret_cast<double2*>(p.BeP + (size_t)8 * cur.slot);
+                rec[0] = make_double2(B[0], B[1]); rec[1] = make_double2(B[2], B[3]);
+                rec[2] = make_double2(B[4], B[5]); rec[3] = make_double2(e[0], e[1]);
+            }
             if (DIAG) {
                 if (p.dX_hat) { p.dX_hat[(size_t)2 * o] = X0[0]; p.dX_hat[(size_t)2 * o + 1] = X0[1]; }
                 if (p.dA) for (int k = 0; k < 2 * NA; k++) p.dA[(size_t)2 * NA * o + k] = A[k];
@@ -123,22 +182,34 @@ k_stage1_cam(Stage1Args p)
             const int tot = cnt * NW;
             for (int t = lane; t < tot; t += 32) Wg[t] = wst[t];
         }
-        // in-order accumulation: lane r owns entry r (and r+32, r+64 for NA = 10)
 #pragma unroll
         for (int t = 0; t < NACC; t++) {
             const int r = lane + 32 * t;
             if (r < NU) {
-                double s = acc[t];
-                for (int k = 0; k < cnt; k++) s = VLG_P(s, ust[k * NU + r]);
-                acc[t] = s;
+                if (ref_order) {
+                    double sv = acc[t][0];
+                    for (int k = 0; k < cnt; k++) sv = VLG_P(sv, ust[k * NU + r]);
+                    acc[t][0] = sv;
+                } else {
+                    int k = 0;
+                    for (; k + 3 < cnt; k += 4) {
+                        acc[t][0] = VLG_P(acc[t][0], ust[k * NU + r]);
+                        acc[t][1] = VLG_P(acc[t][1], ust[(k + 1) * NU + r]);
+                        acc[t][2] = VLG_P(acc[t][2], ust[(k + 2) * NU + r]);
+                        acc[t][3] = VLG_P(acc[t][3], ust[(k + 3) * NU + r]);
+                    }
+                    for (; k < cnt; k++) acc[t][0] = VLG_P(acc[t][0], ust[k * NU + r]);     // tail of the chunk's last batch
+                }
             }
         }
         __syncwarp();
+        cur = nxt; nxt = nn;
+        b0 = n0; b1 = n1; b2 = n2;
     }
 #pragma unroll
     for (int t = 0; t < NACC; t++) {
         const int r = lane + 32 * t;
-        if (r < NU) p.Upart[(size_t)NU * c + r] = acc[t];
+        if (r < NU) p.Upart[(size_t)NU * c + r] = ref_order ? acc[t][0] : VLG_P(VLG_P(acc[t][0], acc[t][1]), VLG_P(acc[t][2], acc[t][3]));
     }
 }
 
@@ -172,69 +243,44 @@ __global__ void k_stage1_cam_finalize(int m, const int* __restrict__ cam_chunk_p
     }
 }
 
-// B (2 x 3) and e of one observation of camera j, as the point passes need them: the camera's
-// parameters come through the read-only path (every lane has its own camera)
-template <int NA>
-__device__ __forceinline__ void point_terms(int j, const double* __restrict__ K4, const double* __restrict__ a,
-                                            const double* __restrict__ rtab, double b0, double b1, double b2,
-                                            double ox, double oy, double* __restrict__ B, double* __restrict__ e)
+// The 10 products a point accumulates per observation, from the record the camera pass left: B'B (upper triangle),
+// B'e and e'e, each the reference's two-term sum (mex_bundle_1_XABeUVWeAeB.c:293-302, :326-332)
+__device__ __forceinline__ void point_products(const double* __restrict__ rec, double* __restrict__ pr)
 {
-    const double* aj = a + (size_t)NA * j;
-    if constexpr (NA == kNaProjective) {
-        double Pl[12], X0[2];
-#pragma unroll
-        for (int k = 0; k < 12; k++) Pl[k] = __ldg(aj + k);
-        obs_jacobian_proj<false>(Pl, b0, b1, b2, ox, oy, X0, nullptr, B, e);
-    } else {
-        const double* R = rtab + (size_t)36 * j;
-        double Rl[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rl[k] = __ldg(R + k);
-        double al[NA];
-#pragma unroll
-        for (int k = 3; k < NA; k++) al[k] = __ldg(aj + k);
-        double fx, fy, cx, cy;
-        double Kl[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) Kl[k] = __ldg(K4 + (size_t)4 * j + k);
-        effective_K<NA>(Kl, al, fx, fy, cx, cy);
-        obs_point_jacobian(Rl, al[3], al[4], al[5], fx, fy, cx, cy, b0, b1, b2, ox, oy, B, e);
-    }
+    const double2* r = reinterpret_cast<const double2*>(rec);
+    const double2 B0 = r[0], B1 = r[1], B2 = r[2], e = r[3];
+    pr[0] = dot2(B0.x, B0.y, B0.x, B0.y);
+    pr[1] = dot2(B1.x, B1.y, B0.x, B0.y);
+    pr[2] = dot2(B2.x, B2.y, B0.x, B0.y);
+    pr[3] = dot2(B1.x, B1.y, B1.x, B1.y);
+    pr[4] = dot2(B2.x, B2.y, B1.x, B1.y);
+    pr[5] = dot2(B2.x, B2.y, B2.x, B2.y);
+    pr[6] = dot2(B0.x, B0.y, e.x, e.y);
+    pr[7] = dot2(B1.x, B1.y, e.x, e.y);
+    pr[8] = dot2(B2.x, B2.y, e.x, e.y);
+    pr[9] = e.x * e.x + e.y * e.y;
 }
 
 // ---------------------------------------------------------------------------------------
-// stage 1, point pass: one thread per point walks its track in ascending camera order
-// (the reference's order for V_i and eB_i, mex_bundle_1_XABeUVWeAeB.c:293-302,:326-332),
-// recomputes B and e (4 of the 10 reprojections, bit-identical to the camera pass) and
-// writes V_i, eB_i and the point's share of the cost e'e (bundle_euclid.m:209).
+// stage 1, point pass: V_i, eB_i and the point's share of the cost e'e (bundle_euclid.m:209) from the
+// B | e records of the camera pass (P-order, so a point's track is contiguous), added in ascending
+// camera order -- the reference's order for V_i and eB_i.  Nothing is reprojected a second time.
+// Thread-per-point form (tracks longer than a tile).
 // ---------------------------------------------------------------------------------------
-template <int NA>
-__global__ void k_stage1_pt(int n, const int* __restrict__ pt_ptr, const int* __restrict__ pt_cam,
-                            const double2* __restrict__ pt_xy, const double* __restrict__ K4,
-                            const double* __restrict__ a, const double* __restrict__ b,
-                            const double* __restrict__ rtab, int fix_structure,
+__global__ void k_stage1_pt(int n, const int* __restrict__ pt_ptr, const double* __restrict__ BeP, int fix_structure,
                             double* __restrict__ V, double* __restrict__ eB, double* __restrict__ cost_pt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double b0 = b[(size_t)3 * i], b1 = b[(size_t)3 * i + 1], b2 = b[(size_t)3 * i + 2];
     double v00 = 0, v10 = 0, v20 = 0, v11 = 0, v21 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
     const int q0 = pt_ptr[i], q1 = pt_ptr[i + 1];
     for (int q = q0; q < q1; q++) {
-        const int j = pt_cam[q];
-        const double2 xy = pt_xy[q];
-        double B[6], e[2];
-        point_terms<NA>(j, K4, a, rtab, b0, b1, b2, xy.x, xy.y, B, e);
-        v00 = VLG_P(v00, dot2(B[0], B[1], B[0], B[1]));
-        v10 = VLG_P(v10, dot2(B[2], B[3], B[0], B[1]));
-        v20 = VLG_P(v20, dot2(B[4], B[5], B[0], B[1]));
-        v11 = VLG_P(v11, dot2(B[2], B[3], B[2], B[3]));
-        v21 = VLG_P(v21, dot2(B[4], B[5], B[2], B[3]));
-        v22 = VLG_P(v22, dot2(B[4], B[5], B[4], B[5]));
-        g0 = VLG_P(g0, dot2(B[0], B[1], e[0], e[1]));
-        g1 = VLG_P(g1, dot2(B[2], B[3], e[0], e[1]));
-        g2 = VLG_P(g2, dot2(B[4], B[5], e[0], e[1]));
-        cost += e[0] * e[0] + e[1] * e[1];
+        double pr[10];
+        point_products(BeP + (size_t)8 * q, pr);
+        v00 = VLG_P(v00, pr[0]); v10 = VLG_P(v10, pr[1]); v20 = VLG_P(v20, pr[2]);
+        v11 = VLG_P(v11, pr[3]); v21 = VLG_P(v21, pr[4]); v22 = VLG_P(v22, pr[5]);
+        g0 = VLG_P(g0, pr[6]); g1 = VLG_P(g1, pr[7]); g2 = VLG_P(g2, pr[8]);
+        cost += pr[9];
     }
     if (fix_structure) { v00 = v10 = v20 = v11 = v21 = v22 = 0.0; g0 = g1 = g2 = 0.0; }   // bundle_euclid.m:140-144
     double* Vi = V + (size_t)9 * i;
@@ -246,45 +292,25 @@ __global__ void k_stage1_pt(int n, const int* __restrict__ pt_ptr, const int* __
 }
 
 // ---------------------------------------------------------------------------------------
-// deterministic sum of a long vector: fixed-shape two-level tree (grid of kRedBlocks CTAs,
-// then one CTA).  out[slot] = sum(in[0..n)).
+// The same with one LANE per observation: a CTA owns a tile of whole points (<= kS1Tile observations); every
+// thread forms the 10 products of one record, then one thread per point adds its track in ascending camera
+// order -- bit-identical to k_stage1_pt, without the divergence of a thread-per-point loop over tracks of 2..64.
 // ---------------------------------------------------------------------------------------
-// The same point pass with one LANE per observation: a CTA owns a tile of whole points (<= kS1Tile
-// observations, the tile list of the PCG point sweep), every thread does the 4 reprojections of one
-// observation and leaves the 10 products (B'B, B'e, e'e) in shared memory, then one thread per point
-// adds its track in ascending camera order -- the reference's order, bit-identical to k_stage1_pt --
-// without the divergence of a thread-per-point loop over tracks of 2..64 observations (0.49 -> see
-// DESIGN.md).
 constexpr int kS1Tile = 512;
 
-template <int NA>
 __global__ void __launch_bounds__(kS1Tile)
 k_stage1_pt_tiled(const int4* __restrict__ ptile_meta /* (q0, nob, p0, npts) */, const int* __restrict__ pt_ptr,
-                  const int* __restrict__ pt_cam, const int* __restrict__ pt_pt, const double2* __restrict__ pt_xy,
-                  const double* __restrict__ K4, const double* __restrict__ a, const double* __restrict__ b,
-                  const double* __restrict__ rtab, int fix_structure, double* __restrict__ V,
+                  const double* __restrict__ BeP, int fix_structure, double* __restrict__ V,
                   double* __restrict__ eB, double* __restrict__ cost_pt)
 {
     __shared__ double pr[10][kS1Tile];
     const int4 meta = __ldg(ptile_meta + blockIdx.x);
     const int q0 = meta.x, nob = meta.y, p0 = meta.z, np = meta.w, tid = threadIdx.x;
     if (tid < nob) {
-        const int q = q0 + tid;
-        const int j = pt_cam[q], i = pt_pt[q];
-        const double2 xy = pt_xy[q];
-        const double b0 = __ldg(b + (size_t)3 * i), b1 = __ldg(b + (size_t)3 * i + 1), b2 = __ldg(b + (size_t)3 * i + 2);
-        double B[6], e[2];
-        point_terms<NA>(j, K4, a, rtab, b0, b1, b2, xy.x, xy.y, B, e);
-        pr[0][tid] = dot2(B[0], B[1], B[0], B[1]);
-        pr[1][tid] = dot2(B[2], B[3], B[0], B[1]);
-        pr[2][tid] = dot2(B[4], B[5], B[0], B[1]);
-        pr[3][tid] = dot2(B[2], B[3], B[2], B[3]);
-        pr[4][tid] = dot2(B[4], B[5], B[2], B[3]);
-        pr[5][tid] = dot2(B[4], B[5], B[4], B[5]);
-        pr[6][tid] = dot2(B[0], B[1], e[0], e[1]);
-        pr[7][tid] = dot2(B[2], B[3], e[0], e[1]);
-        pr[8][tid] = dot2(B[4], B[5], e[0], e[1]);
-        pr[9][tid] = e[0] * e[0] + e[1] * e[1];
+        double v[10];
+        point_products(BeP + (size_t)8 * (q0 + tid), v);
+#pragma unroll
+        for (int k = 0; k < 10; k++) pr[k][tid] = v[k];
     }
     __syncthreads();
     if (tid < np) {
@@ -307,6 +333,10 @@ k_stage1_pt_tiled(const int4* __restrict__ ptile_meta /* (q0, nob, p0, npts) */,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// deterministic sum of a long vector: fixed-shape two-level tree (grid of kRedBlocks CTAs,
+// then one CTA).  out[slot] = sum(in[0..n)).
+// ---------------------------------------------------------------------------------------
 constexpr int kRedBlocks = 296;
 constexpr int kRedThreads = 256;
 
@@ -1152,6 +1182,49 @@ __global__ void __launch_bounds__(1024) k_argmax_sq(int64_t nobs, const double* 
         __syncthreads();
     }
     if (threadIdx.x == 0) { *out_val = sv[0] < 0.0 ? 0.0 : sv[0]; *out_idx = si[0]; }
+}
+
+// ---------------------------------------------------------------------------------------
+// self-test of the shared-reciprocal quotients (ba_math.cuh: Den, fd_quot) against __ddiv_rn on random operands:
+// class 0: a, d with random significands and exponents in +-200 (d inside the reciprocals' safe window);
+// class 1: depths d in [0.01, 1e4), numerators |a| < 1e7 (what a reprojection divides);
+// class 2: a = difference of two nearby image coordinates, d = h (what a forward difference divides).
+// Every thread runs `per_thread` samples of a counter-based generator; mismatches are counted bitwise.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_selftest_quotients(unsigned long long seed, int per_thread, unsigned long long* __restrict__ mismatches)
+{
+    unsigned long long st = seed + 0x632BE59BD9B4E019ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1);
+    unsigned long long bad = 0;
+    for (int k = 0; k < per_thread; k++) {
+        const unsigned long long u = splitmix64(st), v = splitmix64(st), w = splitmix64(st);
+        const int cls = (int)(w % 3);
+        double a, d;
+        if (cls == 0) {
+            const long long ea = 1023 - 200 + (long long)((w >> 8) % 401), ed = 1023 - 200 + (long long)((w >> 24) % 401);
+            a = __longlong_as_double((long long)((u & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)ea << 52)));
+            d = __longlong_as_double((long long)((v & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)ed << 52)));
+        } else if (cls == 1) {
+            d = 0.01 * exp2(19.93 * ((double)(v >> 11) * 0x1.0p-53));
+            a = 2e7 * ((double)(u >> 11) * 0x1.0p-53) - 1e7;
+        } else {
+            const double x0 = 500.0 * ((double)(u >> 11) * 0x1.0p-53);
+            const double x1 = x0 + (((double)(v >> 11) * 0x1.0p-53) - 0.5) * 1e-6 * (double)(1 + (w >> 40) % 1000);
+            a = x1 - x0; d = kFdStep;
+        }
+        const double ref = __ddiv_rn(a, d);
+        const double got = cls == 2 ? fd_quot<true>(a + 0.0, 0.0) : Den<true>(d)(a);
+        bad += __double_as_longlong(ref) != __double_as_longlong(got);
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace vlgba

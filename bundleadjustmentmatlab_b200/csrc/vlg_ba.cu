@@ -130,7 +130,7 @@ struct vlg_ba_ctx {
     std::vector<double> h_obs_xy;
     std::vector<int32_t> h_blk_j, h_blk_k;
     // device: structure
-    double2 *obs_xy = nullptr, *pt_xy = nullptr;
+    double2* obs_xy = nullptr;
     int *obs_pt = nullptr, *obs_cam = nullptr, *cam_ptr = nullptr, *pt_ptr = nullptr, *pt_obs = nullptr, *pt_cam = nullptr;
     int *chunk_cam = nullptr, *chunk_begin = nullptr, *chunk_end = nullptr, *cam_chunk_ptr = nullptr;
     unsigned char* cam_fixed = nullptr;
@@ -144,7 +144,6 @@ struct vlg_ba_ctx {
     int4* ptile_meta = nullptr;      // point tiles of the PCG point sweep: (q0, nob, p0, npts)
     int4* s1tile_meta = nullptr;     // point tiles of the stage-1 point pass (<= kS1Tile observations)
     int ns1tiles = 0;
-    int* pt_pt = nullptr;            // P-order: point of each observation
     int2* chunk_meta = nullptr;      // camera chunks: (begin, nob)
     int nptiles = 0;
     bool tiled_ok = false;           // every track fits one tile
@@ -159,6 +158,8 @@ struct vlg_ba_ctx {
     // device: stage 1 (red1 = U | eA | cost | nvis contiguous for one all-reduce)
     double *red1 = nullptr, *U = nullptr, *eA = nullptr, *scal1 = nullptr;
     double *W = nullptr, *Upart = nullptr, *V = nullptr, *eB = nullptr, *cost_pt = nullptr, *red_part = nullptr;
+    double* BeP = nullptr;            // [nobs][8] P-order: B | e of every observation (stage 1: camera pass -> point pass)
+    int* obs_slot = nullptr;          // C-order position -> P-order slot (inverse of pt_obs)
     // device: stage 2
     double *Ud = nullptr, *Vinv = nullptr, *Spart = nullptr, *S = nullptr;
     double *chol_R = nullptr, *chol_Ld = nullptr, *chol_Dinv = nullptr;
@@ -562,7 +563,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     // optional buffers: which of them exist depends on the solver path of THIS problem
     ctx->init_part = nullptr; ctx->init_bar = nullptr; ctx->persist_bar = nullptr; ctx->init_coop_cap = -1; ctx->S_zeroed = false; ctx->s_split = false;
     ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr; ctx->Mc2 = nullptr;
-    ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr; ctx->pt_pt = nullptr;
+    ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr;
     ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
     ctx->symv_tiles = nullptr; ctx->symv_tile_ptr = nullptr; ctx->symv_rowpart = nullptr; ctx->symv_colpart = nullptr;
     ctx->chol_R = nullptr; ctx->chol_Ld = nullptr; ctx->chol_Dinv = nullptr; ctx->chol_bar = nullptr;
@@ -587,7 +588,6 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
 
     // CSR by camera and by point
     std::vector<int> cam_ptr(m + 1, 0), pt_ptr(n + 1, 0), pt_obs(nobs), pt_cam(nobs);
-    std::vector<double> pt_xy(2 * (size_t)nobs);
     for (int64_t t = 0; t < nobs; t++) { cam_ptr[obs_cam[t] + 1]++; pt_ptr[obs_pt[t] + 1]++; }
     for (int j = 0; j < m; j++) cam_ptr[j + 1] += cam_ptr[j];
     for (int i = 0; i < n; i++) pt_ptr[i + 1] += pt_ptr[i];
@@ -596,7 +596,6 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         for (int64_t t = 0; t < nobs; t++) {
             const int q = fill[obs_pt[t]]++;
             pt_obs[q] = (int)t; pt_cam[q] = obs_cam[t];
-            pt_xy[2 * (size_t)q] = obs_xy[2 * t]; pt_xy[2 * (size_t)q + 1] = obs_xy[2 * t + 1];
         }
     }
     // chunks of the camera segments
@@ -758,7 +757,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
 
     const int NU = nu_of(na);
     // ---- device allocations
-    CHK(dalloc(ctx, &ctx->obs_xy, (size_t)nobs)); CHK(dalloc(ctx, &ctx->pt_xy, (size_t)nobs));
+    CHK(dalloc(ctx, &ctx->obs_xy, (size_t)nobs));
     CHK(dalloc(ctx, &ctx->obs_pt, (size_t)nobs)); CHK(dalloc(ctx, &ctx->obs_cam, (size_t)nobs));
     CHK(dalloc(ctx, &ctx->cam_ptr, (size_t)m + 1)); CHK(dalloc(ctx, &ctx->pt_ptr, (size_t)n + 1));
     CHK(dalloc(ctx, &ctx->pt_obs, (size_t)nobs)); CHK(dalloc(ctx, &ctx->pt_cam, (size_t)nobs));
@@ -771,6 +770,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(dalloc(ctx, &ctx->red1, (size_t)na * N + N + 2));
     ctx->U = ctx->red1; ctx->eA = ctx->red1 + (size_t)na * N; ctx->scal1 = ctx->eA + N;
     CHK(dalloc(ctx, &ctx->W, (size_t)3 * na * nobs)); CHK(dalloc(ctx, &ctx->Upart, (size_t)NU * ctx->nchunks));
+    CHK(dalloc(ctx, &ctx->BeP, (size_t)8 * nobs)); CHK(dalloc(ctx, &ctx->obs_slot, (size_t)nobs));
     CHK(dalloc(ctx, &ctx->V, (size_t)9 * n)); CHK(dalloc(ctx, &ctx->eB, (size_t)3 * n));
     CHK(dalloc(ctx, &ctx->cost_pt, (size_t)n)); CHK(dalloc(ctx, &ctx->red_part, (size_t)kRedBlocks));
     CHK(dalloc(ctx, &ctx->Ud, (size_t)na * N)); CHK(dalloc(ctx, &ctx->Vinv, (size_t)9 * n));
@@ -901,16 +901,17 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         }
     }
     CHK(upload(ctx, (double*)ctx->obs_xy, obs_xy, 2 * (size_t)nobs));
-    CHK(upload(ctx, (double*)ctx->pt_xy, pt_xy.data(), 2 * (size_t)nobs));
     CHK(upload(ctx, ctx->obs_pt, obs_pt, (size_t)nobs)); CHK(upload(ctx, ctx->obs_cam, obs_cam, (size_t)nobs));
     CHK(upload(ctx, ctx->cam_ptr, cam_ptr.data(), (size_t)m + 1)); CHK(upload(ctx, ctx->pt_ptr, pt_ptr.data(), (size_t)n + 1));
     CHK(upload(ctx, ctx->pt_obs, pt_obs.data(), (size_t)nobs)); CHK(upload(ctx, ctx->pt_cam, pt_cam.data(), (size_t)nobs));
+    {
+        std::vector<int> slot((size_t)nobs);
+        for (int64_t q = 0; q < nobs; q++) slot[(size_t)pt_obs[(size_t)q]] = (int)q;
+        CHK(upload(ctx, ctx->obs_slot, slot.data(), (size_t)nobs));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     if (ctx->ns1tiles > 0) {
-        std::vector<int> pt_pt((size_t)nobs);
-        for (int i = 0; i < n; i++)
-            for (int q = pt_ptr[i]; q < pt_ptr[i + 1]; q++) pt_pt[(size_t)q] = i;
-        CHK(dalloc(ctx, &ctx->pt_pt, (size_t)nobs)); CHK(dalloc(ctx, &ctx->s1tile_meta, s1tiles.size()));
-        CHK(upload(ctx, ctx->pt_pt, pt_pt.data(), (size_t)nobs));
+        CHK(dalloc(ctx, &ctx->s1tile_meta, s1tiles.size()));
         CHK(upload(ctx, ctx->s1tile_meta, s1tiles.data(), s1tiles.size()));
         CU(cudaStreamSynchronize(ctx->stream));
     }
@@ -964,7 +965,8 @@ int run_stage1(vlg_ba_ctx* ctx, double* diag_X, double* diag_A, double* diag_B, 
     p.chunk_cam = ctx->chunk_cam; p.chunk_begin = ctx->chunk_begin; p.chunk_end = ctx->chunk_end;
     p.K4 = ctx->K4; p.a = ctx->a; p.b = ctx->b; p.rtab = ctx->rtab; p.cam_fixed = ctx->cam_fixed;
     p.fix_structure = ctx->opt.fix_structure;
-    p.W = ctx->W; p.Upart = ctx->Upart;
+    p.ref_order = ctx->opt.order == VLG_BA_ORDER_REFERENCE ? 1 : 0;
+    p.obs_slot = ctx->obs_slot; p.W = ctx->W; p.BeP = ctx->BeP; p.Upart = ctx->Upart;
     p.dX_hat = diag_X; p.dA = diag_A; p.dB = diag_B; p.de = diag_e;
     const size_t smem = (size_t)kWarpsPerBlock * (36 + NA + 4 + 32 * NU + 32 * 3 * NA) * sizeof(double);
     if (ctx->nchunks > 0) {
@@ -984,13 +986,11 @@ int run_stage1(vlg_ba_ctx* ctx, double* diag_X, double* diag_A, double* diag_B, 
     if (ctx->n > 0) {
         TimedScope ts(ctx, T_STAGE1_PT);
         if (ctx->ns1tiles > 0)
-            k_stage1_pt_tiled<NA><<<ctx->ns1tiles, kS1Tile, 0, ctx->stream>>>(ctx->s1tile_meta, ctx->pt_ptr, ctx->pt_cam, ctx->pt_pt, ctx->pt_xy,
-                                                                           ctx->K4, ctx->a, ctx->b, ctx->rtab, ctx->opt.fix_structure,
-                                                                           ctx->V, ctx->eB, ctx->cost_pt);
+            k_stage1_pt_tiled<<<ctx->ns1tiles, kS1Tile, 0, ctx->stream>>>(ctx->s1tile_meta, ctx->pt_ptr, ctx->BeP, ctx->opt.fix_structure,
+                                                                       ctx->V, ctx->eB, ctx->cost_pt);
         else
-            k_stage1_pt<NA><<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->pt_ptr, ctx->pt_cam, ctx->pt_xy, ctx->K4, ctx->a,
-                                                                        ctx->b, ctx->rtab, ctx->opt.fix_structure, ctx->V, ctx->eB,
-                                                                        ctx->cost_pt);
+            k_stage1_pt<<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->pt_ptr, ctx->BeP, ctx->opt.fix_structure, ctx->V, ctx->eB,
+                                                                    ctx->cost_pt);
         ctx->launches++;
     }
     if (ctx->tiled_ok && ctx->nobs > 0 && !diag) {

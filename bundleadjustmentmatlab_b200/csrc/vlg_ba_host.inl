@@ -3,13 +3,6 @@
 
 namespace {
 
-__global__ void k_gather_xy(int64_t nobs, const int* __restrict__ pt_obs, const double2* __restrict__ obs_xy,
-                            double2* __restrict__ pt_xy)
-{
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nobs) pt_xy[q] = obs_xy[pt_obs[q]];
-}
-
 int* pcg_done_ptr(vlg_ba_ctx* ctx) { return (int*)((char*)ctx->pcg_sc + offsetof(PcgScalars, done)); }
 
 // all-reduce of the per-iteration PCG vector: peer-memory mailboxes when imported, NCCL otherwise
@@ -1142,8 +1135,6 @@ int vlg_ba_trial_step_host(vlg_ba_ctx* ctx, const double* a, const double* b, co
     CU(cudaSetDevice(ctx->device));
     if (obs_xy && ctx->nobs > 0) {
         CHK(upload(ctx, (double*)ctx->obs_xy, obs_xy, 2 * (size_t)ctx->nobs));
-        k_gather_xy<<<cdiv(ctx->nobs, 256), 256, 0, ctx->stream>>>(ctx->nobs, ctx->pt_obs, ctx->obs_xy, ctx->pt_xy);
-        ctx->launches++;
     }
     // new state without a host synchronisation: the caller's buffers stay untouched until this call returns, and the
     // rotation table is computed from the host copy of a while the observations are still on their way to the device
@@ -1196,6 +1187,27 @@ int vlg_ba_get_schur_structure(vlg_ba_ctx* ctx, int64_t* n_blocks, int32_t* blk_
     if (n_blocks) *n_blocks = ctx->nblocks;
     if (blk_j) memcpy(blk_j, ctx->h_blk_j.data(), sizeof(int32_t) * (size_t)ctx->nblocks);
     if (blk_k) memcpy(blk_k, ctx->h_blk_k.data(), sizeof(int32_t) * (size_t)ctx->nblocks);
+    return VLG_BA_OK;
+}
+
+int vlg_ba_selftest_quotients(int device, int64_t nsamples, uint64_t seed, int64_t* mismatches)
+{
+    vlg_ba_ctx* ctx = nullptr;
+    if (!mismatches || nsamples < 0) return fail(nullptr, VLG_BA_EINVAL, "selftest_quotients: bad arguments");
+    if (device >= 0) CU(cudaSetDevice(device));
+    unsigned long long* d_bad = nullptr;
+    CU(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    const int threads = 256, blocks = 148 * 8, per = (int)((nsamples + (int64_t)threads * blocks - 1) / ((int64_t)threads * blocks));
+    cudaError_t e = cudaMemset(d_bad, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        k_selftest_quotients<<<blocks, threads>>>((unsigned long long)seed, per, d_bad);
+        e = cudaGetLastError();
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d_bad, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return fail(nullptr, VLG_BA_ECUDA, "selftest_quotients: %s", cudaGetErrorString(e));
+    *mismatches = (int64_t)h;
     return VLG_BA_OK;
 }
 

@@ -251,6 +251,13 @@ int  vlg_ba_bundle_projective(const vlg_ba_opts *opts, int m, int n, const doubl
                               const double *x, const double *visible,
                               double *Pp_, double *Xp_, double *error_, int *n_error);
 
+/* Self-test of stage 1's quotients: the kernels share one correctly rounded reciprocal per denominator and finish every
+ * quotient with one exact remainder step (csrc/ba_math.cuh, "Quotients") instead of the reference's 34 independent
+ * divisions per observation (mex_bundle_1_XABeUVWeAeB.c:39-40, reproject_point.h:55-56).  Runs >= nsamples random
+ * quotients (generic operands, reprojection-like, forward-difference-like) both ways on `device` (-1: current) and
+ * counts results that differ bitwise from __ddiv_rn; 0 is the only acceptable answer. */
+int  vlg_ba_selftest_quotients(int device, int64_t nsamples, uint64_t seed, int64_t *mismatches);
+
 /* Introspection for tests and benches. */
 int  vlg_ba_get_schur_structure(vlg_ba_ctx *ctx, int64_t *n_blocks, int32_t *blk_j, int32_t *blk_k);
 int64_t vlg_ba_kernel_launches(const vlg_ba_ctx *ctx);

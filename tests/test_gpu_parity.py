@@ -174,6 +174,14 @@ def test_free_running_solve_vs_golden(name):
     assert Xe_.shape == g["Xe_"].shape and K_.shape == g["K_"].shape
 
 
+def test_fast_quotients_are_ieee_quotients():
+    """Stage 1 replaces the reference's 34 divisions per observation by 8 correctly rounded reciprocals and one exact
+    remainder step per quotient (ba_math.cuh).  That is only legitimate if every quotient is still the IEEE quotient:
+    1e9 random operand pairs (generic, reprojection-like, forward-difference-like) against __ddiv_rn, bitwise."""
+    for seed in (1, 2):
+        assert capi.selftest_quotients(10**9, seed=seed) == 0
+
+
 def test_medium_problem_vs_sparse_oracle():
     P = synth.make_problem(30, 3000, 13000, seed=4)
     a = np.vstack([P.w, P.Te]); b = P.Xe[:3].copy()
