@@ -389,7 +389,9 @@ __global__ void k_damp_U(int m, double lambda, const double* __restrict__ U, dou
     Ud[t] = (r % NA == r / NA) ? (1 + lambda) * u : u;
 }
 
-__global__ void k_vinv_damp(int n, double lambda, const double* __restrict__ V, double* __restrict__ Vinv)
+// VE (optional): per point V*^-1 | eB as one 96-byte record (three whole sectors) for the cooperative gathers of ba_schur.cuh
+__global__ void k_vinv_damp(int n, double lambda, const double* __restrict__ V, double* __restrict__ Vinv,
+                            const double* __restrict__ eB = nullptr, double* __restrict__ VE = nullptr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -400,6 +402,12 @@ __global__ void k_vinv_damp(int n, double lambda, const double* __restrict__ V, 
     sym_pinv<3>(Vd, Vi);
 #pragma unroll
     for (int k = 0; k < 9; k++) Vinv[(size_t)9 * i + k] = Vi[k];
+    if (VE) {
+        double2* r = reinterpret_cast<double2*>(VE + (size_t)12 * i);
+        r[0] = make_double2(Vi[0], Vi[1]); r[1] = make_double2(Vi[2], Vi[3]); r[2] = make_double2(Vi[4], Vi[5]);
+        r[3] = make_double2(Vi[6], Vi[7]); r[4] = make_double2(Vi[8], eB[(size_t)3 * i]);
+        r[5] = make_double2(eB[(size_t)3 * i + 1], eB[(size_t)3 * i + 2]);
+    }
 }
 
 // An observation's NW-double block in global memory <-> registers; 16-byte accesses when NW is even

@@ -8,6 +8,7 @@
 #include "ba_kernels.cuh"
 #include "ba_chol.cuh"
 #include "ba_pcg.cuh"
+#include "ba_schur.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -139,6 +140,12 @@ struct vlg_ba_ctx {
     int2* pairs = nullptr;
     int *blk_heavy = nullptr, *blk_light = nullptr;   // S-assembly work lists: blocks with many / few pairs
     int nheavy = 0, nlight = 0;
+    // chunk kernel of ba_schur.cuh (num_a = 6, chunked order): per-point records, segments of the heavy blocks
+    bool schur_chunk_ok = false;
+    double *VE = nullptr, *Hpart = nullptr;
+    int *chunk_seg_ptr = nullptr, *sblk = nullptr, *sblk_hptr = nullptr;
+    int4* segs = nullptr;
+    int nsblk = 0, nsegs = 0;
     double* Ybuf = nullptr;                           // Y = W V*^-1 per observation (C-order), explicit-S paths
     double* red2_local = nullptr;                     // this rank's per-camera Schur sums before the all-reduce
     int4* ptile_meta = nullptr;      // point tiles of the PCG point sweep: (q0, nob, p0, npts)
@@ -565,6 +572,8 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     ctx->S = nullptr; ctx->Ybuf = nullptr; ctx->red2_local = nullptr; ctx->Cblk = nullptr; ctx->McL = nullptr; ctx->Mc2 = nullptr;
     ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr;
     ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
+    ctx->schur_chunk_ok = false; ctx->VE = nullptr; ctx->Hpart = nullptr; ctx->chunk_seg_ptr = nullptr; ctx->sblk = nullptr;
+    ctx->sblk_hptr = nullptr; ctx->segs = nullptr; ctx->nsblk = 0; ctx->nsegs = 0;
     ctx->symv_tiles = nullptr; ctx->symv_tile_ptr = nullptr; ctx->symv_rowpart = nullptr; ctx->symv_colpart = nullptr;
     ctx->chol_R = nullptr; ctx->chol_Ld = nullptr; ctx->chol_Dinv = nullptr; ctx->chol_bar = nullptr;
     CU(cudaSetDevice(ctx->device));
@@ -616,6 +625,10 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         cam_chunk_ptr[j + 1] = (int)chunk_cam.size();
     }
     ctx->nchunks = (int)chunk_cam.size();
+    {
+        const char* e = getenv("VLG_BA_SCHUR_CHUNK");      // 0: the round-1 kernels (camera pass + pair lists for every block)
+        ctx->schur_chunk_ok = na == 6 && cs <= kSchurTile && o.order != VLG_BA_ORDER_REFERENCE && (e ? atoi(e) != 0 : true);
+    }
 
     std::vector<unsigned char> fixed(m, 0);
     for (int j = 0; j < m; j++) fixed[j] = (o.fix_motion || (pivot && pivot[j] != 0.0)) ? 1 : 0;
@@ -774,6 +787,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(dalloc(ctx, &ctx->V, (size_t)9 * n)); CHK(dalloc(ctx, &ctx->eB, (size_t)3 * n));
     CHK(dalloc(ctx, &ctx->cost_pt, (size_t)n)); CHK(dalloc(ctx, &ctx->red_part, (size_t)kRedBlocks));
     CHK(dalloc(ctx, &ctx->Ud, (size_t)na * N)); CHK(dalloc(ctx, &ctx->Vinv, (size_t)9 * n));
+    if (ctx->schur_chunk_ok) CHK(dalloc(ctx, &ctx->VE, (size_t)kVE * n));
     CHK(dalloc(ctx, &ctx->Spart, (size_t)NU * ctx->nchunks));
     CHK(dalloc(ctx, &ctx->red2, (size_t)NU * m));
     CHK(dalloc(ctx, &ctx->Sjj, (size_t)na * N)); CHK(dalloc(ctx, &ctx->ebar, N));
@@ -887,11 +901,89 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         CHK(upload(ctx, ctx->blk_ptr, blk_ptr.data(), (size_t)ctx->nblocks + 1));
         CHK(upload(ctx, ctx->pairs, pairs.data(), (size_t)ctx->npairs));
         {
-            std::vector<int> heavy, light;
-            // diagonal blocks are not on these lists: k_cam_schur_diag already sums them (k_schur_diag_fill)
-            for (int64_t bb = 0; bb < ctx->nblocks; bb++)
-                if (ctx->h_blk_j[(size_t)bb] != ctx->h_blk_k[(size_t)bb])
-                    (blk_ptr[bb + 1] - blk_ptr[bb] > kSchurHeavy ? heavy : light).push_back((int)bb);
+            std::vector<int> heavy, light, sblk, sblk_hptr(1, 0);
+            struct SegH { int chunk, blk, q0, q1, slot; };
+            std::vector<SegH> segh;
+            // diagonal blocks are not on these lists: the camera pass already sums them (k_schur_diag_fill).  Blocks with very
+            // many pairs go to the chunk kernel (ba_schur.cuh): cut into (block, chunk of camera j) segments -- a camera's
+            // observations ascend in the point index, and so do a block's pairs, hence a segment is a contiguous pair range
+            int64_t seg_heavy = kSegHeavy;
+            { const char* e = getenv("VLG_BA_SEG_HEAVY"); if (e) seg_heavy = atoll(e); }       // experiments: threshold of the chunk kernel's blocks
+            for (int64_t bb = 0; bb < ctx->nblocks; bb++) {
+                const int j = ctx->h_blk_j[(size_t)bb];
+                if (j == ctx->h_blk_k[(size_t)bb]) continue;
+                const int64_t np_b = blk_ptr[bb + 1] - blk_ptr[bb];
+                if (ctx->schur_chunk_ok && np_b > seg_heavy && pairs.size() < ((size_t)1 << 31)) {
+                    int cur = -1;
+                    for (int64_t q = blk_ptr[bb]; q < blk_ptr[bb + 1]; q++) {
+                        const int ch = cam_chunk_ptr[j] + (pairs[(size_t)q].x - cam_ptr[j]) / cs;
+                        if (ch != cur) {
+                            if (cur >= 0) segh.back().q1 = (int)q;
+                            segh.push_back({ch, (int)bb, (int)q, (int)q, (int)segh.size()});
+                            cur = ch;
+                        }
+                    }
+                    segh.back().q1 = (int)blk_ptr[bb + 1];
+                    sblk.push_back((int)bb);
+                    sblk_hptr.push_back((int)segh.size());
+                } else {
+                    (np_b > kSchurHeavy ? heavy : light).push_back((int)bb);
+                }
+            }
+            if (ctx->schur_chunk_ok) {
+                // segments grouped by chunk (counting sort; inside a chunk in block order), cut into ROUNDS of <= 32 pairs; warp
+                // w of the chunk's CTA takes the rounds [nr w / 8, nr (w + 1) / 8) of the chunk, so a segment that straddles
+                // two warps leaves one partial per warp ("piece").  Partial slots are numbered block-major, then chunk, then
+                // piece: k_schur_fold adds a block's slots in that order.
+                const int nseg = (int)segh.size();
+                std::vector<int> cptr((size_t)ctx->nchunks + 1, 0), crounds((size_t)ctx->nchunks + 1, 0);
+                for (const SegH& g : segh) { cptr[(size_t)g.chunk + 1]++; crounds[(size_t)g.chunk + 1] += (g.q1 - g.q0 + 31) / 32; }
+                for (int c = 0; c < ctx->nchunks; c++) { cptr[(size_t)c + 1] += cptr[(size_t)c]; crounds[(size_t)c + 1] += crounds[(size_t)c]; }
+                std::vector<int> fill(cptr.begin(), cptr.end() - 1), order((size_t)nseg);
+                for (int g = 0; g < nseg; g++) order[(size_t)fill[(size_t)segh[(size_t)g].chunk]++] = g;
+                // a chunk's segments are dealt to the 8 warps of its CTA, longest first to the least loaded warp; a warp's
+                // rounds are contiguous in `rounds`, a segment never straddles two warps (one partial per segment)
+                std::vector<int> slot_base((size_t)nseg + 1, 0);
+                for (int g = 0; g < nseg; g++) slot_base[(size_t)g + 1] = slot_base[(size_t)g] + 1;
+                for (size_t t = 0; t < sblk_hptr.size(); t++) sblk_hptr[t] = slot_base[(size_t)sblk_hptr[t]];      // segment index -> slot index
+                std::vector<int4> rounds((size_t)crounds.back());
+                std::vector<int> wptr((size_t)kSchurWarps * ctx->nchunks + 1, 0);
+                {
+                    std::vector<int> segs_c, load(kSchurWarps);
+                    std::vector<std::vector<int>> mine(kSchurWarps);
+                    int pos = 0;
+                    for (int c = 0; c < ctx->nchunks; c++) {
+                        segs_c.assign(order.begin() + cptr[(size_t)c], order.begin() + cptr[(size_t)c + 1]);
+                        auto nrounds = [&](int g) { return (segh[(size_t)g].q1 - segh[(size_t)g].q0 + 31) / 32; };
+                        std::stable_sort(segs_c.begin(), segs_c.end(), [&](int x, int y) { return nrounds(x) > nrounds(y); });
+                        std::fill(load.begin(), load.end(), 0);
+                        for (auto& v : mine) v.clear();
+                        for (int g : segs_c) {
+                            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                            load[(size_t)w] += nrounds(g) + 1;        // + the flush
+                            mine[(size_t)w].push_back(g);
+                        }
+                        for (int w = 0; w < kSchurWarps; w++) {
+                            wptr[(size_t)kSchurWarps * c + w] = pos;
+                            for (int g : mine[(size_t)w]) {
+                                const SegH& sg = segh[(size_t)g];
+                                const int n = nrounds(g);
+                                for (int t = 0; t < n; t++)
+                                    rounds[(size_t)pos++] = make_int4(sg.q0 + 32 * t, std::min(32, sg.q1 - (sg.q0 + 32 * t)), slot_base[(size_t)g], t + 1 == n ? 1 : 0);
+                            }
+                        }
+                    }
+                    wptr.back() = pos;
+                }
+                const std::vector<int>& crounds_up = wptr;
+                ctx->nsblk = (int)sblk.size(); ctx->nsegs = (int)rounds.size();
+                CHK(dalloc(ctx, &ctx->chunk_seg_ptr, crounds_up.size())); CHK(dalloc(ctx, &ctx->segs, rounds.size()));
+                CHK(dalloc(ctx, &ctx->sblk, sblk.size())); CHK(dalloc(ctx, &ctx->sblk_hptr, sblk_hptr.size()));
+                CHK(dalloc(ctx, &ctx->Hpart, (size_t)slot_base.back() * (size_t)na * na));
+                CHK(upload(ctx, ctx->chunk_seg_ptr, crounds_up.data(), crounds_up.size())); CHK(upload(ctx, ctx->segs, rounds.data(), rounds.size()));
+                CHK(upload(ctx, ctx->sblk, sblk.data(), sblk.size())); CHK(upload(ctx, ctx->sblk_hptr, sblk_hptr.data(), sblk_hptr.size()));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
             ctx->nheavy = (int)heavy.size(); ctx->nlight = (int)light.size();
             CHK(dalloc(ctx, &ctx->blk_heavy, heavy.size())); CHK(dalloc(ctx, &ctx->blk_light, light.size()));
             CHK(upload(ctx, ctx->blk_heavy, heavy.data(), heavy.size())); CHK(upload(ctx, ctx->blk_light, light.data(), light.size()));

@@ -23,6 +23,12 @@ int assemble_S(vlg_ba_ctx* ctx, int add_U, double* S, int ccams = 0)
 {
     k_schur_diag_fill<NA><<<cdiv((int64_t)ctx->m * NA * NA, 256), 256, 0, ctx->stream>>>(ctx->m, ctx->Np, ccams, add_U, ctx->red2_local, ctx->Ud, S);
     ctx->launches++;
+    if (ctx->nsblk > 0) {
+        // the heavy blocks: their (block, chunk) partials were left by k_schur_chunk in this LM step's camera pass
+        k_schur_fold<NA><<<cdiv(ctx->nsblk, 4), 128, 0, ctx->stream>>>(ctx->nsblk, ctx->sblk, ctx->sblk_hptr, ctx->Np, ccams, ctx->blk_j, ctx->blk_k,
+                                                                      ctx->Hpart, S);
+        ctx->launches++;
+    }
     if (ctx->nheavy > 0) {
         k_schur_blocks_heavy<NA><<<cdiv(ctx->nheavy, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
             ctx->nheavy, ctx->blk_heavy, ctx->Np, ccams, add_U, ctx->blk_j, ctx->blk_k, ctx->blk_ptr, ctx->pairs, ctx->Ybuf, ctx->W, ctx->Ud, S);
@@ -65,13 +71,22 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
         k_damp_U<NA><<<cdiv((int64_t)m * NA * NA, 256), 256, 0, ctx->stream>>>(m, lambda, ctx->U, ctx->Ud);
         ctx->launches++;
         if (n > 0) {
-            k_vinv_damp<<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, lambda, ctx->V, ctx->Vinv);
+            k_vinv_damp<<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, lambda, ctx->V, ctx->Vinv, ctx->eB, ctx->VE);
             ctx->launches++;
         }
     }
     {
         TimedScope ts(ctx, T_SCHUR);
-        if (ctx->nchunks > 0) {
+        if (ctx->nchunks > 0 && ctx->schur_chunk_ok) {
+            if constexpr (NA == 6) {
+                SchurChunkArgs sa;
+                sa.chunk_meta = ctx->chunk_meta; sa.obs_pt = ctx->obs_pt; sa.W = ctx->W; sa.VE = ctx->VE; sa.part = ctx->Spart; sa.Yout = ctx->Ybuf;
+                sa.chunk_round_ptr = ctx->nsegs > 0 ? ctx->chunk_seg_ptr : nullptr; sa.rounds = ctx->segs; sa.pairs = ctx->pairs; sa.Hpart = ctx->Hpart;
+                CU(cudaFuncSetAttribute(k_schur_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurChunkSmem));
+                k_schur_chunk<<<ctx->nchunks, kSchurTile, kSchurChunkSmem, ctx->stream>>>(sa);
+                ctx->launches++;
+            }
+        } else if (ctx->nchunks > 0) {
             k_cam_schur_diag<NA><<<cdiv(ctx->nchunks, kWarpsPerBlock), kWarpsPerBlock * 32, 0, ctx->stream>>>(
                 ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->eB, ctx->Spart, ctx->Ybuf);
             ctx->launches++;
