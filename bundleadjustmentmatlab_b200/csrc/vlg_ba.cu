@@ -637,9 +637,23 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     ctx->Np = (int)((N + kNB - 1) / kNB * kNB);
     {
         // explicit-S PCG: one iteration streams the lower triangle (4 Np^2 bytes) instead of W twice
-        // (2 x (24 na + 8) bytes per observation); assembling S costs about a dozen sweeps
+        // (2 x (24 na + 8) bytes per observation); assembling S costs about a dozen sweeps.  Every rank multiplies 1/nranks
+        // of S and sweeps its own shard of W, so the rule compares the WHOLE problem's figures -- and it must: the choice of
+        // solver is collective (ranks on different paths would wait for each other's exchanges forever), so it may only
+        // depend on quantities that are identical on every rank
+        double nobs_all = (double)nobs;
+        if (ctx->nranks > 1) {
+            double* d_cnt = nullptr;
+            CU(cudaMalloc(&d_cnt, sizeof(double)));
+            int rc = upload(ctx, d_cnt, &nobs_all, 1);
+            if (rc == VLG_BA_OK) rc = allreduce(ctx, d_cnt, 1);
+            if (rc == VLG_BA_OK) rc = download(ctx, &nobs_all, d_cnt, 1);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_cnt);
+            CHK(rc);
+        }
         const double s_bytes = 8.0 * (double)ctx->Np * (double)ctx->Np;
-        const bool pays = 0.75 * s_bytes < 2.0 * (24.0 * na + 8.0) * (double)nobs && s_bytes <= 8e9 && (int64_t)m * m <= ((int64_t)1 << 28);
+        const bool pays = 0.75 * s_bytes < 2.0 * (24.0 * na + 8.0) * nobs_all && s_bytes <= 8e9 && (int64_t)m * m <= ((int64_t)1 << 28);
         ctx->use_explicit = !ctx->use_chol && (o.solver == VLG_BA_SOLVER_PCG_EXPLICIT || (o.solver == VLG_BA_SOLVER_AUTO && pays));
     }
     const bool need_S = ctx->use_chol || ctx->use_explicit;
@@ -852,7 +866,10 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         std::vector<vlg_ba_ctx::SymvTileH>& seq = ctx->h_symv_seq;
         int ncell = 0;
         symv_sequence(Np, ctx->s_J0, ctx->s_J1, seq, ctx->h_symv_cum, ncell);
-        const int G = std::max(1, std::min(ctx->nsm, (int)seq.size()));
+        // one CTA per SM at most; never fewer CTAs than preconditioner clusters (when those fit one per SM), even if this
+        // rank's column block has fewer tiles than that (surplus CTAs get an empty piece): whether the whole solve runs as the
+        // persistent kernel (coop_grid <= symv_grid, run_stage2) must come out the same on every rank
+        const int G = std::max(1, std::min(ctx->nsm, std::max((int)seq.size(), ctx->coop_grid)));
         ctx->symv_grid = G;
         ctx->symv_ncell = ncell;
         ctx->symv_speed.assign((size_t)G, 1.0);

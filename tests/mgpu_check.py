@@ -78,9 +78,19 @@ def main():
     c1.set_problem_sparse(P2.K.T, a2, b2, P2.obs_xy, P2.obs_pt, P2.obs_cam)
     ref2 = c1.trial_step()
     c1.close()
+    # ... and a problem so small (22 cameras: 5 strips of S, 2 preconditioner clusters) that some ranks' column blocks have
+    # fewer matvec tiles than there are clusters: the choice "whole solve as one persistent kernel" must still come out
+    # the same on every rank (round 2: ranks on different paths disagreed on the stop iteration in the last bit and waited
+    # for each other's exchanges forever)
+    P3 = synth.make_problem(22, 5000, 23000, seed=6)
+    a3 = np.ascontiguousarray(np.vstack([P3.w, P3.Te]).T); b3 = np.ascontiguousarray(P3.Xe[:3].T)
+    c1 = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG_EXPLICIT, pcg_rtol=1e-12, device=local)
+    c1.set_problem_sparse(P3.K.T, a3, b3, P3.obs_xy, P3.obs_pt, P3.obs_cam)
+    ref3 = c1.trial_step()
+    c1.close()
     ctx = capi.Context(num_variableK=0, solver=capi.SOLVER_PCG_EXPLICIT, pcg_rtol=1e-12, device=local)
     ctx.set_comm(rank, world, fresh_uid())
-    for (PP, aa, bb, want) in ((P, a, b, ref[capi.SOLVER_PCG_EXPLICIT][0][1]), (P2, a2, b2, ref2)):
+    for (PP, aa, bb, want) in ((P, a, b, ref[capi.SOLVER_PCG_EXPLICIT][0][1]), (P2, a2, b2, ref2), (P3, a3, b3, ref3)):
         xy, pt, cam, bl, _ = shard.shard_points(PP.obs_xy, PP.obs_pt, PP.obs_cam, bb, rank, world)
         ctx.set_problem_sparse(PP.K.T, aa, bl, xy, pt, cam)
         exchange_mailboxes(ctx)

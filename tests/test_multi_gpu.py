@@ -19,5 +19,5 @@ def test_ranks_match_one_gpu(world):
         pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", str(29611 + world), os.path.join(ROOT, "tests", "mgpu_check.py")],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
