@@ -61,7 +61,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan", "vlg_ba_selftest_quotients",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan", "vlg_ba_selftest_quotients", "vlg_ba_dense_release", "vlg_ba_dense_cache_stats",
 ]
 
 
@@ -321,6 +321,17 @@ class Context:
         ms, cnt = C.c_double(), C.c_int64()
         self._ck(self._L.vlg_ba_kernel_time(self._h, name.encode(), C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
+
+
+def dense_cache_stats():
+    """(re-uses, rebuilds) of the cached contexts behind vlg_ba_mex{1,2,3}_dense on this thread."""
+    h, b = C.c_int64(), C.c_int64()
+    lib().vlg_ba_dense_cache_stats(C.byref(h), C.byref(b))
+    return int(h.value), int(b.value)
+
+
+def dense_release():
+    lib().vlg_ba_dense_release()
 
 
 def selftest_quotients(nsamples: int = 10**9, seed: int = 1, device: int = -1) -> int:

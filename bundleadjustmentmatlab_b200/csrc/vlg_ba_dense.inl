@@ -1,9 +1,108 @@
 // vlg_ba_dense.inl -- included inside the extern "C" block of vlg_ba_host.inl.
 //
-// Stateless entry points with exactly the dense argument layout of the reference's three
-// mexFunctions, for the drop-in mex wrappers in mex/ (bundle_euclid.m then runs unmodified),
-// plus the whole of bundle_euclid.m behind one call.  Each compacts the dense n x m arrays to
-// the visible cells, runs the same CUDA kernels as the fused path, and scatters back.
+// Entry points with exactly the dense argument layout of the reference's three mexFunctions, for the
+// drop-in mex wrappers in mex/ (bundle_euclid.m then runs unmodified), plus the whole of
+// bundle_euclid.m behind one call.  Each compacts the dense n x m arrays to the visible cells, runs
+// the same CUDA kernels as the fused path, and scatters back.
+//
+// The three stage entries keep their contexts between calls (bundle_euclid.m calls mex1, mex2,
+// mex3 once per trial step on the same visibility pattern): one context for mex1/mex3 and one for mex2 per host
+// thread, re-used while (m, n, num_a) and the list of contributing cells stay the same -- then a call only uploads
+// its operands instead of creating a CUDA stream, compacting, building the CSR / block structure and cudaMalloc-ing
+// everything three times per trial step.  vlg_ba_dense_release() drops them (the mex wrappers register it with
+// mexAtExit and mexLock themselves); vlg_ba_dense_cache_stats() counts hits and rebuilds for the tests.
+
+}  // extern "C" (the cache helpers have C++ linkage)
+
+namespace {
+
+struct DenseSlot {
+    vlg_ba_ctx* ctx = nullptr;
+    int m = 0, n = 0, na = 0;      // no destructor: at process exit the CUDA runtime may be gone before thread-local storage is
+};
+thread_local DenseSlot g_dense13, g_dense2;
+thread_local int64_t g_dense_hits = 0, g_dense_builds = 0;
+
+void dense_drop(DenseSlot& s)
+{
+    if (s.ctx) vlg_ba_destroy(s.ctx);
+    s.ctx = nullptr;
+}
+
+// the context of a dense (K, a, b, X, visible) call: re-used when the visible cells are the same list as last time
+int dense_acquire13(int m, int n, int num_a, const double* K, const double* a, const double* b, const double* X,
+                    const double* visible, vlg_ba_ctx** out)
+{
+    *out = nullptr;
+    if (m <= 0 || n < 0 || !a || (n > 0 && (!b || !X || !visible))) return fail(nullptr, VLG_BA_EINVAL, "dense entry: NULL argument");
+    std::vector<double> xy;
+    std::vector<int32_t> pt, cam;
+    for (int j = 0; j < m; j++)
+        for (int i = 0; i < n; i++) {
+            const size_t c = (size_t)i + (size_t)n * j;
+            if (visible[c] != 0.0) {                               // mex_bundle_1_XABeUVWeAeB.c:196
+                xy.push_back(X[2 * c]); xy.push_back(X[2 * c + 1]);
+                pt.push_back(i); cam.push_back(j);
+            }
+        }
+    DenseSlot& s = g_dense13;
+    vlg_ba_ctx* ctx = s.ctx;
+    const bool proj = num_a == kNaProjective;
+    if (ctx && s.m == m && s.n == n && s.na == num_a && ctx->h_obs_pt == pt && ctx->h_obs_cam == cam) {
+        g_dense_hits++;
+        CU(cudaSetDevice(ctx->device));
+        ctx->h_obs_xy = xy;
+        CHK(upload(ctx, (double*)ctx->obs_xy, xy.data(), xy.size()));
+        if (!proj && K) { ctx->h_K.assign(K, K + 4 * (size_t)m); CHK(upload(ctx, ctx->K4, K, 4 * (size_t)m)); }
+        CHK(vlg_ba_set_state(ctx, a, b, -1.0, -1.0));               // synchronises: the host vectors above may go
+        *out = ctx;
+        return VLG_BA_OK;
+    }
+    dense_drop(s);
+    g_dense_builds++;
+    vlg_ba_opts o;
+    vlg_ba_opts_default(&o);
+    // num_a = 12 (and K = NULL) is the projective model: mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible)
+    if (proj) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
+    o.order = VLG_BA_ORDER_REFERENCE;            // U, eA in the reference's exact accumulation order
+    o.solver = VLG_BA_SOLVER_PCG;                // no block structure needed for stage 1 / stage 3
+    o.pcg_cluster = 0;
+    int r = vlg_ba_create(&o, &ctx);
+    if (r != VLG_BA_OK) return r;
+    r = build_problem(ctx, m, n, K, a, b, (int64_t)pt.size(), xy.data(), pt.data(), cam.data(), nullptr);
+    if (r != VLG_BA_OK) {
+        snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err);
+        vlg_ba_destroy(ctx);
+        return r;
+    }
+    s.ctx = ctx; s.m = m; s.n = n; s.na = num_a;
+    *out = ctx;
+    return VLG_BA_OK;
+}
+
+// a failed call leaves nothing cached (the context may be in an undefined state)
+int dense_fail13(vlg_ba_ctx* ctx, int r)
+{
+    if (ctx) snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err);
+    dense_drop(g_dense13);
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+void vlg_ba_dense_release(void)
+{
+    dense_drop(g_dense13);
+    dense_drop(g_dense2);
+}
+
+void vlg_ba_dense_cache_stats(int64_t* hits, int64_t* builds)
+{
+    if (hits) *hits = g_dense_hits;
+    if (builds) *builds = g_dense_builds;
+}
 
 // mex_bundle_1_XABeUVWeAeB(K, a, b, X, visible) -> X_hat A B e U V W eA eB
 // (mex_bundle_1_XABeUVWeAeB.c:72-337; outputs may be NULL).
@@ -11,17 +110,10 @@ int vlg_ba_mex1_dense(int m, int n, int num_a, const double* K, const double* a,
                       const double* visible, double* X_hat, double* A, double* B, double* e, double* U, double* V,
                       double* W, double* eA, double* eB)
 {
-    vlg_ba_opts o;
-    vlg_ba_opts_default(&o);
-    // num_a = 12 (and K = NULL) is the projective model: mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible)
-    if (num_a == kNaProjective) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
-    o.order = VLG_BA_ORDER_REFERENCE;            // U, eA in the reference's exact accumulation order
-    o.solver = VLG_BA_SOLVER_PCG;                // no block structure needed for stage 1
     vlg_ba_ctx* ctx = nullptr;
-    int r = vlg_ba_create(&o, &ctx);
+    int r = dense_acquire13(m, n, num_a, K, a, b, X, visible, &ctx);
     if (r != VLG_BA_OK) return r;
-    r = vlg_ba_set_problem_dense(ctx, m, n, K, a, b, X, visible, nullptr);
-    const size_t no = r == VLG_BA_OK ? (size_t)ctx->nobs : 0, na = (size_t)num_a, nm = (size_t)n * m;
+    const size_t no = (size_t)ctx->nobs, na = (size_t)num_a, nm = (size_t)n * m;
     std::vector<double> sX(2 * no), sA(2 * na * no), sB(6 * no), se(2 * no), sW(3 * na * no);
     if (r == VLG_BA_OK) r = vlg_ba_get_jacobians(ctx, sX.data(), sA.data(), sB.data(), se.data());
     if (r == VLG_BA_OK) r = vlg_ba_stage1(ctx, nullptr);
@@ -42,9 +134,8 @@ int vlg_ba_mex1_dense(int m, int n, int num_a, const double* K, const double* a,
             if (W) memcpy(W + 3 * na * c, sW.data() + 3 * na * t, sizeof(double) * 3 * na);
         }
     } else {
-        snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err);
+        return dense_fail13(ctx, r);
     }
-    vlg_ba_destroy(ctx);
     return r;
 }
 
@@ -68,15 +159,25 @@ int vlg_ba_mex2_dense(int m, int n, int num_a, const double* Y, const double* W,
             }
         }
     const size_t no = pt.size();
-    vlg_ba_opts o;
-    vlg_ba_opts_default(&o);
-    if (num_a == kNaProjective) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
-    o.solver = VLG_BA_SOLVER_CHOL;               // builds the block structure of S
-    vlg_ba_ctx* ctx = nullptr;
-    int r = vlg_ba_create(&o, &ctx);
-    if (r != VLG_BA_OK) return r;
-    std::vector<double> K1(4 * (size_t)m, 1.0), a0(na * m, 0.0), b0(3 * (size_t)std::max(n, 1), 0.0), xy(2 * std::max<size_t>(no, 1), 0.0);
-    r = vlg_ba_set_problem_sparse(ctx, m, n, K1.data(), a0.data(), b0.data(), (int64_t)no, xy.data(), pt.data(), cam.data(), nullptr);
+    DenseSlot& slot = g_dense2;
+    vlg_ba_ctx* ctx = slot.ctx;
+    int r = VLG_BA_OK;
+    if (ctx && slot.m == m && slot.n == n && slot.na == num_a && ctx->h_obs_pt == pt && ctx->h_obs_cam == cam) {
+        g_dense_hits++;                          // same contributing cells as last time: the block structure of S stands
+    } else {
+        dense_drop(slot);
+        g_dense_builds++;
+        vlg_ba_opts o;
+        vlg_ba_opts_default(&o);
+        if (num_a == kNaProjective) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
+        o.solver = VLG_BA_SOLVER_CHOL;           // builds the block structure of S
+        r = vlg_ba_create(&o, &ctx);
+        if (r != VLG_BA_OK) return r;
+        std::vector<double> K1(4 * (size_t)m, 1.0), a0(na * m, 0.0), b0(3 * (size_t)std::max(n, 1), 0.0), xy(2 * std::max<size_t>(no, 1), 0.0);
+        r = vlg_ba_set_problem_sparse(ctx, m, n, K1.data(), a0.data(), b0.data(), (int64_t)no, xy.data(), pt.data(), cam.data(), nullptr);
+        if (r != VLG_BA_OK) { snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err); vlg_ba_destroy(ctx); return r; }
+        slot.ctx = ctx; slot.m = m; slot.n = n; slot.na = num_a;
+    }
     double* dY = nullptr;
     const int N = num_a * m;
     auto body = [&]() -> int {
@@ -108,8 +209,7 @@ int vlg_ba_mex2_dense(int m, int n, int num_a, const double* Y, const double* W,
     };
     if (r == VLG_BA_OK) r = body();
     if (dY) cudaFree(dY);
-    if (r != VLG_BA_OK) snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err);
-    vlg_ba_destroy(ctx);
+    if (r != VLG_BA_OK) { snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err); dense_drop(slot); }
     return r;
 }
 
@@ -119,15 +219,10 @@ int vlg_ba_mex3_dense(int m, int n, int num_a, const double* W, const double* da
                       const double* K, const double* a, const double* b, const double* X, const double* visible,
                       double* db, double* a_new, double* b_new, double* X_hat)
 {
-    vlg_ba_opts o;
-    vlg_ba_opts_default(&o);
     // num_a = 12 (and K = NULL): mex_bundle_proj_3_db_new(W, da, eB, V_inv, a, b, X, visible)
-    if (num_a == kNaProjective) o.model = VLG_BA_MODEL_PROJECTIVE; else o.num_variableK = num_a - 6;
-    o.solver = VLG_BA_SOLVER_PCG;
     vlg_ba_ctx* ctx = nullptr;
-    int r = vlg_ba_create(&o, &ctx);
+    int r = dense_acquire13(m, n, num_a, K, a, b, X, visible, &ctx);
     if (r != VLG_BA_OK) return r;
-    r = vlg_ba_set_problem_dense(ctx, m, n, K, a, b, X, visible, nullptr);
     const size_t na = (size_t)num_a, nw = 3 * na, nm = (size_t)n * m;
     double* dXh = nullptr;
     auto body = [&]() -> int {
@@ -162,9 +257,10 @@ int vlg_ba_mex3_dense(int m, int n, int num_a, const double* W, const double* da
         return VLG_BA_OK;
     };
     if (r == VLG_BA_OK) r = body();
+    ctx->xhat_out = nullptr;
     if (dXh) cudaFree(dXh);
-    if (r != VLG_BA_OK) snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err);
-    vlg_ba_destroy(ctx);
+    if (r != VLG_BA_OK) return dense_fail13(ctx, r);
+    ctx->s1_valid = ctx->s2_valid = ctx->s3_valid = false;      // the stage flags were forced for this call only
     return r;
 }
 

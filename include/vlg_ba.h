@@ -206,8 +206,11 @@ int  vlg_ba_trial_step_host(vlg_ba_ctx *ctx, const double *a, const double *b,
                             double *a_new, double *b_new, vlg_ba_trial_info *info);
 
 /* ---- dense drop-ins: the exact argument layout of the reference's three mexFunctions -------
- * Stateless (context created and destroyed inside); used by mex/mex_bundle_*.c so that the
- * reference's bundle_euclid.m runs unmodified on the GPU.  Output pointers may be NULL.
+ * Used by mex/mex_bundle_*.c so that the reference's bundle_euclid.m runs unmodified on the GPU.  Output pointers may be
+ * NULL.  The three stage entries keep one context for mex1/mex3 and one for mex2 per host thread and re-use them while
+ * (m, n, num_a) and the list of contributing cells stay the same (bundle_euclid.m:139,192,204 calls them once per
+ * trial step on one visibility pattern); vlg_ba_dense_release() frees them (the mex wrappers register it with mexAtExit),
+ * vlg_ba_dense_cache_stats() reports re-uses and rebuilds.
  *   mex1: [X_hat A B e U V W eA eB] = mex_bundle_1_XABeUVWeAeB(K, a, b, X, visible)
  *         (mex_bundle_1_XABeUVWeAeB.c:76-83 inputs, :136-175 outputs)
  *   mex2: [S e_] = mex_bundle_2_Se_(Y, W, U_, eA, eB)          (mex_bundle_2_Se_.c:21-27,:59-66)
@@ -226,6 +229,8 @@ int  vlg_ba_mex3_dense(int m, int n, int num_a, const double *W, const double *d
                        const double *Vinv, const double *K, const double *a, const double *b,
                        const double *X, const double *visible, double *db, double *a_new,
                        double *b_new, double *X_hat);
+void vlg_ba_dense_release(void);
+void vlg_ba_dense_cache_stats(int64_t *hits, int64_t *builds);
 /* [K_ Te_ w_ Xe_ error_] = bundle_euclid(K, Te, w, Xe, x, ...) (bundle_euclid.m:1-269) in one
  * call: K 4xm, Te 3xm, w 3xm, Xe 4xn, x 3xnxm, visible nxm or NULL (derive from x,
  * bundle_euclid.m:50), pivot m or NULL; error_ holds max_iter doubles. */

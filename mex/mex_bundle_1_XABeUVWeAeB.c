@@ -12,12 +12,14 @@
  */
 #include "mex.h"
 #include "vlg_ba.h"
+#include "vlg_mex_state.h"
 
 void mexFunction(int nout, mxArray *pout[], int nin, const mxArray *pin[])
 {
     mwSize dX[3], dA[4], dB[4], dU[3], dV[3], dW[4];
     int m, n, num_a, rc;
     (void)nout;
+    vlg_mex_keep_state();
     if (nin != 5) mexErrMsgIdAndTxt("vlg:mex1:nargin", "mex_bundle_1_XABeUVWeAeB(K, a, b, X, visible): 5 inputs required");
     m = (int)mxGetN(pin[1]);
     n = (int)mxGetN(pin[2]);

@@ -10,12 +10,14 @@
  */
 #include "mex.h"
 #include "vlg_ba.h"
+#include "vlg_mex_state.h"
 
 void mexFunction(int nout, mxArray *pout[], int nin, const mxArray *pin[])
 {
     mwSize dX[3];
     int m, n, num_a, rc;
     (void)nout;
+    vlg_mex_keep_state();
     if (nin != 9) mexErrMsgIdAndTxt("vlg:mex3:nargin", "mex_bundle_3_db_new(W, da, eB, V_inv, K, a, b, X, visible): 9 inputs required");
     m = (int)mxGetN(pin[5]);
     n = (int)mxGetN(pin[6]);

@@ -10,6 +10,7 @@
  */
 #include "mex.h"
 #include "vlg_ba.h"
+#include "vlg_mex_state.h"
 
 void mexFunction(int nout, mxArray *pout[], int nin, const mxArray *pin[])
 {
@@ -17,6 +18,7 @@ void mexFunction(int nout, mxArray *pout[], int nin, const mxArray *pin[])
     const int num_a = 12;
     int m, n, rc;
     (void)nout;
+    vlg_mex_keep_state();
     if (nin != 4) mexErrMsgIdAndTxt("vlg:pmex1:nargin", "mex_bundle_proj_1_XABeUVWeAeB(a, b, X, visible): 4 inputs required");
     m = (int)mxGetN(pin[0]);
     n = (int)mxGetN(pin[1]);

@@ -7,12 +7,14 @@
  */
 #include "mex.h"
 #include "vlg_ba.h"
+#include "vlg_mex_state.h"
 
 void mexFunction(int nout, mxArray *pout[], int nin, const mxArray *pin[])
 {
     const int num_a = 12;
     int m, n, rc;
     (void)nout;
+    vlg_mex_keep_state();
     if (nin != 5) mexErrMsgIdAndTxt("vlg:pmex2:nargin", "mex_bundle_proj_2_Se_(Y, W, U_, eA, eB): 5 inputs required");
     m = (int)mxGetN(pin[3]);
     n = (int)mxGetN(pin[4]);

@@ -8,6 +8,7 @@
  */
 #include "mex.h"
 #include "vlg_ba.h"
+#include "vlg_mex_state.h"
 
 void mexFunction(int nout, mxArray *pout[], int nin, const mxArray *pin[])
 {
@@ -15,6 +16,7 @@ void mexFunction(int nout, mxArray *pout[], int nin, const mxArray *pin[])
     const int num_a = 12;
     int m, n, rc;
     (void)nout;
+    vlg_mex_keep_state();
     if (nin != 8) mexErrMsgIdAndTxt("vlg:pmex3:nargin", "mex_bundle_proj_3_db_new(W, da, eB, V_inv, a, b, X, visible): 8 inputs required");
     m = (int)mxGetN(pin[4]);
     n = (int)mxGetN(pin[5]);

@@ -68,6 +68,14 @@ static inline void mexErrMsgIdAndTxt(const char *id, const char *msg)
     fprintf(stderr, "mexErrMsgIdAndTxt: %s\n", vlg_shim_last_error);
     abort();
 }
+/* mexLock / mexIsLocked / mexAtExit: the shim records them; vlg_shim_run_atexit() is what "MATLAB exits" does */
+static int vlg_shim_locked;
+static void (*vlg_shim_atexit_fn)(void);
+static inline void mexLock(void) { vlg_shim_locked++; }
+static inline void mexUnlock(void) { if (vlg_shim_locked > 0) vlg_shim_locked--; }
+static inline int mexIsLocked(void) { return vlg_shim_locked > 0; }
+static inline int mexAtExit(void (*fn)(void)) { vlg_shim_atexit_fn = fn; return 0; }
+static inline void vlg_shim_run_atexit(void) { if (vlg_shim_atexit_fn) vlg_shim_atexit_fn(); }
 static inline void mxDestroyArray(mxArray *a)
 {
     if (!a) return;

@@ -96,10 +96,18 @@ def test_reference_driver_over_gpu_mex_wrappers(name):
     mex drop-ins instead of the reference's mex files."""
     g = load_golden(name)
     lm.use_ref_library(build_shim())
+    capi.dense_release()
+    h0, b0 = capi.dense_cache_stats()
     try:
         res = lm.bundle_euclid(g["K"], g["Te"], g["w"], g["Xe"], g["x"], *golden_opts(g), backend="ref")
     finally:
         lm.use_ref_library(None)
+    # the wrappers keep their contexts between calls (SURVEY.md 8b(i)): one build for mex1/mex3, one for mex2, every
+    # later call of the loop is a re-use -- and the trajectory below is still the reference's
+    h1, b1 = capi.dense_cache_stats()
+    ntrial = len(res.trials)
+    assert b1 - b0 == 2 and h1 - h0 == 3 * ntrial - 2, (h1 - h0, b1 - b0, ntrial)
+    capi.dense_release()
     ref = g["error_"]
     assert len(res.error_) == len(ref)
     assert rel(res.error_[0], ref[0]) <= 1e-13 and rel(res.error_[1], ref[1]) <= 1e-9
