@@ -61,7 +61,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan", "vlg_ba_selftest_quotients", "vlg_ba_dense_release", "vlg_ba_dense_cache_stats",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan", "vlg_ba_selftest_quotients", "vlg_ba_solve_cameras_independent", "vlg_ba_dense_release", "vlg_ba_dense_cache_stats",
 ]
 
 
@@ -293,6 +293,14 @@ class Context:
         x4 = None if Xe4 is None else _c(Xe4)
         self._ck(self._L.vlg_ba_solve(self._h, _d(K_), _d(Te_), _d(w_), _d(Xe_), _d(x4), _d(err), C.byref(ne)))
         return K_, Te_, w_, Xe_, err[:ne.value].copy()
+
+    def solve_cameras_independent(self):
+        """Per-camera LM loops side by side (fix_structure contexts): -> a (m, na), list of per-camera error_ arrays, rounds."""
+        m, mi = self.m, self.opts.max_iter
+        a = np.zeros((m, self.na)); err = np.zeros((m, mi)); ne = np.zeros(m, dtype=np.int32)
+        rounds = C.c_int()
+        self._ck(self._L.vlg_ba_solve_cameras_independent(self._h, _d(a), _d(err), _i(ne), C.byref(rounds)))
+        return a, [err[j, :ne[j]].copy() for j in range(m)], rounds.value
 
     # ---- introspection
     def schur_structure(self):

@@ -1193,6 +1193,63 @@ __global__ void __launch_bounds__(1024) k_argmax_sq(int64_t nobs, const double* 
 }
 
 // ---------------------------------------------------------------------------------------
+// Batched independent single-camera problems (estimate_camera.m:247-253 runs bundle_euclid with
+// 'fix_structure' on ONE camera; incr_reconstruction.m:223-348 does that once per added camera).  With the structure
+// fixed the reduced system is block diagonal -- S_jj = U*_j, e_j = eA_j (mex_bundle_2_Se_.c:80-101,132-155 with Y = 0) --
+// so B such problems are one context with B cameras whose LM loops run side by side, each with its own lambda, nu,
+// accept decision and stop rule (vlg_ba_solve_cameras_independent).  These kernels are the per-camera pieces.
+// ---------------------------------------------------------------------------------------
+// U*_j = U_j with its diagonal scaled by (1 + lambda_j)   (bundle_euclid.m:162-167, one lambda per camera)
+template <int NA>
+__global__ void k_damp_U_vec(int m, const double* __restrict__ lam, const double* __restrict__ U, double* __restrict__ Ud)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * NA * NA) return;
+    const int j = t / (NA * NA), r = t - j * NA * NA;
+    const double u = U[t];
+    Ud[t] = (r % NA == r / NA) ? (1 + lam[j]) * u : u;
+}
+
+// da_j = pinv(U*_j) eA_j (bundle_euclid.m:193 on a block-diagonal S) and da_j'(lambda_j da_j + eA_j) (:217 with db = 0);
+// cameras that are not active get da_j = 0
+template <int NA>
+__global__ void k_cam_solve_diag(int m, const double* __restrict__ Ud, const double* __restrict__ eA, const double* __restrict__ lam,
+                                 const unsigned char* __restrict__ active, double* __restrict__ da, double* __restrict__ denom)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double M[NA * NA], Mi[NA * NA], g[NA];
+#pragma unroll
+    for (int k = 0; k < NA * NA; k++) M[k] = Ud[(size_t)NA * NA * j + k];
+#pragma unroll
+    for (int k = 0; k < NA; k++) g[k] = eA[(size_t)NA * j + k];
+    sym_pinv<NA>(M, Mi);
+    double dn = 0.0;
+#pragma unroll
+    for (int r = 0; r < NA; r++) {
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < NA; c++) v += Mi[r + NA * c] * g[c];
+        if (!active[j]) v = 0.0;
+        da[(size_t)NA * j + r] = v;
+        dn += v * (lam[j] * v + g[r]);
+    }
+    denom[j] = dn;
+}
+
+// per-camera sum of a per-observation quantity over the camera's (contiguous, C-order) segment: one warp per camera,
+// lanes stride over the segment, fixed xor tree
+__global__ void k_cam_seg_sum(int m, const int* __restrict__ cam_ptr, const double* __restrict__ v, double* __restrict__ out)
+{
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= m) return;
+    double s = 0.0;
+    for (int o = cam_ptr[j] + lane; o < cam_ptr[j + 1]; o += 32) s += v[o];
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
+}
+
+// ---------------------------------------------------------------------------------------
 // self-test of the shared-reciprocal quotients (ba_math.cuh: Den, fd_quot) against __ddiv_rn on random operands:
 // class 0: a, d with random significands and exponents in +-200 (d inside the reciprocals' safe window);
 // class 1: depths d in [0.01, 1e4), numerators |a| < 1e7 (what a reprojection divides);

@@ -259,6 +259,71 @@ k_schur_chunk(SchurChunkArgs p)
     if (p.Yout && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // Yt must outlive the bulk store's reads
 }
 
+// ---------------------------------------------------------------------------------------
+// Back-substitution (mex_bundle_3_db_new.c:100-146) with one lane per observation over tiles of whole points, as
+// k_backsub_tiled -- the same operations in the same order, bit-identical -- but the W records (C-order, 144 bytes,
+// scattered when walked in point order) arrive by warp-cooperative cp.async instead of nine lane-private 16-byte
+// gathers: ncu of the round-1 kernel showed 0.41 ms at 3 % FP64 / 5 % issue utilisation, all of it LSU wavefronts.
+// ---------------------------------------------------------------------------------------
+template <int NA>
+__global__ void __launch_bounds__(kS1Tile)
+k_backsub_coop(const int4* __restrict__ ptile_meta, const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
+               const int* __restrict__ pt_cam, const double* __restrict__ W, const double* __restrict__ Vinv,
+               const double* __restrict__ eB, const double* __restrict__ da, const double* __restrict__ b, double lambda,
+               int all_rows, double* __restrict__ db, double* __restrict__ b_new, double* __restrict__ denom_pt)
+{
+    constexpr int NW = 3 * NA;
+    static_assert(NW % 2 == 0, "16-byte units");
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* wt = reinterpret_cast<double*>(smraw);                 // kS1Tile x NW, one 32-record slab per warp
+    __shared__ double pr[3][kS1Tile];
+    const int4 meta = __ldg(ptile_meta + blockIdx.x);
+    const int q0 = meta.x, nob = meta.y, p0 = meta.z, np = meta.w, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nrow = all_rows ? NA : 6;
+    if (warp * 32 < nob) {
+        const int o = tid < nob ? __ldg(pt_obs + q0 + tid) : -1;
+        const int j = tid < nob ? __ldg(pt_cam + q0 + tid) : 0;
+        double* slab = wt + (size_t)warp * 32 * NW;
+        warp_gather_records<NW / 2>(reinterpret_cast<const char*>(W), o, reinterpret_cast<char*>(slab), lane);
+        double dj[NA];
+#pragma unroll
+        for (int r = 0; r < NA; r++) dj[r] = __ldg(da + (size_t)NA * j + r);
+        cp_async_wait_all();
+        __syncwarp();
+        if (tid < nob) {
+            double Wo[NW];
+            load_block<NW>(slab, lane, Wo);
+            double s0 = VLG_M(Wo[0], dj[0]), s1 = VLG_M(Wo[NA], dj[0]), s2 = VLG_M(Wo[2 * NA], dj[0]);
+#pragma unroll
+            for (int r = 1; r < NA; r++) {
+                if (r < nrow) {
+                    s0 = VLG_P(s0, VLG_M(Wo[r], dj[r]));
+                    s1 = VLG_P(s1, VLG_M(Wo[r + NA], dj[r]));
+                    s2 = VLG_P(s2, VLG_M(Wo[r + 2 * NA], dj[r]));
+                }
+            }
+            pr[0][tid] = s0; pr[1][tid] = s1; pr[2][tid] = s2;
+        }
+    }
+    __syncthreads();
+    if (tid < np) {
+        const int i = p0 + tid;
+        double w0 = eB[(size_t)3 * i], w1 = eB[(size_t)3 * i + 1], w2 = eB[(size_t)3 * i + 2];
+        const double g0 = w0, g1 = w1, g2 = w2;
+        const int o0 = pt_ptr[i] - q0, o1 = pt_ptr[i + 1] - q0;
+        for (int o = o0; o < o1; o++) { w0 = VLG_S(w0, pr[0][o]); w1 = VLG_S(w1, pr[1][o]); w2 = VLG_S(w2, pr[2][o]); }
+        const double* Vi = Vinv + (size_t)9 * i;
+        const double d0 = VLG_P(VLG_P(VLG_M(Vi[0], w0), VLG_M(Vi[3], w1)), VLG_M(Vi[6], w2));
+        const double d1 = VLG_P(VLG_P(VLG_M(Vi[1], w0), VLG_M(Vi[4], w1)), VLG_M(Vi[7], w2));
+        const double d2 = VLG_P(VLG_P(VLG_M(Vi[2], w0), VLG_M(Vi[5], w1)), VLG_M(Vi[8], w2));
+        db[(size_t)3 * i] = d0; db[(size_t)3 * i + 1] = d1; db[(size_t)3 * i + 2] = d2;
+        b_new[(size_t)3 * i] = VLG_P(b[(size_t)3 * i], d0);
+        b_new[(size_t)3 * i + 1] = VLG_P(b[(size_t)3 * i + 1], d1);
+        b_new[(size_t)3 * i + 2] = VLG_P(b[(size_t)3 * i + 2], d2);
+        denom_pt[i] = d0 * (lambda * d0 + g0) + d1 * (lambda * d1 + g1) + d2 * (lambda * d2 + g2);
+    }
+}
+
 // S_jk (and S_kj) of the heavy blocks: the block's segments added in chunk order
 template <int NA>
 __global__ void __launch_bounds__(128)

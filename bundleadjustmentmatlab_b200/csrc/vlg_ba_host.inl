@@ -462,7 +462,20 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
     {
         TimedScope ts(ctx, T_STAGE3);
         if (n > 0) {
-            if (ctx->ns1tiles > 0)
+            bool coop_done = false;
+            if constexpr ((3 * NA) % 2 == 0) {
+                static const bool coop_on = []() { const char* e = getenv("VLG_BA_BACKSUB_COOP"); return e ? atoi(e) != 0 : true; }();
+                if (ctx->ns1tiles > 0 && coop_on) {
+                    const size_t sm = sizeof(double) * (size_t)kS1Tile * 3 * NA;
+                    CU(cudaFuncSetAttribute(k_backsub_coop<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    k_backsub_coop<NA><<<ctx->ns1tiles, kS1Tile, sm, ctx->stream>>>(ctx->s1tile_meta, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W,
+                                                                                   ctx->Vinv, ctx->eB, ctx->da, ctx->b, lambda,
+                                                                                   ctx->opt.backsub_all_rows, ctx->db, ctx->b_new, ctx->denom_pt);
+                    coop_done = true;
+                }
+            }
+            if (coop_done) {
+            } else if (ctx->ns1tiles > 0)
                 k_backsub_tiled<NA><<<ctx->ns1tiles, kS1Tile, 0, ctx->stream>>>(ctx->s1tile_meta, ctx->pt_ptr, ctx->pt_obs, ctx->pt_cam, ctx->W,
                                                                              ctx->Vinv, ctx->eB, ctx->da, ctx->b, lambda,
                                                                              ctx->opt.backsub_all_rows, ctx->db, ctx->b_new, ctx->denom_pt);
@@ -1273,3 +1286,5 @@ int vlg_ba_timer_stop(vlg_ba_ctx* ctx, float* elapsed_ms)
 #include "vlg_ba_dense.inl"
 
 }  // extern "C"
+
+#include "vlg_ba_batch.inl"

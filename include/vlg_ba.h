@@ -198,6 +198,16 @@ int  vlg_ba_lm_continue(const vlg_ba_ctx *ctx);
 int  vlg_ba_solve(vlg_ba_ctx *ctx, double *K_, double *Te_, double *w_, double *Xe_,
                   const double *Xe4, double *error_, int *n_error);
 
+/* B independent single-camera motion-only bundle adjustments side by side (toolbox/geometry/estimate_camera.m:247-253:
+ * bundle_euclid(K, T, Omega, X, x, 'fix_structure', 'fix_calibration', 'visibility', inlier') on ONE camera, once per camera
+ * added in incr_reconstruction.m:223-348).  The context holds all B cameras (opts.fix_structure = 1; camera j sees its own
+ * points); with the structure fixed the cameras decouple, and every camera runs its own loop of bundle_euclid.m:111-249
+ * -- own lambda, nu, accept decisions, stop rule -- exactly as if bundle_euclid had been called on it alone, but one
+ * ROUND of kernels advances all cameras that have not stopped.  a_out: num_a x m final parameters; error_: max_iter
+ * doubles per camera (camera j at error_ + j*max_iter), n_error[j] its length (0: no accepted step); *rounds: trial
+ * rounds run.  Any of the outputs may be NULL. */
+int  vlg_ba_solve_cameras_independent(vlg_ba_ctx *ctx, double *a_out, double *error_, int *n_error, int *rounds);
+
 /* End-to-end convenience used by the mex wrapper and bench.py's e2e leg: host buffers in,
  * one LM trial step, host buffers out (H2D of a, b and the observation list, D2H of a_new,
  * b_new and the costs all inside the call). */
