@@ -489,12 +489,102 @@ def run_ours(args):
         raise SystemExit(rc)
 
 
+# ------------------------------------------------------------------------------------------
+# --config incremental: the cadence of the reference's heaviest caller
+# ------------------------------------------------------------------------------------------
+def run_incremental(args):
+    """incr_reconstruction.m:223-348 adds one camera at a time and calls bundle_euclid about three times per camera: a
+    single-camera motion-only BA (estimate_camera.m:247-253, 'fix_structure'), a BA of all cameras so far (:262/266) and the
+    same again after triangulation (:324/328).  test_incremental.m:19-27 runs it on 50 cameras / <= 200 tracked points.
+    Here: the same sequence of calls on a synthetic scene of that size, ONE context re-used for every call (set_problem on
+    a live context), timed end to end with host buffers (every call uploads its problem and downloads its result), against
+    the CPU oracle making the same calls; plus the batched entry (all resections of the sequence side by side)."""
+    import torch
+    from bundleadjustmentmatlab_b200 import capi, synth
+    from oracle import lm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    P = synth.make_problem(50, 2000, 16000, seed=args.seed)
+    a_all = np.ascontiguousarray(np.vstack([P.w, P.Te]).T); b_all = np.ascontiguousarray(P.Xe[:3].T)
+    calls = []                      # (kind, camera range, options)
+    for mc in range(3, P.m + 1):
+        calls.append(("resect", (mc - 1, mc)))
+        calls.append(("full", (0, mc)))
+        calls.append(("full", (0, mc)))
+    def sub(c0, c1):
+        keep = (P.obs_cam >= c0) & (P.obs_cam < c1)
+        return np.ascontiguousarray(P.obs_xy[keep]), P.obs_pt[keep], (P.obs_cam[keep] - c0).astype(np.int32)
+    subs = {rng: sub(*rng) for _, rng in calls}
+    ctx = {"resect": capi.Context(num_variableK=0, fix_structure=1), "full": capi.Context(num_variableK=0)}
+    def gpu_call(kind, rng):
+        xy, pt, cam = subs[rng]
+        c = ctx[kind]
+        c.set_problem_sparse(P.K.T[rng[0]:rng[1]], a_all[rng[0]:rng[1]], b_all, xy, pt, cam)
+        return c.solve()[4]
+    for kind, rng in calls[:6]:
+        gpu_call(kind, rng)                                   # warm-up (module load, first allocations)
+    torch.cuda.synchronize()
+    l0 = sum(c.kernel_launches for c in ctx.values())
+    t0 = time.perf_counter()
+    errs = [gpu_call(kind, rng) for kind, rng in calls]
+    torch.cuda.synchronize()
+    t_gpu = time.perf_counter() - t0
+    launches = sum(c.kernel_launches for c in ctx.values()) - l0
+    # the batched entry: every resection of the sequence in one solve
+    cb = capi.Context(num_variableK=0, fix_structure=1)
+    cb.set_problem_sparse(P.K.T, a_all, b_all, P.obs_xy, P.obs_pt, P.obs_cam)
+    cb.solve_cameras_independent()
+    cb.set_problem_sparse(P.K.T, a_all, b_all, P.obs_xy, P.obs_pt, P.obs_cam)
+    t0 = time.perf_counter()
+    _, berrs, rounds = cb.solve_cameras_independent()
+    t_batch = time.perf_counter() - t0
+    # CPU oracle: the same calls (bounded sample: every `stride`-th call)
+    lib = lm.sparse_lib()
+    lib.orc_set_num_threads(args.cpu_threads if args.cpu_threads > 0 else len(os.sched_getaffinity(0)))
+    stride = 6
+    t_cpu, worst, nsample = 0.0, 0.0, 0
+    for k in range(0, len(calls), stride):
+        kind, rng = calls[k]
+        xy, pt, cam = subs[rng]
+        mc = rng[1] - rng[0]
+        x = np.zeros((3, P.n, mc), order="F"); vis = np.zeros((P.n, mc), order="F")
+        x[0, pt, cam] = xy[:, 0]; x[1, pt, cam] = xy[:, 1]; x[2] = 1.0; vis[pt, cam] = 1.0
+        opts = ["fix_calibration", "visibility", vis] + (["fix_structure"] if kind == "resect" else [])
+        t0 = time.perf_counter()
+        ref = lm.bundle_euclid(P.K[:, rng[0]:rng[1]], P.Te[:, rng[0]:rng[1]], P.w[:, rng[0]:rng[1]], P.Xe, x, *opts, backend="sparse", record=False)
+        t_cpu += time.perf_counter() - t0
+        nsample += 1
+        e = errs[k]
+        worst = max(worst, abs(e[0] - ref.error_[0]) / ref.error_[0], abs(e[1] - ref.error_[1]) / ref.error_[1])
+    for c in list(ctx.values()) + [cb]:
+        c.close()
+    val = len(calls) / t_gpu
+    cpu_val = nsample / t_cpu
+    line = {"metric": "incremental-reconstruction cadence, bundle_euclid calls/s (set-up + solve, host buffers in and out)", "value": val,
+            "unit": "calls/s", "n_gpus": 1, "steps": len(calls), "warmup": 6, "ms_per_step": 1e3 * t_gpu / len(calls), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"incremental cadence (incr_reconstruction.m:223-348): cameras 3..{P.m} of a {P.m}-camera / {P.n}-point / {P.nobs}-observation scene, "
+                                   "per added camera one single-camera 'fix_structure' BA + two BAs of all cameras so far, one context re-used"},
+            "e2e": {"value": val, "unit": "calls/s", "h2d_bytes_per_step": int(np.mean([subs[r][0].nbytes + subs[r][1].nbytes + subs[r][2].nbytes for _, r in calls]) + b_all.nbytes),
+                    "d2h_bytes_per_step": int(b_all.nbytes * 4 / 3)},
+            "gpu_launches": int(launches), "roofline": None,
+            "cpu_baseline": {"value": cpu_val, "unit": "calls/s", "cores": int(lib.orc_num_threads()), "kind": "port",
+                             "sample": f"every {stride}th call of the same sequence ({nsample} calls, {t_cpu:.1f} s): oracle/lm.py bundle_euclid over oracle_sparse.c (dense pinv solve)"},
+            "parity": {"against": "oracle, first accepted step of the sampled calls", "new_rel": worst, "tol": 1e-9, "ok": bool(worst <= 1e-9)},
+            "batched_resections": {"cameras": P.m, "rounds": rounds, "ms": 1e3 * t_batch, "resections_per_sec": P.m / t_batch,
+                                   "note": "vlg_ba_solve_cameras_independent: all single-camera 'fix_structure' problems of the sequence side by side"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
     args = parse()
-    if args.impl == "reference":
+    if args.config == "incremental":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_incremental(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

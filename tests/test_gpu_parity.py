@@ -182,6 +182,29 @@ def test_fast_quotients_are_ieee_quotients():
         assert capi.selftest_quotients(10**9, seed=seed) == 0
 
 
+def test_repeated_steps_are_bit_identical_on_every_solver():
+    """The hand-rolled synchronisation (mbarrier rings, grid barriers, cp.async pipelines, cooperative kernels) has no
+    race-detector record -- compute-sanitizer is closed on the GPU pool (profiles/compute_sanitizer_r02_refused.txt).  What a
+    race in them would break first is run-to-run reproducibility: every reduction here has a fixed shape, so forty repeats
+    of the same LM trial step must give the same bits -- costs, iteration counts and the whole step da."""
+    P = synth.make_problem(130, 14000, 66000, seed=41)
+    a = np.ascontiguousarray(np.vstack([P.w, P.Te]).T); b = np.ascontiguousarray(P.Xe[:3].T)
+    for solver in (capi.SOLVER_CHOL, capi.SOLVER_PCG, capi.SOLVER_PCG_EXPLICIT):
+        ctx = capi.Context(num_variableK=0, solver=solver)
+        ctx.set_problem_sparse(P.K.T, a, b, P.obs_xy, P.obs_pt, P.obs_cam)
+        first = None
+        for rep in range(40):
+            ctx.set_state(a=a, b=b, lam=1e-3, nu=2.0)
+            ctx.stage1(); ctx.stage2(1e-3)
+            da = ctx.get_reduced()["da"].copy()
+            new_cost, denom = ctx.stage3(1e-3)
+            cur = (new_cost, denom, da.tobytes())
+            if first is None:
+                first = cur
+            assert cur == first, (solver, rep)
+        ctx.close()
+
+
 def test_medium_problem_vs_sparse_oracle():
     P = synth.make_problem(30, 3000, 13000, seed=4)
     a = np.vstack([P.w, P.Te]); b = P.Xe[:3].copy()
