@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--model", default="euclid", choices=["euclid", "projective"],
                     help="euclid: bundle_euclid.m with 'fix_calibration' (num_a = 6, the headline); projective: bundle_projective.m (num_a = 12)")
+    ap.add_argument("--banded", action="store_true", help="tracks are contiguous camera windows (no loop-closure cameras): S is banded")
     ap.add_argument("--no-verify", action="store_true", help="multi-GPU: skip the check of the first N-rank step against rank 0 alone")
     ap.add_argument("--autotune", type=int, default=0,
                     help="opts.pcg_autotune: re-weight the matvec cut by the measured per-SM rate over the first N solves (0 = off)")
@@ -105,7 +106,7 @@ class ClockSampler:
 def make_global(args):
     """The ONE problem of this run (every rank generates the same one: the generator is deterministic)."""
     from bundleadjustmentmatlab_b200 import synth
-    P = synth.make_config(args.config, seed=args.seed, scale=args.scale)
+    P = synth.make_config(args.config, seed=args.seed, scale=args.scale, banded=getattr(args, "banded", False))
     if getattr(args, "model", "euclid") == "projective":
         # a = vec(P_j), P_j = K_j [R(w_j) T_j]  (bundle_projective.m:69-72)
         a = np.zeros((P.m, 12))
@@ -131,7 +132,7 @@ def make_local(P, b, rank, world):
 
 def workload_name(args, P, world):
     return (f"{args.config}-shaped synthetic BA: {P.m} cameras, {P.n} points, {P.nobs} observations (ONE problem); "
-            f"{world} rank(s), point-sharded")
+            f"{world} rank(s), point-sharded" + ("; banded visibility (no loop-closure cameras)" if getattr(args, "banded", False) else ""))
 
 
 # ------------------------------------------------------------------------------------------
@@ -200,6 +201,8 @@ def algorithmic_bytes(name, L, na=6, pcg_iters=0.0, world=1):
     no, n, m = L.nobs, L.n, L.m
     W = 3 * na * 8
     Np = (na * m + 31) // 32 * 32
+    # S bytes one matvec of this rank streams: the kept tiles of its column block (vlg_ba_symv_bytes) when the library says so
+    sbytes = getattr(L, "symv_bytes", 0) or 4 * Np * (Np + 32) / world
     table = {
         # read (u,v)+point id, write W and the per-observation V/eB terms (read back by the point pass); per point b;
         # per camera table/a/K in, partial U/eA out
@@ -213,9 +216,9 @@ def algorithmic_bytes(name, L, na=6, pcg_iters=0.0, world=1):
         "w_copy": no * (2 * W + 4),
         # explicit-S PCG: this rank's column block of the lower triangle of S (32-column strips incl. the full diagonal
         # blocks; the blocks of the ranks have equal areas) + partial vectors
-        "pcg_symv": 4 * Np * (Np + 32) / world + 8 * Np * 4,
+        "pcg_symv": sbytes + 8 * Np * 4,
         # the persistent PCG kernel: one launch = `pcg_iters` matvecs over this rank's block (+ the vectors)
-        "pcg_persistent": pcg_iters * (4 * Np * (Np + 32) / world + 8 * Np * 8),
+        "pcg_persistent": pcg_iters * (sbytes + 8 * Np * 8),
     }
     return table.get(name)
 
@@ -278,6 +281,7 @@ def run_ours(args):
         dist.broadcast(uid, 0)
         ctx.set_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
     ctx.set_problem_sparse(None if proj else L.K.T, a0, b0, L.obs_xy, L.obs_pt, L.obs_cam)
+    L.symv_bytes = ctx.symv_bytes
     p2p = world > 1 and not args.no_p2p
     if p2p:
         # the per-iteration PCG vector goes through NVLink peer-memory mailboxes (CUDA IPC), not NCCL

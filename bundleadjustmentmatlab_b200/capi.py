@@ -61,7 +61,7 @@ SYMBOLS = [
     "vlg_ba_set_da", "vlg_ba_stage3", "vlg_ba_get_update", "vlg_ba_trial_step", "vlg_ba_solve",
     "vlg_ba_trial_step_host", "vlg_ba_get_schur_structure", "vlg_ba_kernel_launches", "vlg_ba_kernel_time",
     "vlg_ba_reset_timers", "vlg_ba_timer_start", "vlg_ba_timer_stop", "vlg_ba_lm_reset", "vlg_ba_lm_continue",
-    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan", "vlg_ba_selftest_quotients", "vlg_ba_solve_cameras_independent", "vlg_ba_dense_release", "vlg_ba_dense_cache_stats",
+    "vlg_ba_mex1_dense", "vlg_ba_mex2_dense", "vlg_ba_mex3_dense", "vlg_ba_bundle_euclid", "vlg_ba_bundle_euclid_sparse", "vlg_ba_bundle_projective", "vlg_ba_reproj_errors", "vlg_ba_symv_plan", "vlg_ba_selftest_quotients", "vlg_ba_symv_plan_occ", "vlg_ba_symv_bytes", "vlg_ba_solve_cameras_independent", "vlg_ba_dense_release", "vlg_ba_dense_cache_stats",
 ]
 
 
@@ -325,6 +325,13 @@ class Context:
         self._ck(self._L.vlg_ba_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    @property
+    def symv_bytes(self) -> int:
+        """Bytes of S one assembled-S matvec streams on this rank (kept tiles of the lower triangle)."""
+        self._L.vlg_ba_symv_bytes.restype = C.c_int64
+        self._L.vlg_ba_symv_bytes.argtypes = [C.c_void_p]
+        return int(self._L.vlg_ba_symv_bytes(self._h))
+
     def kernel_time(self, name: str):
         ms, cnt = C.c_double(), C.c_int64()
         self._ck(self._L.vlg_ba_kernel_time(self._h, name.encode(), C.byref(ms), C.byref(cnt)))
@@ -352,7 +359,7 @@ def selftest_quotients(nsamples: int = 10**9, seed: int = 1, device: int = -1) -
     return int(bad.value)
 
 
-def symv_plan(Np: int, G: int, J0: int = 0, J1: int | None = None, speed=None) -> dict:
+def symv_plan(Np: int, G: int, J0: int = 0, J1: int | None = None, speed=None, occ=None) -> dict:
     """Host-side plan of the assembled-S matvec (vlg_ba_symv_plan): tiles, per-CTA pieces and fold lists.  No GPU needed."""
     L = lib()
     if J1 is None:
@@ -361,8 +368,11 @@ def symv_plan(Np: int, G: int, J0: int = 0, J1: int | None = None, speed=None) -
     sp = None if speed is None else np.ascontiguousarray(speed, dtype=np.float64)
     spp = None if sp is None else sp.ctypes.data_as(C.POINTER(C.c_double))
 
+    oc = None if occ is None else np.ascontiguousarray(occ, dtype=np.uint8)
+    ocp = None if oc is None else oc.ctypes.data_as(C.POINTER(C.c_uint8))
+
     def call(*arrs):
-        r = L.vlg_ba_symv_plan(C.c_int(Np), C.c_int(G), C.c_int(J0), C.c_int(J1), spp, *arrs, sizes)
+        r = L.vlg_ba_symv_plan_occ(C.c_int(Np), C.c_int(G), C.c_int(J0), C.c_int(J1), spp, ocp, *arrs, sizes)
         if r != 0:
             raise VlgBaError(f"vlg_ba_symv_plan: {L.vlg_ba_last_error(None).decode()}")
 

@@ -103,6 +103,7 @@ struct vlg_ba_ctx {
     std::vector<double> h_symv_cum, symv_speed;
     std::vector<int> h_symv_tptr, symv_smid;
     int symv_ncell = 0, symv_learn_left = 0;
+    int64_t symv_bytes = 0;                   // bytes of S one matvec of this rank streams (kept tiles only)
     long long* symv_stat = nullptr;           // device [2 G]: matvec clocks of the last solve, SM id, per CTA
     unsigned int* persist_bar = nullptr;   // grid barrier counter of k_pcg_persistent
     unsigned int* init_bar = nullptr;      // ... of k_pcg_init_defl_coop
@@ -425,8 +426,13 @@ struct SymvPlan {
     int nfrag = 0;
 };
 
-void symv_sequence(int Np, int J0, int J1, std::vector<vlg_ba_ctx::SymvTileH>& seq, std::vector<double>& cum, int& ncell)
+// `occ` (optional, [ceil(Np / 256)][Np / 32], row-major): 1 where the 256-row slot x 32-column strip of the lower triangle
+// holds a structurally non-zero block of S; tiles of empty slots are left out of the sequence -- they would stream zeros
+// (a banded scene, i.e. cameras that only share points with their neighbours, has most of the triangle empty).
+void symv_sequence(int Np, int J0, int J1, std::vector<vlg_ba_ctx::SymvTileH>& seq, std::vector<double>& cum, int& ncell,
+                   const unsigned char* occ = nullptr)
 {
+    const int nstrips_all = Np / kSymvCols;
     seq.clear();
     ncell = 0;
     for (int Js = J0; Js < J1; Js += kSymvSlab) {
@@ -437,7 +443,7 @@ void symv_sequence(int Np, int J0, int J1, std::vector<vlg_ba_ctx::SymvTileH>& s
                 const int hi = std::min(Np, b0 + kSymvBlkRows);
                 while (lo < hi) {
                     const int nx = std::min(hi, (lo / kSymvRows + 1) * kSymvRows);
-                    seq.push_back({J, lo, nx - lo, ncell, J - Js});
+                    if (!occ || occ[(size_t)(lo / kSymvRows) * nstrips_all + J]) seq.push_back({J, lo, nx - lo, ncell, J - Js});
                     lo = nx;
                 }
             }
@@ -865,7 +871,35 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
         ctx->s_J1 = ctx->s_split ? ctx->s_bounds[(size_t)ctx->rank + 1] : nstrips;
         std::vector<vlg_ba_ctx::SymvTileH>& seq = ctx->h_symv_seq;
         int ncell = 0;
-        symv_sequence(Np, ctx->s_J0, ctx->s_J1, seq, ctx->h_symv_cum, ncell);
+        // which (256-row slot, strip) pairs of the lower triangle hold a non-zero block: block (j, k), j <= k, puts the rows
+        // of camera k against the columns of camera j; a strip's own diagonal tile is always kept (U* sits there)
+        std::vector<unsigned char> occ((size_t)((Np + kSymvRows - 1) / kSymvRows) * nstrips, 0);
+        {
+            const char* e = getenv("VLG_BA_SYMV_DENSE");         // 1: stream every tile of the triangle (round-1 behaviour)
+            if (e && atoi(e) != 0) std::fill(occ.begin(), occ.end(), 1);
+            for (size_t bb = 0; bb < ctx->h_blk_j.size(); bb++) {
+                const int j = ctx->h_blk_j[bb], k = ctx->h_blk_k[bb];
+                for (int rs = (na * k) / kSymvRows; rs <= (na * k + na - 1) / kSymvRows; rs++)
+                    for (int J = (na * j) / kSymvCols; J <= (na * j + na - 1) / kSymvCols; J++) occ[(size_t)rs * nstrips + J] = 1;
+            }
+            for (int J = 0; J < nstrips; J++) occ[(size_t)((kSymvCols * J) / kSymvRows) * nstrips + J] = 1;
+        }
+        if (ctx->nranks > 1) {
+            // a rank multiplies its column block of the SUM of all ranks' shares: the pattern is the union over ranks
+            std::vector<double> od(occ.begin(), occ.end());
+            double* d_occ = nullptr;
+            CU(cudaMalloc(&d_occ, sizeof(double) * od.size()));
+            int rc = upload(ctx, d_occ, od.data(), od.size());
+            if (rc == VLG_BA_OK) rc = allreduce(ctx, d_occ, od.size());
+            if (rc == VLG_BA_OK) rc = download(ctx, od.data(), d_occ, od.size());
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_occ);
+            CHK(rc);
+            for (size_t t = 0; t < occ.size(); t++) occ[t] = od[t] > 0.0 ? 1 : 0;
+        }
+        symv_sequence(Np, ctx->s_J0, ctx->s_J1, seq, ctx->h_symv_cum, ncell, occ.data());
+        ctx->symv_bytes = 0;
+        for (const auto& t : seq) ctx->symv_bytes += (int64_t)t.rows * kSymvCols * 8;
         // one CTA per SM at most; never fewer CTAs than preconditioner clusters (when those fit one per SM), even if this
         // rank's column block has fewer tiles than that (surplus CTAs get an empty piece): whether the whole solve runs as the
         // persistent kernel (coop_grid <= symv_grid, run_stage2) must come out the same on every rank

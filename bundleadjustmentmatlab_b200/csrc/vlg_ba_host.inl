@@ -998,15 +998,23 @@ int vlg_ba_get_reduced(vlg_ba_ctx* ctx, double* Vinv, double* S, double* e_, dou
     return VLG_BA_OK;
 }
 
+int64_t vlg_ba_symv_bytes(const vlg_ba_ctx* ctx) { return ctx && ctx->use_explicit ? ctx->symv_bytes : 0; }
+
 int vlg_ba_symv_plan(int Np, int G, int J0, int J1, const double* speed, int32_t* tiles4, int32_t* tile_ptr, int32_t* row_ptr,
                      int32_t* row_list, int32_t* col_ptr, int32_t* col_list, int64_t* sizes)
+{
+    return vlg_ba_symv_plan_occ(Np, G, J0, J1, speed, nullptr, tiles4, tile_ptr, row_ptr, row_list, col_ptr, col_list, sizes);
+}
+
+int vlg_ba_symv_plan_occ(int Np, int G, int J0, int J1, const double* speed, const unsigned char* occ, int32_t* tiles4, int32_t* tile_ptr,
+                         int32_t* row_ptr, int32_t* row_list, int32_t* col_ptr, int32_t* col_list, int64_t* sizes)
 {
     if (Np <= 0 || Np % kSymvCols != 0 || G <= 0 || J0 < 0 || J1 > Np / kSymvCols || J0 > J1 || !sizes)
         return fail(nullptr, VLG_BA_EINVAL, "symv_plan: Np must be a positive multiple of 32, 0 <= J0 <= J1 <= Np/32, G > 0");
     std::vector<vlg_ba_ctx::SymvTileH> seq;
     std::vector<double> cum, sp((size_t)G, 1.0);
     int ncell = 0;
-    symv_sequence(Np, J0, J1, seq, cum, ncell);
+    symv_sequence(Np, J0, J1, seq, cum, ncell, occ);
     if (speed) sp.assign(speed, speed + G);
     SymvPlan pl;
     symv_cut(Np, G, seq, cum, sp, pl);

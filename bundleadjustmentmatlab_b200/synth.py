@@ -89,7 +89,7 @@ def project(K, w, Te, X, obs_pt, obs_cam):
     return np.stack([u, v], axis=1)
 
 
-def _tracks(m: int, n: int, nobs: int, rng) -> tuple[np.ndarray, np.ndarray]:
+def _tracks(m: int, n: int, nobs: int, rng, window_frac: float = 0.9) -> tuple[np.ndarray, np.ndarray]:
     tmax = min(m, 64)
     mean = max(nobs / n, 2.0)
     if tmax <= 2 or mean <= 2.0:
@@ -112,7 +112,7 @@ def _tracks(m: int, n: int, nobs: int, rng) -> tuple[np.ndarray, np.ndarray]:
     start = np.repeat(np.cumsum(t) - t, t)
     r = np.arange(pt.shape[0], dtype=np.int64) - start
     tt = np.repeat(t, t)
-    nwin = np.maximum(2, np.ceil(0.9 * tt).astype(np.int64))
+    nwin = np.maximum(2, np.ceil(window_frac * tt).astype(np.int64))
     nwin = np.minimum(nwin, tt)
     centre = np.repeat(rng.integers(0, m, size=n), t)
     first = centre - nwin // 2
@@ -134,9 +134,11 @@ def _tracks(m: int, n: int, nobs: int, rng) -> tuple[np.ndarray, np.ndarray]:
 
 
 def make_problem(m: int, n: int, nobs: int, seed: int = 0, noise_px: float = 0.5,
-                 point_seed: int | None = None) -> Problem:
+                 point_seed: int | None = None, banded: bool = False) -> Problem:
     """`seed` fixes the cameras; `point_seed` (default: continue the same stream) fixes the points,
-    tracks and image noise -- shards of one scene share `seed` and differ in `point_seed`."""
+    tracks and image noise -- shards of one scene share `seed` and differ in `point_seed`.
+    `banded`: every track is one contiguous camera window (no random "loop closure" cameras), so cameras share points
+    only with their <= 63 neighbours and S is banded -- what a sequence without revisits looks like."""
     rng = np.random.default_rng(seed)
     cam_noise = np.random.default_rng([seed, 7])
     depth = 100.0
@@ -162,7 +164,7 @@ def make_problem(m: int, n: int, nobs: int, seed: int = 0, noise_px: float = 0.5
     d /= np.linalg.norm(d, axis=0)
     X_true = centre[:, None] + d * (25.0 * rng.random(n) ** (1.0 / 3.0))
 
-    pt, cam = _tracks(m, n, nobs, rng)
+    pt, cam = _tracks(m, n, nobs, rng, 1.0 if banded else 0.9)
     order = np.lexsort((pt, cam))            # ascending i + n*j
     pt, cam = pt[order], cam[order]
     xy = project(K, w_true, Te_true, X_true, pt, cam)
@@ -175,9 +177,9 @@ def make_problem(m: int, n: int, nobs: int, seed: int = 0, noise_px: float = 0.5
     return Problem(m, n, K, w0, T0, Xe, np.ascontiguousarray(xy), pt, cam, w_true, Te_true, X_true)
 
 
-def make_config(name: str, seed: int = 0, scale: float = 1.0, point_seed: int | None = None) -> Problem:
+def make_config(name: str, seed: int = 0, scale: float = 1.0, point_seed: int | None = None, banded: bool = False) -> Problem:
     m, n, nobs = CONFIGS[name]
     if scale != 1.0:
         n = max(int(n * scale), 8)
         nobs = max(int(nobs * scale), 2 * n)
-    return make_problem(m, n, nobs, seed, point_seed=point_seed)
+    return make_problem(m, n, nobs, seed, point_seed=point_seed, banded=banded)

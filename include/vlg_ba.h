@@ -292,6 +292,13 @@ int  vlg_ba_timer_stop(vlg_ba_ctx *ctx, float *elapsed_ms);
  * 4 first / 8 last tile of a fragment.  CPU tests replay the plan against a dense product. */
 int  vlg_ba_symv_plan(int Np, int G, int J0, int J1, const double *speed, int32_t *tiles4, int32_t *tile_ptr,
                       int32_t *row_ptr, int32_t *row_list, int32_t *col_ptr, int32_t *col_list, int64_t *sizes);
+/* The same with an occupancy map occ[ceil(Np/256)][Np/32] (row-major, 1 = the 256-row slot x 32-column strip holds a
+ * non-zero block of S): tiles of empty slots are left out, as build_problem does from the block structure -- a scene whose
+ * cameras share points only with their neighbours has a banded S, and its matvec streams the band, not the triangle. */
+int  vlg_ba_symv_plan_occ(int Np, int G, int J0, int J1, const double *speed, const unsigned char *occ, int32_t *tiles4,
+                          int32_t *tile_ptr, int32_t *row_ptr, int32_t *row_list, int32_t *col_ptr, int32_t *col_list, int64_t *sizes);
+/* Bytes of S one assembled-S matvec of this rank streams (kept tiles only; 0 on the other solver paths). */
+int64_t vlg_ba_symv_bytes(const vlg_ba_ctx *ctx);
 
 #ifdef __cplusplus
 }
