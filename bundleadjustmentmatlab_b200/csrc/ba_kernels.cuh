@@ -1252,6 +1252,7 @@ __global__ void k_cam_seg_sum(int m, const int* __restrict__ cam_ptr, const doub
 // ---------------------------------------------------------------------------------------
 // self-test of the shared-reciprocal quotients (ba_math.cuh: Den, fd_quot) against __ddiv_rn on random operands:
 // class 0: a, d with random significands and exponents in +-200 (d inside the reciprocals' safe window);
+// every class also compares the branch-free reciprocal (rcp_fast) with __drcp_rn;
 // class 1: depths d in [0.01, 1e4), numerators |a| < 1e7 (what a reprojection divides);
 // class 2: a = difference of two nearby image coordinates, d = h (what a forward difference divides).
 // Every thread runs `per_thread` samples of a counter-based generator; mismatches are counted bitwise.
@@ -1288,6 +1289,9 @@ __global__ void k_selftest_quotients(unsigned long long seed, int per_thread, un
         const double ref = __ddiv_rn(a, d);
         const double got = cls == 2 ? fd_quot<true>(a + 0.0, 0.0) : Den<true>(d)(a);
         bad += __double_as_longlong(ref) != __double_as_longlong(got);
+        // the branch-free reciprocal against CUDA's own, wherever the callers would accept it
+        const double rf = rcp_fast(d);
+        if (rcp_in_window(rf)) bad += __double_as_longlong(rf) != __double_as_longlong(__drcp_rn(d));
     }
     if (bad) atomicAdd(mismatches, bad);
 }
