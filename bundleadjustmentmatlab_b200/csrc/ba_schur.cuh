@@ -7,7 +7,7 @@
 // V*^-1 and eB (0.44 ms at Venice shape), and two pair-list kernels that gathered Y_ij AND W_ik from global memory for
 // every pair (1.06 ms) -- and ncu (profiles/ncu_r02c_*) showed what bounds them: not DRAM (40 %) and not FP64 (13 %),
 // but L1/LSU wavefronts: a lane-private 144-byte record costs nine 16-byte requests to nine wavefronts.  Here
-//   * a CTA owns one chunk of one camera (<= 256 observations, the chunks of stage 1): the chunk's W arrives as ONE TMA
+//   * a CTA owns one tile of one camera's segment (<= kSchurTile observations): the tile's W arrives as ONE TMA
 //     bulk copy, the points' (V*^-1 | eB) records (96 bytes, written by k_vinv_damp) by warp-cooperative 16-byte
 //     cp.async -- adjacent lanes fetch adjacent pieces of a record, ~1.5 wavefronts per record instead of 12;
 //   * lane t forms Y_t (kept in shared memory, and stored to HBM with one TMA bulk store for the light blocks), the
@@ -23,7 +23,14 @@
 
 namespace vlgba {
 
-constexpr int kSchurTile = 256;     // observations per chunk == threads per CTA (== kCamTile)
+// observations per tile == threads per CTA.  The tiles are this kernel's own cut of the camera segments (not the <= 256-
+// observation chunks of stage 1): 128 observations = 55 KB of shared memory and 128 x 128 registers, i.e. FOUR CTAs per
+// SM in different phases instead of two (the camera phase and the pair phase of one CTA are serial: round 2, 256-
+// observation tiles: 0.99 ms at Venice shape)
+#ifndef VLG_SCHUR_TILE
+#define VLG_SCHUR_TILE 128
+#endif
+constexpr int kSchurTile = VLG_SCHUR_TILE;
 constexpr int kSchurWarps = kSchurTile / 32;
 constexpr int kSegHeavy = 128;      // blocks with more pairs than this are processed by the chunk kernel
 constexpr int kVE = 12;             // doubles per point record: V*^-1 (9, column-major) | eB (3)
@@ -92,7 +99,7 @@ struct SchurChunkArgs {
 // W tile (later: gather buffers A) | gather buffers B (before: the points' records) | Y tile | warp sums | barrier
 constexpr size_t kSchurChunkSmem = sizeof(double) * ((size_t)3 * kSchurTile * 18 + kSchurWarps * 27) + 16;
 
-__global__ void __launch_bounds__(kSchurTile, 2)
+__global__ void __launch_bounds__(kSchurTile, 65536 / (kSchurTile * 128))
 k_schur_chunk(SchurChunkArgs p)
 {
     constexpr int NA = 6, NW = 18, NU = 27;

@@ -145,6 +145,9 @@ struct vlg_ba_ctx {
     bool schur_chunk_ok = false;
     double *VE = nullptr, *Hpart = nullptr;
     int *chunk_seg_ptr = nullptr, *sblk = nullptr, *sblk_hptr = nullptr;
+    int2* stile_meta = nullptr;       // the chunk kernel's own tiles of the camera segments: (begin, nob), nob <= kSchurTile
+    int* cam_stile_ptr = nullptr;     // [m + 1]
+    int nstiles = 0;
     int4* segs = nullptr;
     int nsblk = 0, nsegs = 0;
     double* Ybuf = nullptr;                           // Y = W V*^-1 per observation (C-order), explicit-S paths
@@ -579,7 +582,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     ctx->Wp = nullptr; ctx->ptile_meta = nullptr; ctx->s1tile_meta = nullptr;
     ctx->blk_heavy = nullptr; ctx->blk_light = nullptr; ctx->nheavy = 0; ctx->nlight = 0;
     ctx->schur_chunk_ok = false; ctx->VE = nullptr; ctx->Hpart = nullptr; ctx->chunk_seg_ptr = nullptr; ctx->sblk = nullptr;
-    ctx->sblk_hptr = nullptr; ctx->segs = nullptr; ctx->nsblk = 0; ctx->nsegs = 0;
+    ctx->sblk_hptr = nullptr; ctx->segs = nullptr; ctx->nsblk = 0; ctx->nsegs = 0; ctx->stile_meta = nullptr; ctx->cam_stile_ptr = nullptr; ctx->nstiles = 0;
     ctx->symv_tiles = nullptr; ctx->symv_tile_ptr = nullptr; ctx->symv_rowpart = nullptr; ctx->symv_colpart = nullptr;
     ctx->chol_R = nullptr; ctx->chol_Ld = nullptr; ctx->chol_Dinv = nullptr; ctx->chol_bar = nullptr;
     CU(cudaSetDevice(ctx->device));
@@ -633,7 +636,18 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     ctx->nchunks = (int)chunk_cam.size();
     {
         const char* e = getenv("VLG_BA_SCHUR_CHUNK");      // 0: the round-1 kernels (camera pass + pair lists for every block)
-        ctx->schur_chunk_ok = na == 6 && cs <= kSchurTile && o.order != VLG_BA_ORDER_REFERENCE && (e ? atoi(e) != 0 : true);
+        ctx->schur_chunk_ok = na == 6 && o.order != VLG_BA_ORDER_REFERENCE && (e ? atoi(e) != 0 : true);
+    }
+    // ... and that kernel's tiles
+    std::vector<int2> stile_meta;
+    std::vector<int> cam_stile_ptr((size_t)m + 1, 0);
+    if (ctx->schur_chunk_ok) {
+        for (int j = 0; j < m; j++) {
+            for (int64_t sb = cam_ptr[j]; sb < cam_ptr[j + 1]; sb += kSchurTile)
+                stile_meta.push_back(make_int2((int)sb, (int)std::min<int64_t>(kSchurTile, cam_ptr[j + 1] - sb)));
+            cam_stile_ptr[(size_t)j + 1] = (int)stile_meta.size();
+        }
+        ctx->nstiles = (int)stile_meta.size();
     }
 
     std::vector<unsigned char> fixed(m, 0);
@@ -807,8 +821,14 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
     CHK(dalloc(ctx, &ctx->V, (size_t)9 * n)); CHK(dalloc(ctx, &ctx->eB, (size_t)3 * n));
     CHK(dalloc(ctx, &ctx->cost_pt, (size_t)n)); CHK(dalloc(ctx, &ctx->red_part, (size_t)kRedBlocks));
     CHK(dalloc(ctx, &ctx->Ud, (size_t)na * N)); CHK(dalloc(ctx, &ctx->Vinv, (size_t)9 * n));
-    if (ctx->schur_chunk_ok) CHK(dalloc(ctx, &ctx->VE, (size_t)kVE * n));
-    CHK(dalloc(ctx, &ctx->Spart, (size_t)NU * ctx->nchunks));
+    if (ctx->schur_chunk_ok) {
+        CHK(dalloc(ctx, &ctx->VE, (size_t)kVE * n));
+        CHK(dalloc(ctx, &ctx->stile_meta, stile_meta.size())); CHK(dalloc(ctx, &ctx->cam_stile_ptr, cam_stile_ptr.size()));
+        CHK(upload(ctx, ctx->stile_meta, stile_meta.data(), stile_meta.size()));
+        CHK(upload(ctx, ctx->cam_stile_ptr, cam_stile_ptr.data(), cam_stile_ptr.size()));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    CHK(dalloc(ctx, &ctx->Spart, (size_t)NU * std::max(ctx->nchunks, ctx->nstiles)));
     CHK(dalloc(ctx, &ctx->red2, (size_t)NU * m));
     CHK(dalloc(ctx, &ctx->Sjj, (size_t)na * N)); CHK(dalloc(ctx, &ctx->ebar, N));
     CHK(dalloc(ctx, &ctx->Minv, (size_t)na * N)); CHK(dalloc(ctx, &ctx->da, N));
@@ -967,7 +987,7 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
                 if (ctx->schur_chunk_ok && np_b > seg_heavy && pairs.size() < ((size_t)1 << 31)) {
                     int cur = -1;
                     for (int64_t q = blk_ptr[bb]; q < blk_ptr[bb + 1]; q++) {
-                        const int ch = cam_chunk_ptr[j] + (pairs[(size_t)q].x - cam_ptr[j]) / cs;
+                        const int ch = cam_stile_ptr[(size_t)j] + (pairs[(size_t)q].x - cam_ptr[j]) / kSchurTile;
                         if (ch != cur) {
                             if (cur >= 0) segh.back().q1 = (int)q;
                             segh.push_back({ch, (int)bb, (int)q, (int)q, (int)segh.size()});
@@ -987,9 +1007,9 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
                 // two warps leaves one partial per warp ("piece").  Partial slots are numbered block-major, then chunk, then
                 // piece: k_schur_fold adds a block's slots in that order.
                 const int nseg = (int)segh.size();
-                std::vector<int> cptr((size_t)ctx->nchunks + 1, 0), crounds((size_t)ctx->nchunks + 1, 0);
+                std::vector<int> cptr((size_t)ctx->nstiles + 1, 0), crounds((size_t)ctx->nstiles + 1, 0);
                 for (const SegH& g : segh) { cptr[(size_t)g.chunk + 1]++; crounds[(size_t)g.chunk + 1] += (g.q1 - g.q0 + 31) / 32; }
-                for (int c = 0; c < ctx->nchunks; c++) { cptr[(size_t)c + 1] += cptr[(size_t)c]; crounds[(size_t)c + 1] += crounds[(size_t)c]; }
+                for (int c = 0; c < ctx->nstiles; c++) { cptr[(size_t)c + 1] += cptr[(size_t)c]; crounds[(size_t)c + 1] += crounds[(size_t)c]; }
                 std::vector<int> fill(cptr.begin(), cptr.end() - 1), order((size_t)nseg);
                 for (int g = 0; g < nseg; g++) order[(size_t)fill[(size_t)segh[(size_t)g].chunk]++] = g;
                 // a chunk's segments are dealt to the 8 warps of its CTA, longest first to the least loaded warp; a warp's
@@ -998,12 +1018,12 @@ int build_problem(vlg_ba_ctx* ctx, int m, int n, const double* K, const double* 
                 for (int g = 0; g < nseg; g++) slot_base[(size_t)g + 1] = slot_base[(size_t)g] + 1;
                 for (size_t t = 0; t < sblk_hptr.size(); t++) sblk_hptr[t] = slot_base[(size_t)sblk_hptr[t]];      // segment index -> slot index
                 std::vector<int4> rounds((size_t)crounds.back());
-                std::vector<int> wptr((size_t)kSchurWarps * ctx->nchunks + 1, 0);
+                std::vector<int> wptr((size_t)kSchurWarps * ctx->nstiles + 1, 0);
                 {
                     std::vector<int> segs_c, load(kSchurWarps);
                     std::vector<std::vector<int>> mine(kSchurWarps);
                     int pos = 0;
-                    for (int c = 0; c < ctx->nchunks; c++) {
+                    for (int c = 0; c < ctx->nstiles; c++) {
                         segs_c.assign(order.begin() + cptr[(size_t)c], order.begin() + cptr[(size_t)c + 1]);
                         auto nrounds = [&](int g) { return (segh[(size_t)g].q1 - segh[(size_t)g].q0 + 31) / 32; };
                         std::stable_sort(segs_c.begin(), segs_c.end(), [&](int x, int y) { return nrounds(x) > nrounds(y); });

@@ -77,13 +77,14 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
     }
     {
         TimedScope ts(ctx, T_SCHUR);
-        if (ctx->nchunks > 0 && ctx->schur_chunk_ok) {
+        const bool chunk_kernel = ctx->nstiles > 0 && ctx->schur_chunk_ok;
+        if (chunk_kernel) {
             if constexpr (NA == 6) {
                 SchurChunkArgs sa;
-                sa.chunk_meta = ctx->chunk_meta; sa.obs_pt = ctx->obs_pt; sa.W = ctx->W; sa.VE = ctx->VE; sa.part = ctx->Spart; sa.Yout = ctx->Ybuf;
+                sa.chunk_meta = ctx->stile_meta; sa.obs_pt = ctx->obs_pt; sa.W = ctx->W; sa.VE = ctx->VE; sa.part = ctx->Spart; sa.Yout = ctx->Ybuf;
                 sa.chunk_round_ptr = ctx->nsegs > 0 ? ctx->chunk_seg_ptr : nullptr; sa.rounds = ctx->segs; sa.pairs = ctx->pairs; sa.Hpart = ctx->Hpart;
                 CU(cudaFuncSetAttribute(k_schur_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurChunkSmem));
-                k_schur_chunk<<<ctx->nchunks, kSchurTile, kSchurChunkSmem, ctx->stream>>>(sa);
+                k_schur_chunk<<<ctx->nstiles, kSchurTile, kSchurChunkSmem, ctx->stream>>>(sa);
                 ctx->launches++;
             }
         } else if (ctx->nchunks > 0) {
@@ -91,7 +92,8 @@ int run_stage2(vlg_ba_ctx* ctx, double lambda)
                 ctx->nchunks, ctx->chunk_begin, ctx->chunk_end, ctx->obs_pt, ctx->W, ctx->Vinv, ctx->eB, ctx->Spart, ctx->Ybuf);
             ctx->launches++;
         }
-        k_cam_sum_partials<<<cdiv((int64_t)m * NU, 128), 128, 0, ctx->stream>>>(m, NU, ctx->cam_chunk_ptr, ctx->Spart, nullptr, ctx->red2);
+        k_cam_sum_partials<<<cdiv((int64_t)m * NU, 128), 128, 0, ctx->stream>>>(m, NU, chunk_kernel ? ctx->cam_stile_ptr : ctx->cam_chunk_ptr, ctx->Spart, nullptr,
+                                                                                 ctx->red2);
         ctx->launches++;
     }
     if (ctx->red2_local)      // this rank's own sums feed the diagonal blocks of its share of S
