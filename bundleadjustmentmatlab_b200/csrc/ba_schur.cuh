@@ -32,7 +32,7 @@ namespace vlgba {
 #endif
 constexpr int kSchurTile = VLG_SCHUR_TILE;
 constexpr int kSchurWarps = kSchurTile / 32;
-constexpr int kSegHeavy = 128;      // blocks with more pairs than this are processed by the chunk kernel
+constexpr int kSegHeavy = 256;      // blocks with more pairs than this are processed by the chunk kernel (measured 64 / 128 / 256 / 512: Schur pieces 1.34 / 1.25 / 1.21 / 1.3 ms)
 constexpr int kVE = 12;             // doubles per point record: V*^-1 (9, column-major) | eB (3)
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)

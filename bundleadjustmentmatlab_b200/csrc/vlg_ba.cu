@@ -383,14 +383,15 @@ void rodrigues_host(double w0, double w1, double w2, double* R)
     R[8] = 1.0 - mcth * (xx + yy);
 }
 
-void rtab_host(int m, int na, const double* a, int nmat, double* out)
+// matrices k0 .. nmat-1 of every camera (k = 0: base, k = 1..3: rotation component k-1 perturbed by h)
+void rtab_host(int m, int na, const double* a, int nmat, double* out, int k0 = 0)
 {
     const double h = 1e-10;
     // serial on purpose: a host thread team per rank (8 ranks x 8 spinning libgomp threads) cost 20 ms per LM step on
     // the 8-GPU box, while the table itself is ~0.1 ms at Venice shape
     for (int j = 0; j < m; j++) {
         const double* w = a + (size_t)na * j;
-        for (int k = 0; k < nmat; k++) {
+        for (int k = k0; k < nmat; k++) {
             double w0 = w[0], w1 = w[1], w2 = w[2];
             if (k == 1) w0 = w0 + h;
             if (k == 2) w1 = w1 + h;

@@ -504,12 +504,11 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
             for (int t = 0; t < N; t++) ctx->h_a_new[t] = ctx->h_a[t] + ctx->h_da[t];
             CHK(upload(ctx, ctx->a_new, ctx->h_a_new.data(), (size_t)N));
             if (NA != kNaProjective) {
-                rtab_host(m, NA, ctx->h_a_new.data(), 4, ctx->h_rtab_next.data());
-                for (int j = 0; j < m; j++)
-                    for (int q = 0; q < 9; q++) ctx->h_rtab_new[(size_t)9 * j + q] = ctx->h_rtab_next[(size_t)36 * j + q];
+                // only the candidate's BASE matrices stand between da and the new cost; the three perturbed ones per camera
+                // (three quarters of the libm work: 0.2 ms at Venice shape, serial on purpose) are computed further down,
+                // while the GPU is busy with the new cost and its reductions
+                rtab_host(m, NA, ctx->h_a_new.data(), 1, ctx->h_rtab_new.data());
                 CHK(upload(ctx, ctx->rtab_new, ctx->h_rtab_new.data(), (size_t)9 * m));
-                CHK(upload(ctx, ctx->rtab_next, ctx->h_rtab_next.data(), (size_t)36 * m));
-                ctx->rtab_next_valid = true;
             }
         }
         if (ctx->nobs > 0) {
@@ -526,6 +525,15 @@ int run_stage3(vlg_ba_ctx* ctx, double lambda, double* new_cost, double* denom)
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(ctx->h_pin, ctx->scal3, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_tab && NA != kNaProjective) {
+        // the candidate's full table (base + the three perturbed matrices per camera), so that the next stage 1 finds it
+        // ready when the step is accepted: computed now, under the kernels queued above
+        for (int j = 0; j < m; j++)
+            for (int q = 0; q < 9; q++) ctx->h_rtab_next[(size_t)36 * j + q] = ctx->h_rtab_new[(size_t)9 * j + q];
+        rtab_host(m, NA, ctx->h_a_new.data(), 4, ctx->h_rtab_next.data(), 1);
+        CHK(upload(ctx, ctx->rtab_next, ctx->h_rtab_next.data(), (size_t)36 * m));
+        ctx->rtab_next_valid = true;
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     *new_cost = ctx->h_pin[0];
     // dp = [da; db], g = [eA; eB] (bundle_euclid.m:215-217)
