@@ -24,6 +24,8 @@ CASES = {
     "euclid_fixprincipal": (5, 60, 260, 13, ("fix_principal",)),
     "euclid_fixstructure": (4, 50, 180, 14, ("fix_calibration", "fix_structure")),
     "euclid_fixpivot": (6, 70, 330, 15, ("fix_calibration", "fix_pivot", [1, 1, 0, 0, 0, 0])),
+    # structure-only BA (bundle_euclid.m:145-149): U, W, eA zeroed -> S = 0, da = pinv(0) e_ = 0, only the points move
+    "euclid_fixmotion": (5, 60, 270, 16, ("fix_calibration", "fix_motion")),
 }
 
 
