@@ -556,3 +556,18 @@ def test_reprojection_error_map_vs_error_reproj():
     assert rel(g["max_sq_err"], st["max_sq_err"]) <= 1e-10
     assert (int(pt[g["argmax"]]), int(cam[g["argmax"]])) == st["argmax"]
 
+
+
+@pytest.mark.parametrize("name", ["euclid_fixcal", "euclid_ucla4_fixcal"])
+def test_reprojection_error_map_vs_reference_built_reprojections(name):
+    """Row N4 pinned on reference-run data: the goldens' X_hat is the output of the reference's own mex1 (oracle/_ref), so
+    ||x - X_hat|| per observation is what error_reproj.m / remove_outlier would see; vlg_ba_reproj_errors must give it."""
+    g = load_golden(name)
+    ctx = ctx_from_golden(g)
+    out = ctx.reproj_errors(depth_max=1e9)
+    ctx.close()
+    ref = np.sqrt(((g["obs_xy"] - g["X_hat"]) ** 2).sum(axis=1))
+    assert np.abs(out["err"] - ref).max() <= 1e-12 * max(ref.max(), 1.0)
+    assert rel(out["mean_err"], ref.mean()) <= 1e-12
+    ok = out["depth"] >= 0
+    assert rel(out["max_sq_err"], float((ref[ok] ** 2).max())) <= 1e-12 and out["argmax"] == int(np.argmax(np.where(ok, ref, -1.0) ** 2 * np.where(ok, 1, -1)))

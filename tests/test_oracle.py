@@ -128,3 +128,20 @@ def test_cpu_port_pcg_step_matches_exact_solve():
     assert abs(p["old"] - t["old"]) <= 1e-12 * t["old"]
     assert abs(p["new"] - t["new"]) <= 1e-9 * t["new"]
     assert abs(p["denom"] - t["denom"]) <= 1e-8 * abs(t["denom"])
+
+
+@pytest.mark.parametrize("name", ["euclid_fixcal", "euclid_ucla4_fixcal"])
+def test_error_reproj_restatement_pinned_by_reference_reprojections(name):
+    """error_reproj.m is MATLAB (not runnable here); its restatement (oracle/lm.py) multiplies
+    P_j = K_j [R_j T_j] out before projecting, the reference's C (reproject_point.h) does not.  Pin the restatement on the
+    reprojections the REFERENCE BUILD produced: the goldens' X_hat is mex1's output (oracle/_ref), so
+    ||x - X_hat|| per visible cell is reference-run data; the restated error map must agree to rounding."""
+    g = load_golden(name)
+    a = g["t_a"][0]
+    n, m = int(g["n"]), int(g["m"])
+    X4 = np.vstack([g["t_b"][0], np.ones((1, n))])
+    vis = g["visible"].copy(); vis[n - 1, m - 1] = 1.0           # error_reproj.m:76 tests the LAST cell only
+    err, emap = lm.error_reproj(g["x"], g["K"], a[3:6], a[0:3], X4, vis)
+    pt, cam = g["obs_pt"], g["obs_cam"]
+    ref = np.sqrt(((g["obs_xy"] - g["X_hat"]) ** 2).sum(axis=1))
+    assert np.abs(emap[pt, cam] - ref).max() <= 1e-10 * max(ref.max(), 1.0)

@@ -73,3 +73,38 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def projective():
+    """The same question for the projective model (row N3: full-problem teacher-forced cost 4.8e-7 from the oracle): the
+    15-dimensional projective gauge leaves S with 15 eigenvalues ~ lambda * diag(U), cond(S) ~ 1 / lambda larger."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import proj_golden_names
+    for name in proj_golden_names():
+        g = load_golden(name)
+        fs = "fix_structure" in g["options"]
+        a, b, lam = g["t_a"][0], g["t_b"][0], float(g["t_lam"][0])
+        X = np.asfortranarray(g["x"][:2]); vis = np.asfortranarray(g["visible"])
+        t = lm.lm_trial_proj(a, b, X, vis, lam, fix_structure=fs)
+        S, e_ = t["blocks"]["S"], t["blocks"]["e_"]
+        sv = np.linalg.svd(S, compute_uv=False)
+        nz = sv[sv > sv[0] * 1e-300]
+        x_ch, keep = chol_elim(S, e_)
+        x_lu = np.zeros_like(e_); x_lu[keep] = np.linalg.solve(S[np.ix_(keep, keep)], e_[keep])
+        x_ref = refine(S, e_, x_ch, keep)
+        W, eB, Vinv = t["blocks"]["W_dense"], np.asfortranarray(t["blocks"]["eB"].T), np.asfortranarray(np.transpose(t["blocks"]["Vinv"], (2, 1, 0)))
+
+        def cost(da):
+            _, _, _, X_hat_new = lm.stage3_ref_proj(W, da, eB, Vinv, a, b, X, vis)
+            en = X - X_hat_new
+            return float(np.dot(en.reshape(-1, order="F"), en.reshape(-1, order="F")))
+        c_ref = cost(x_ref)
+        rel = lambda x: np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref)
+        crel = lambda x: abs(cost(x) - c_ref) / c_ref
+        print(f"{name}: cond(S) over the non-zero part {nz[0] / nz[-1]:.2e} ({S.shape[0] - len(keep)} zero rows), lambda {lam:g}")
+        print(f"   |da - da_ref| / |da_ref|:  SVD pinv (oracle) {rel(t['da']):.1e}   LU {rel(x_lu):.1e}   Cholesky+elimination (GPU's method) {rel(x_ch):.1e}")
+        print(f"   one-step cost vs the refined solve:  SVD pinv {crel(t['da']):.1e}   LU {crel(x_lu):.1e}   Cholesky {crel(x_ch):.1e}")
+
+
+if __name__ == "__main__":
+    projective()
