@@ -130,6 +130,23 @@ def test_cpu_port_pcg_step_matches_exact_solve():
     assert abs(p["denom"] - t["denom"]) <= 1e-8 * abs(t["denom"])
 
 
+@pytest.mark.parametrize("config", ["ladybug", "trafalgar"])
+def test_cpu_port_pcg_step_pinned_on_the_baseline_shapes(config):
+    """BASELINE configs 2 and 3 fit the pinv oracle (the restated bundle_euclid.m:193 on the dense S); the PCG port is the
+    only oracle that can run config 4 (Venice shape: tests/test_baseline_configs.py, bench.py's `parity`), so it is pinned
+    here, at full C2 / C3 size, against the pinv trial step: same old cost, new cost to 1e-11, same accept decision."""
+    P = synth.make_config(config, seed=0)
+    a = np.vstack([P.w, P.Te]); b = P.Xe[:3].copy()
+    obs = lm.ObsList(P.m, P.n, P.obs_xy, P.obs_pt, P.obs_cam)
+    o = lm.parse_options(P.m, P.n, np.ones((2, 1, 1)), ["fix_calibration", "visibility", np.zeros(0)])
+    t = lm.lm_trial(P.K, a, b, obs, 1e-3, o, backend="sparse")
+    p = lm.trial_step_pcg(P.K, a, b, obs, 1e-3, pcg_rtol=1e-12, pcg_max_iter=2000)
+    assert abs(p["old"] - t["old"]) <= 1e-13 * t["old"]
+    assert abs(p["new"] - t["new"]) <= 1e-11 * t["new"]
+    assert (p["old"] - p["new"] > 0) == (t["old"] - t["new"] > 0)
+    assert np.abs(p["a_new"] - t["a_new"]).max() <= 1e-8 * max(np.abs(t["a_new"]).max(), 1.0)
+
+
 @pytest.mark.parametrize("name", ["euclid_fixcal", "euclid_ucla4_fixcal"])
 def test_error_reproj_restatement_pinned_by_reference_reprojections(name):
     """error_reproj.m is MATLAB (not runnable here); its restatement (oracle/lm.py) multiplies
